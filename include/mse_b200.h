@@ -1,0 +1,117 @@
+/*
+ * mse_b200.h -- C ABI of libmse_b200.so: the B200-native embed-and-search hot path of
+ * osmarks/meme-search-engine.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * repository root).  Host code in the reference is Rust; INTEGRATION.md shows the `extern "C"`
+ * block + safe wrappers a maintainer would add.
+ *
+ * Conventions
+ *   - return 0 on success, a negative MSE_ERR_* otherwise; mse_last_error() gives a thread-local message
+ *   - the caller owns every buffer it passes; the library owns what is behind its opaque handles
+ *   - one in-flight call per handle (the reference has one inference thread / one &mut Scratch per thread);
+ *     handles on different devices are independent
+ *   - fixed-point scores are i64 = trunc(f32 * 2^32) exactly as diskann/src/vector.rs:46,249-250,408-416
+ *   - "_dev" variants take device pointers and a cudaStream_t (as void*) and do not synchronise
+ *   - there is NO CPU fallback: every compute entry fails with MSE_ERR_CUDA when no sm_100 device is usable
+ */
+#ifndef MSE_B200_H
+#define MSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSE_OK 0
+#define MSE_ERR_INVALID (-1)     /* bad argument */
+#define MSE_ERR_CUDA (-2)        /* CUDA runtime/driver failure, or no usable device */
+#define MSE_ERR_OOM (-3)         /* device or host allocation failed */
+#define MSE_ERR_UNSUPPORTED (-4) /* shape outside what the kernels were built for */
+#define MSE_ERR_STATE (-5)       /* handle is missing something the call needs (graph, codes, ...) */
+
+#define MSE_ID_NONE 0xFFFFFFFFu /* padding id when k > ntotal (FAISS returns -1: src/main.rs:908) */
+
+const char *mse_last_error(void);
+/* library / device facts: writes up to cap bytes of a JSON object (sm count, device name, kernels built) */
+int mse_device_info(int device, char *json_out, size_t cap);
+/* number of kernel launches this library has issued in this process (bench.py's gpu_launches) */
+uint64_t mse_launch_count(void);
+
+/* =====================================================================================
+ * Distance kernel -- diskann/src/vector.rs:192-306 (fast_dot / fast_dot_noprefetch)
+ * ===================================================================================== */
+
+/* scores[i] = fast_dot(query, rows[row_ids[i]]) bit-identically to the reference's AVX2 routine
+ * (32 partial sums in fp32 FMA, its reduction tree, trunc(x*2^32)).  d % 64 == 0.  Host pointers.
+ * row_ids == NULL means rows 0..n_ids-1. */
+int mse_fast_dot_batch(int device, const uint16_t *query_f16, const uint16_t *rows_f16, uint64_t n_rows, uint32_t d,
+                       const uint32_t *row_ids, uint64_t n_ids, int64_t *scores);
+
+/* =====================================================================================
+ * Index handle -- VectorList (diskann/src/vector.rs:118-186) + IndexGraph (diskann/src/lib.rs:16-39)
+ *                 + FAISS IndexScalarQuantizer(QT_fp16, InnerProduct) (src/main.rs:822)
+ * One handle = one id-range shard resident in one GPU's HBM.
+ * ===================================================================================== */
+
+typedef struct mse_index mse_index;
+
+/* VectorList::from_f16s / ScalarQuantizerIndexImpl::new.  x_f16 may be NULL with n == 0 (empty index).
+ * id_base is added to every returned id (the shard's first global vector id). */
+int mse_index_create(const uint16_t *x_f16, uint64_t n, uint32_t d, int device, uint32_t id_base, mse_index **out);
+/* faiss Index::add(&[f32]) (src/main.rs:858,892): rows are rounded to fp16 (RNE) as QT_fp16 stores them */
+int mse_index_add(mse_index *ix, const float *x_f32, uint64_t n);
+/* VectorList::push for already-fp16 rows */
+int mse_index_add_f16(mse_index *ix, const uint16_t *x_f16, uint64_t n);
+/* same, source rows already in device memory */
+int mse_index_add_f16_dev(mse_index *ix, const uint16_t *d_x_f16, uint64_t n, void *stream);
+/* Vec::with_capacity for the row store (generate_index_shard.rs:52-53 pre-sizes with -N): no reallocation below `rows` */
+int mse_index_reserve(mse_index *ix, uint64_t rows);
+/* faiss Index::ntotal (src/main.rs:1015,1053) / VectorList::len */
+uint64_t mse_index_ntotal(const mse_index *ix);
+uint32_t mse_index_dim(const mse_index *ix);
+int mse_index_device(const mse_index *ix);
+/* device address of the fp16 rows (for zero-copy interop with the caller's own CUDA code) */
+const uint16_t *mse_index_vectors_dev(const mse_index *ix);
+void mse_index_destroy(mse_index *ix);
+
+/* =====================================================================================
+ * Flat search -- faiss Index::search on IndexScalarQuantizer(QT_fp16, IP)  (src/main.rs:900; mse.py:79)
+ * score_i = sum_d q_d * f32(x_id)  ranked by (score desc, id asc); q stays f32 (never rounded to fp16).
+ * ids/scores are [nq][k]; slots past ntotal hold MSE_ID_NONE / -inf.
+ * Results are exact: candidates found by the tensor-core pass are re-scored in fp64 and the cut is
+ * certified against the rounding bound of the fp16 pass; uncertified queries are re-run on the exact scan.
+ * ===================================================================================== */
+int mse_search_flat(mse_index *ix, const float *q, uint32_t nq, uint32_t k, uint32_t *ids, float *scores);
+int mse_search_flat_dev(mse_index *ix, const float *d_q, uint32_t nq, uint32_t k, uint32_t *d_ids, float *d_scores,
+                        void *stream);
+/* statistics of the last mse_search_flat* call on this handle:
+ * out[0]=tensor-path queries, out[1]=exact-scan queries, out[2]=queries escalated after a failed certificate,
+ * out[3]=candidate-buffer overflows, out[4]=kernel launches, out[5]=chunks,
+ * out[6]=nanoseconds spent inside the scoring kernels (CUDA events; only with profiling on), out[7]=scoring launches */
+int mse_search_flat_stats(const mse_index *ix, uint64_t out[8]);
+/* bracket every scoring-kernel launch with CUDA events on the launching stream (feeds out[6], out[7]) */
+int mse_search_flat_profile(mse_index *ix, int enable);
+/* force a path for testing: 0 = auto, 1 = exact fp64 scan only, 2 = tensor-core pass (+ certified rerank) only */
+int mse_search_flat_set_mode(mse_index *ix, int mode);
+
+/* k-way merge of per-shard top-k lists (the step after the all-gather of SURVEY 8e): lists are
+ * [n_shards][nq][k] (ids, scores), output [nq][k] by (score desc, id asc). Device pointers. */
+int mse_merge_topk_dev(int device, const uint32_t *d_ids, const float *d_scores, uint32_t n_shards, uint32_t nq,
+                       uint32_t k, uint32_t *d_out_ids, float *d_out_scores, void *stream);
+
+/* =====================================================================================
+ * Dense GEMM building block (tcgen05 + TMA): C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]), fp16 in, fp32 accumulate
+ * and output.  act: 0 none, 1 erf-GELU, 2 tanh-GELU.  This is the contraction behind every linear layer of the
+ * towers and the OPQ rotation (diskann/src/vector.rs:320-329, matrixmultiply::sgemm); exposed with host
+ * pointers so the tensor path can be validated on its own.  K % 8 == 0.
+ * ===================================================================================== */
+int mse_gemm_f16_tn(int device, const uint16_t *a_f16, const uint16_t *b_f16, uint32_t M, uint32_t N, uint32_t K,
+                    const float *bias, int act, float *c_f32);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSE_B200_H */

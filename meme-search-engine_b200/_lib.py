@@ -1,0 +1,97 @@
+"""ctypes binding of libmse_b200.so (the declarations mirror include/mse_b200.h one to one)."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class MseError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libmse_b200.so")
+
+
+def build(verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into libmse_b200.so (in-tree)."""
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j", str(os.cpu_count() or 4)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout)
+    if r.returncode != 0:
+        raise MseError("building libmse_b200.so failed")
+    return lib_path()
+
+
+def header_symbols() -> list[str]:
+    """Every function include/mse_b200.h declares."""
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "mse_b200.h")
+    txt = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(mse_[a-z0-9_]+)\s*\(", txt)))
+
+
+_vp, _u64, _u32, _i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+_SIGS = {
+    "mse_last_error": (C.c_char_p, []),
+    "mse_device_info": (_i32, [_i32, C.c_char_p, C.c_size_t]),
+    "mse_launch_count": (_u64, []),
+    "mse_fast_dot_batch": (_i32, [_i32, _vp, _vp, _u64, _u32, _vp, _u64, _vp]),
+    "mse_index_create": (_i32, [_vp, _u64, _u32, _i32, _u32, C.POINTER(_vp)]),
+    "mse_index_add": (_i32, [_vp, _vp, _u64]),
+    "mse_index_add_f16": (_i32, [_vp, _vp, _u64]),
+    "mse_index_add_f16_dev": (_i32, [_vp, _vp, _u64, _vp]),
+    "mse_index_reserve": (_i32, [_vp, _u64]),
+    "mse_index_ntotal": (_u64, [_vp]),
+    "mse_index_dim": (_u32, [_vp]),
+    "mse_index_device": (_i32, [_vp]),
+    "mse_index_vectors_dev": (_vp, [_vp]),
+    "mse_index_destroy": (None, [_vp]),
+    "mse_search_flat": (_i32, [_vp, _vp, _u32, _u32, _vp, _vp]),
+    "mse_search_flat_dev": (_i32, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
+    "mse_search_flat_stats": (_i32, [_vp, _vp]),
+    "mse_search_flat_set_mode": (_i32, [_vp, _i32]),
+    "mse_search_flat_profile": (_i32, [_vp, _i32]),
+    "mse_merge_topk_dev": (_i32, [_i32, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "mse_gemm_f16_tn": (_i32, [_i32, _vp, _vp, _u32, _u32, _u32, _vp, _i32, _vp]),
+}
+
+
+def lib():
+    """Load the CUDA library.  Fails loudly when it has not been built -- there is no other implementation."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise MseError(f"{path} is missing: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
+        l = C.CDLL(path)
+        for name, (res, args) in _SIGS.items():
+            f = getattr(l, name)
+            f.restype, f.argtypes = res, args
+        _LIB = l
+    return _LIB
+
+
+def last_error() -> str:
+    return (lib().mse_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise MseError(f"{what or 'mse call'} failed ({rc}): {last_error()}")
+
+
+def launch_count() -> int:
+    return int(lib().mse_launch_count())
+
+
+def device_info(device: int = 0) -> dict:
+    buf = C.create_string_buffer(1024)
+    check(lib().mse_device_info(device, buf, 1024), "mse_device_info")
+    return json.loads(buf.value.decode())

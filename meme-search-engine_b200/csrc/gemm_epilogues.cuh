@@ -1,0 +1,112 @@
+// Epilogues for linear layers on the tcgen05 mainloop: each epilogue thread owns one output row and
+// receives 32 consecutive fp32 columns at a time.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace mse {
+
+enum { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_GELU_TANH = 2 };
+
+struct GemmOut {
+    float *c32;            // fp32 output [M][ldc] or NULL
+    __half *c16;           // fp16 output [M][ldc] or NULL
+    uint32_t ldc;
+    const float *bias;     // [N] fp32 or NULL
+    const __half *res;     // residual [res_rows][ldc] fp16 added after activation, or NULL
+    uint32_t res_mod;      // residual row = row % res_mod (position embeddings); 0 = row
+    int act;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_tanh(float x) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    return 0.5f * x * (1.0f + tanhf(k0 * (x + k1 * x * x * x)));
+}
+
+struct LinearEpilogue {
+    GemmOut o;
+    uint32_t M, N;
+    __device__ __forceinline__ void begin_tile(uint32_t, uint32_t) {}
+    __device__ __forceinline__ void columns(uint32_t row, uint32_t col0, const uint32_t (&v)[32]) {
+        if (row >= M || col0 >= N) return;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+        const bool full = col0 + 32 <= N;
+        if (o.bias) {
+            if (full) {
+                const float4 *b4 = (const float4 *)(o.bias + col0);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    float4 b = __ldg(b4 + j);
+                    f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (col0 + j < N) f[j] += o.bias[col0 + j];
+            }
+        }
+        if (o.act == ACT_GELU_ERF) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) f[j] = gelu_erf(f[j]);
+        } else if (o.act == ACT_GELU_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) f[j] = gelu_tanh(f[j]);
+        }
+        if (o.res) {
+            const uint32_t rr = o.res_mod ? row % o.res_mod : row;
+            const __half *rp = o.res + (size_t)rr * o.ldc + col0;
+            if (full) {
+                const uint4 *r4 = (const uint4 *)rp;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint4 u = __ldg(r4 + j);
+                    const __half2 *h = (const __half2 *)&u;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        float2 t = __half22float2(h[e]);
+                        f[8 * j + 2 * e] += t.x;
+                        f[8 * j + 2 * e + 1] += t.y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (col0 + j < N) f[j] += __half2float(rp[j]);
+            }
+        }
+        if (o.c16) {
+            __half *cp = o.c16 + (size_t)row * o.ldc + col0;
+            if (full) {
+                uint4 *c4 = (uint4 *)cp;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint4 u;
+                    __half2 *h = (__half2 *)&u;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) h[e] = __floats2half2_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
+                    c4[j] = u;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (col0 + j < N) cp[j] = __float2half_rn(f[j]);
+            }
+        }
+        if (o.c32) {
+            float *cp = o.c32 + (size_t)row * o.ldc + col0;
+            if (full) {
+                float4 *c4 = (float4 *)cp;
+#pragma unroll
+                for (int j = 0; j < 8; j++) c4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (col0 + j < N) cp[j] = f[j];
+            }
+        }
+    }
+};
+
+int gemm_f16_tn_dev(int device, const __half *dA, const __half *dB, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb,
+                    const GemmOut &out, cudaStream_t st);
+
+}  // namespace mse

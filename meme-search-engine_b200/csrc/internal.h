@@ -1,0 +1,55 @@
+// Internal structures shared by the translation units of libmse_b200.so.
+#pragma once
+#include "common.cuh"
+
+namespace mse {
+
+// Flat-search workspace, sized per (nq, kp); lives in the index handle so steady-state searches allocate nothing.
+struct FlatWork {
+    DevBuf q;         // f32 [nq][d]        (host API only: staged queries)
+    DevBuf q16;       // f16 [nq_pad][d]    tensor path A operand (rows >= nq are zero)
+    DevBuf qstat;     // f32 [nq][4]        {|q|, |q - f16(q)|, eps, unused}
+    DevBuf top;       // u64 [nq][kp]       running top list (rank keys, best first)
+    DevBuf ntop;      // u32 [nq]
+    DevBuf thr;       // f32 [nq]           score of the kp-th best so far, or -inf
+    DevBuf cand;      // u64 [nq][cap]      candidates that passed the threshold in the current chunk
+    DevBuf count;     // u32 [nq]
+    DevBuf flags;     // u32 [4 + nq]       [0]=overflow seen, [1]=#uncertified, [4+q]=per-query status bits
+    DevBuf out_ids;   // u32 [nq][k]        (host API only)
+    DevBuf out_sc;    // f32 [nq][k]
+    DevBuf sel;       // u32 [nq]           query subset for the exact re-run
+    DevBuf tmp_ids;   // u32 [nq][k]        exact re-run results
+    DevBuf tmp_sc;    // f32 [nq][k]
+    void release() {
+        q.release(); q16.release(); qstat.release(); top.release(); ntop.release(); thr.release(); cand.release();
+        count.release(); flags.release(); out_ids.release(); out_sc.release(); sel.release(); tmp_ids.release(); tmp_sc.release();
+    }
+};
+
+}  // namespace mse
+
+struct mse_index {
+    int device = 0;
+    uint32_t d = 0;
+    uint32_t id_base = 0;
+    uint64_t n = 0;      // rows held
+    uint64_t cap = 0;    // rows allocated
+    __half *x = nullptr; // [cap][d] fp16 rows in HBM
+    float *max_norm = nullptr;  // device scalar: max_i |x_i|_2 (upper bound; feeds the certificate)
+    int flat_mode = 0;
+    int profile = 0;                 // time the scoring kernels with CUDA events (bench.py roofline)
+    std::vector<cudaEvent_t> prof_ev; // start/stop pairs, reused
+    size_t prof_used = 0;
+    uint64_t stats[8] = {0};
+    mse::FlatWork fw;
+    cudaStream_t stream = nullptr;  // handle-owned stream for the host-pointer API
+    // tensor-map cache for the tensor path (encoded lazily, invalidated on growth)
+    bool tmap_valid = false;
+    alignas(64) unsigned char tmap_x[128];
+};
+
+namespace mse {
+// flat_tc.cu: tensor-core scoring pass over rows [row0, row0+nrows) for queries [0,nq) (q16 padded to 128 rows)
+int flat_tc_score_chunk(mse_index *ix, uint32_t nq, uint64_t row0, uint64_t nrows, uint32_t cap, cudaStream_t st);
+int flat_tc_supported(const mse_index *ix);
+}  // namespace mse
