@@ -33,9 +33,10 @@ struct LinearEpilogue {
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
-        const bool full = col0 + 32 <= N;
+        const bool fullc = col0 + 32 <= N;          // all 32 columns in range
+        const bool full = fullc && (o.ldc % 8 == 0);  // ... and 16-byte vector access to C / residual rows is aligned
         if (o.bias) {
-            if (full) {
+            if (fullc) {
                 const float4 *b4 = (const float4 *)(o.bias + col0);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
