@@ -103,6 +103,33 @@ int mse_merge_topk_dev(int device, const uint32_t *d_ids, const float *d_scores,
                        uint32_t k, uint32_t *d_out_ids, float *d_out_scores, void *stream);
 
 /* =====================================================================================
+ * Embedding towers -- clip_server.py (OpenCLIP ViT-SO400M-14-SigLIP-384, precision fp16)
+ *   model creation            clip_server.py:23      -> mse_encoder_create
+ *   preprocess + encode_image clip_server.py:140,114 -> mse_encode_images_u8   (u8 RGB HWC in, x/127.5-1 on device)
+ *   tokenizer + encode_text   clip_server.py:137,98  -> mse_encode_text_ids    (token ids in; SentencePiece stays host-side)
+ *   features /= norm; fp16    clip_server.py:99,115,166 -> fused; outputs are unit-norm fp16 rows [batch][dim]
+ *   batch > max_batch_size    clip_server.py:136,139 -> MSE_ERR_INVALID with the same message
+ * Weights: an "MSEW0001" container holding the OpenCLIP/timm state_dict tensors under their own names
+ * (visual.trunk.blocks.N.attn.qkv.weight, text.transformer.resblocks.N.attn.in_proj_weight, ... as
+ * clip_server.py:46-62 lists them) plus an i32 "config" tensor; written by meme-search-engine_b200/weights.py.
+ * One in-flight call per handle (the reference has a single inference thread, clip_server.py:126-128).
+ * ===================================================================================== */
+typedef struct mse_encoder mse_encoder;
+
+int mse_encoder_create(const char *weights_path, int device, int max_batch, mse_encoder **out);
+/* out[0..12] = image_size, patch, dim, vision depth, heads, mlp dim, vocab, context length, activation (1 erf-GELU,
+ * 2 tanh-GELU), has_vision, has_text, text depth, padded patch K   (feeds GET /config: clip_server.py:176-183) */
+int mse_encoder_config(const mse_encoder *e, int32_t out[16]);
+int mse_encode_images_u8(mse_encoder *e, const uint8_t *rgb_hwc, int batch, uint16_t *out_f16);
+int mse_encode_images_u8_dev(mse_encoder *e, const uint8_t *d_rgb_hwc, int batch, uint16_t *d_out_f16, void *stream);
+int mse_encode_text_ids(mse_encoder *e, const int32_t *ids, int batch, uint16_t *out_f16);
+int mse_encode_text_ids_dev(mse_encoder *e, const int32_t *d_ids, int batch, uint16_t *d_out_f16, void *stream);
+/* per-layer parity hooks: token activations [batch*S][dim] fp16 after the embedding and the first n_blocks blocks */
+int mse_encode_images_hidden(mse_encoder *e, const uint8_t *rgb_hwc, int batch, int n_blocks, uint16_t *out_tokens_f16);
+int mse_encode_text_hidden(mse_encoder *e, const int32_t *ids, int batch, int n_blocks, uint16_t *out_tokens_f16);
+void mse_encoder_destroy(mse_encoder *e);
+
+/* =====================================================================================
  * Dense GEMM building block (tcgen05 + TMA): C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]), fp16 in, fp32 accumulate
  * and output.  act: 0 none, 1 erf-GELU, 2 tanh-GELU.  This is the contraction behind every linear layer of the
  * towers and the OPQ rotation (diskann/src/vector.rs:320-329, matrixmultiply::sgemm); exposed with host

@@ -59,6 +59,15 @@ _SIGS = {
     "mse_search_flat_set_mode": (_i32, [_vp, _i32]),
     "mse_search_flat_profile": (_i32, [_vp, _i32]),
     "mse_merge_topk_dev": (_i32, [_i32, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "mse_encoder_create": (_i32, [C.c_char_p, _i32, _i32, C.POINTER(_vp)]),
+    "mse_encoder_config": (_i32, [_vp, _vp]),
+    "mse_encode_images_u8": (_i32, [_vp, _vp, _i32, _vp]),
+    "mse_encode_images_u8_dev": (_i32, [_vp, _vp, _i32, _vp, _vp]),
+    "mse_encode_text_ids": (_i32, [_vp, _vp, _i32, _vp]),
+    "mse_encode_text_ids_dev": (_i32, [_vp, _vp, _i32, _vp, _vp]),
+    "mse_encode_images_hidden": (_i32, [_vp, _vp, _i32, _i32, _vp]),
+    "mse_encode_text_hidden": (_i32, [_vp, _vp, _i32, _i32, _vp]),
+    "mse_encoder_destroy": (None, [_vp]),
     "mse_gemm_f16_tn": (_i32, [_i32, _vp, _vp, _u32, _u32, _u32, _vp, _i32, _vp]),
 }
 

@@ -1,0 +1,625 @@
+// SigLIP ViT-SO400M-14/384 image and text towers behind the clip_server boundary.
+//
+// Reference: clip_server.py:23 (OpenCLIP `ViT-SO400M-14-SigLIP-384`, precision fp16), :98 encode_text, :114 encode_image,
+// :99/:115 L2 normalisation, :140 preprocessing; the layer graph is the one the author restates in
+// aitemplate/model.py:13-122 (pre-LN blocks, erf-GELU MLP, learned position embedding, final LN, MAP head with one
+// probe) with weight names as clip_server.py:46-62 maps them.  Text tower: OpenCLIP TextTransformer (token + position
+// embedding, 27 non-causal blocks, final LN, LAST token, Linear 1152->1152 with bias).
+//
+// Every dense contraction runs on the tcgen05 GEMM (gemm_sm100.cuh) with bias / GELU / residual / position-embedding
+// fused into its epilogue; LayerNorm, the im2col + u8 normalisation, attention (attention.cuh), the MAP pooling
+// attention and the final L2 normalisation are the hand-written kernels in this file.  Activations are token-major
+// fp16 [B*S][D] in HBM; statistics, softmax and accumulation are fp32.
+#include "internal.h"
+#include "gemm_epilogues.cuh"
+#include "attention.cuh"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <algorithm>
+#include <map>
+#include <string>
+
+namespace mse {
+
+// ------------------------------------------------------------------ kernels
+
+// u8 HWC image -> im2col rows for the 14x14/14 VALID patch conv: A[b*P*P + py*P + px][c*196 + ky*14 + kx] =
+// x/127.5 - 1 (torchvision ToTensor + Normalize(0.5, 0.5), clip_server.py:140), K padded 588 -> kpad with zeros.
+__global__ void __launch_bounds__(256) k_im2col_patch14(const uint8_t *__restrict__ img, __half *__restrict__ A, int B, int img_size,
+                                                        int grid_p, int kpad) {
+    const int patch = blockIdx.x;  // b*P*P + py*P + px
+    const int b = patch / (grid_p * grid_p), pp = patch % (grid_p * grid_p), py = pp / grid_p, px = pp % grid_p;
+    const uint8_t *src = img + (size_t)b * img_size * img_size * 3;
+    __half *dst = A + (size_t)patch * kpad;
+    for (int i = threadIdx.x; i < kpad; i += blockDim.x) {
+        float v = 0.f;
+        if (i < 588) {
+            // iterate in source order (ky, kx, c) for coalesced reads; scatter into (c, ky, kx)
+            int ky = i / 42, r = i % 42, kx = r / 3, c = r % 3;
+            uint8_t u = src[((size_t)(py * 14 + ky) * img_size + (px * 14 + kx)) * 3 + c];
+            v = (float)u * (1.0f / 127.5f) - 1.0f;
+            dst[c * 196 + ky * 14 + kx] = __float2half_rn(v);
+        } else {
+            dst[i] = __float2half_rn(0.f);
+        }
+    }
+}
+
+// LayerNorm over the last dim (D % 8 == 0, D <= 2048), fp32 statistics, one warp per row
+__global__ void __launch_bounds__(256) k_layernorm(const __half *__restrict__ x, __half *__restrict__ y, const float *__restrict__ g,
+                                                   const float *__restrict__ bta, uint32_t rows, uint32_t D, float eps,
+                                                   uint32_t in_stride, uint32_t in_offset) {
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const uint4 *xr = (const uint4 *)(x + (size_t)row * in_stride + in_offset);
+    const uint32_t nv = D >> 3;
+    float v[8][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t p = lane + 32 * i;
+        if (p < nv) {
+            uint4 u = xr[p];
+            const __half2 *h = (const __half2 *)&u;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float2 f = __half22float2(h[e]);
+                v[i][2 * e] = f.x; v[i][2 * e + 1] = f.y;
+                s += f.x + f.y;
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t p = lane + 32 * i;
+        if (p < nv) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) { float d = v[i][e] - mean; q = fmaf(d, d, q); }
+        }
+    }
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)D + eps);
+    uint4 *yr = (uint4 *)(y + (size_t)row * D);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t p = lane + 32 * i;
+        if (p < nv) {
+            const float4 g0 = __ldg((const float4 *)(g + p * 8)), g1 = __ldg((const float4 *)(g + p * 8 + 4));
+            const float4 b0 = __ldg((const float4 *)(bta + p * 8)), b1 = __ldg((const float4 *)(bta + p * 8 + 4));
+            uint4 u;
+            __half2 *h = (__half2 *)&u;
+            h[0] = __floats2half2_rn((v[i][0] - mean) * rstd * g0.x + b0.x, (v[i][1] - mean) * rstd * g0.y + b0.y);
+            h[1] = __floats2half2_rn((v[i][2] - mean) * rstd * g0.z + b0.z, (v[i][3] - mean) * rstd * g0.w + b0.w);
+            h[2] = __floats2half2_rn((v[i][4] - mean) * rstd * g1.x + b1.x, (v[i][5] - mean) * rstd * g1.y + b1.y);
+            h[3] = __floats2half2_rn((v[i][6] - mean) * rstd * g1.z + b1.z, (v[i][7] - mean) * rstd * g1.w + b1.w);
+            yr[p] = u;
+        }
+    }
+}
+
+// MAP head pooling (aitemplate/model.py:98-111): one learned probe query per head against all S tokens.
+// kv: [B*S][2*D] (k | v).  qp: [D] fp32 = Wq*probe + bq, precomputed at load.  out: [B][D] fp16.  grid (H, B), 128 threads
+__global__ void __launch_bounds__(128) k_map_pool(const __half *__restrict__ kv, const float *__restrict__ qp, __half *__restrict__ out,
+                                                  int S, int H, float scale) {
+    extern __shared__ float s_sc[];  // S scores + 72 query values + scratch
+    float *s_q = s_sc + S;
+    __shared__ float s_red[4];
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, D = H * attn::kDH;
+    const __half *kb = kv + (size_t)b * S * 2 * D + (size_t)h * attn::kDH;
+    const __half *vb = kb + D;
+    if (tid < attn::kDH) s_q[tid] = qp[h * attn::kDH + tid] * scale;
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int t = tid; t < S; t += blockDim.x) {
+        const uint4 *kr = (const uint4 *)(kb + (size_t)t * 2 * D);
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+            uint4 u = __ldg(kr + c);
+            const __half2 *hh = (const __half2 *)&u;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float2 f = __half22float2(hh[e]);
+                a = fmaf(f.x, s_q[c * 8 + 2 * e], a);
+                a = fmaf(f.y, s_q[c * 8 + 2 * e + 1], a);
+            }
+        }
+        s_sc[t] = a;
+        mx = fmaxf(mx, a);
+    }
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int t = tid; t < S; t += blockDim.x) {
+        float p = __expf(s_sc[t] - mx);
+        s_sc[t] = p;
+        sum += p;
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = sum;
+    __syncthreads();
+    sum = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+    if (tid < attn::kDH) {
+        float acc = 0.f;
+        for (int t = 0; t < S; t++) acc = fmaf(s_sc[t], __half2float(vb[(size_t)t * 2 * D + tid]), acc);
+        out[(size_t)b * D + h * attn::kDH + tid] = __float2half_rn(acc / sum);
+    }
+}
+
+// out[b] = x[b] / |x[b]|_2 as fp16 (clip_server.py:99,115,166); one warp per row
+__global__ void __launch_bounds__(256) k_l2norm_f16(const __half *__restrict__ x, __half *__restrict__ out, uint32_t rows, uint32_t D) {
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float s = 0.f;
+    for (uint32_t j = lane; j < D; j += 32) {
+        float v = __half2float(x[(size_t)row * D + j]);
+        s = fmaf(v, v, s);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv = rsqrtf(s);
+    for (uint32_t j = lane; j < D; j += 32) out[(size_t)row * D + j] = __float2half_rn(__half2float(x[(size_t)row * D + j]) * inv);
+}
+
+// text embedding: x[b*S + t] = tok_emb[ids[b*S + t]] + pos_emb[t]
+__global__ void __launch_bounds__(256) k_text_embed(const int32_t *__restrict__ ids, const __half *__restrict__ tok, const __half *__restrict__ pos,
+                                                    __half *__restrict__ x, uint32_t rows, uint32_t S, uint32_t D, uint32_t vocab) {
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    uint32_t id = (uint32_t)ids[row];
+    if (id >= vocab) id = 0;
+    const __half2 *tr = (const __half2 *)(tok + (size_t)id * D), *pr = (const __half2 *)(pos + (size_t)(row % S) * D);
+    __half2 *xr = (__half2 *)(x + (size_t)row * D);
+    for (uint32_t j = lane; j < D / 2; j += 32) {
+        float2 a = __half22float2(tr[j]), p = __half22float2(pr[j]);
+        xr[j] = __floats2half2_rn(a.x + p.x, a.y + p.y);
+    }
+}
+
+// gather one token per sequence: out[b] = x[b*S + idx]
+__global__ void k_gather_token(const __half *__restrict__ x, __half *__restrict__ out, uint32_t B, uint32_t S, uint32_t idx, uint32_t D) {
+    const uint32_t b = blockIdx.x;
+    for (uint32_t j = threadIdx.x; j < D / 8; j += blockDim.x)
+        ((uint4 *)(out + (size_t)b * D))[j] = ((const uint4 *)(x + ((size_t)b * S + idx) * D))[j];
+}
+
+// ------------------------------------------------------------------ weights
+
+struct Tensor {
+    int dtype = 0;  // 0 f32, 1 f16, 2 i32
+    std::vector<uint32_t> dims;
+    const uint8_t *data = nullptr;
+    size_t nbytes = 0;
+    size_t numel() const { size_t n = 1; for (auto d : dims) n *= d; return n; }
+};
+
+struct WeightFile {
+    std::vector<uint8_t> blob;
+    std::map<std::string, Tensor> t;
+    int load(const char *path) {
+        FILE *f = fopen(path, "rb");
+        MSE_REQUIRE(f != nullptr, MSE_ERR_INVALID, "encoder: cannot open weights file %s", path);
+        fseek(f, 0, SEEK_END);
+        long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        blob.resize((size_t)sz);
+        size_t got = fread(blob.data(), 1, (size_t)sz, f);
+        fclose(f);
+        MSE_REQUIRE(got == (size_t)sz && sz >= 12 && memcmp(blob.data(), "MSEW0001", 8) == 0, MSE_ERR_INVALID,
+                    "encoder: %s is not an MSEW0001 weights file", path);
+        uint32_t n;
+        memcpy(&n, blob.data() + 8, 4);
+        size_t off = 12;
+        for (uint32_t i = 0; i < n; i++) {
+            MSE_REQUIRE(off + 2 <= blob.size(), MSE_ERR_INVALID, "encoder: truncated weights file");
+            uint16_t nl;
+            memcpy(&nl, blob.data() + off, 2);
+            off += 2;
+            std::string name((const char *)blob.data() + off, nl);
+            off += nl;
+            Tensor T;
+            T.dtype = blob[off++];
+            uint8_t nd = blob[off++];
+            for (uint8_t k = 0; k < nd; k++) {
+                uint32_t dd;
+                memcpy(&dd, blob.data() + off, 4);
+                off += 4;
+                T.dims.push_back(dd);
+            }
+            uint64_t nb;
+            memcpy(&nb, blob.data() + off, 8);
+            off += 8;
+            off = (off + 15) & ~(size_t)15;
+            MSE_REQUIRE(off + nb <= blob.size(), MSE_ERR_INVALID, "encoder: tensor %s overruns the file", name.c_str());
+            T.data = blob.data() + off;
+            T.nbytes = nb;
+            off += nb;
+            t[name] = T;
+        }
+        return MSE_OK;
+    }
+    const Tensor *find(const std::string &n) const {
+        auto it = t.find(n);
+        return it == t.end() ? nullptr : &it->second;
+    }
+};
+
+static inline float h2f_host(uint16_t h) { return __half2float(*reinterpret_cast<const __half *>(&h)); }
+
+}  // namespace mse
+
+using namespace mse;
+
+struct LayerW {
+    float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *qkv_b, *proj_b, *fc1_b, *fc2_b;
+    __half *qkv_w, *proj_w, *fc1_w, *fc2_w;
+};
+
+struct TowerW {
+    std::vector<LayerW> layers;
+    float *lnf_g = nullptr, *lnf_b = nullptr;
+};
+
+struct mse_encoder {
+    int device = 0;
+    int32_t cfg[16] = {0};  // img, patch, dim, depth_v, heads, mlp, vocab, ctx, act, has_vision, has_text, depth_t, kpad
+    int max_batch = 0;
+    std::vector<void *> allocs;
+    // vision
+    TowerW vis;
+    __half *patch_w = nullptr, *pos_v = nullptr, *kv_w = nullptr, *pproj_w = nullptr, *pfc1_w = nullptr, *pfc2_w = nullptr;
+    float *patch_b = nullptr, *q_pool = nullptr, *kv_b = nullptr, *pproj_b = nullptr, *pln_g = nullptr, *pln_b = nullptr, *pfc1_b = nullptr,
+          *pfc2_b = nullptr;
+    // text
+    TowerW txt;
+    __half *tok_emb = nullptr, *pos_t = nullptr, *tproj_w = nullptr;
+    float *tproj_b = nullptr;
+    // workspace
+    __half *x = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr, *pool = nullptr, *y = nullptr, *yn = nullptr,
+           *hh = nullptr, *z = nullptr, *outb = nullptr;
+    uint8_t *img_dev = nullptr;
+    int32_t *ids_dev = nullptr;
+    cudaStream_t stream = nullptr;
+    size_t max_tokens = 0;
+};
+
+namespace {
+
+int dev_alloc(mse_encoder *e, void **p, size_t bytes) {
+    cudaError_t err = cudaMalloc(p, bytes ? bytes : 16);
+    if (err != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("encoder: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(err));
+        return MSE_ERR_OOM;
+    }
+    e->allocs.push_back(*p);
+    return MSE_OK;
+}
+
+// upload a tensor as fp16 (matrices) or fp32 (vectors), converting on the host; optional column padding
+int upload(mse_encoder *e, const WeightFile &wf, const std::string &name, bool as_half, void **out, size_t expect_numel,
+           uint32_t rows = 0, uint32_t cols = 0, uint32_t cols_pad = 0) {
+    const Tensor *T = wf.find(name);
+    MSE_REQUIRE(T != nullptr, MSE_ERR_INVALID, "encoder: weights file lacks tensor '%s'", name.c_str());
+    MSE_REQUIRE(T->numel() == expect_numel, MSE_ERR_INVALID, "encoder: tensor '%s' has %zu elements, expected %zu", name.c_str(),
+                T->numel(), expect_numel);
+    MSE_REQUIRE(T->dtype == 0 || T->dtype == 1, MSE_ERR_INVALID, "encoder: tensor '%s' has unsupported dtype", name.c_str());
+    const size_t n = T->numel();
+    auto get = [&](size_t i) -> float {
+        return T->dtype == 0 ? ((const float *)T->data)[i] : h2f_host(((const uint16_t *)T->data)[i]);
+    };
+    if (as_half) {
+        const size_t on = cols_pad ? (size_t)rows * cols_pad : n;
+        std::vector<__half> h(on, __float2half(0.f));
+        if (cols_pad) {
+            for (uint32_t r = 0; r < rows; r++)
+                for (uint32_t c = 0; c < cols; c++) h[(size_t)r * cols_pad + c] = __float2half_rn(get((size_t)r * cols + c));
+        } else if (T->dtype == 1) {
+            memcpy(h.data(), T->data, n * 2);
+        } else {
+            for (size_t i = 0; i < n; i++) h[i] = __float2half_rn(get(i));
+        }
+        MSE_CHECK(dev_alloc(e, out, on * 2));
+        MSE_CUDA(cudaMemcpy(*out, h.data(), on * 2, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> f(n);
+        for (size_t i = 0; i < n; i++) f[i] = get(i);
+        MSE_CHECK(dev_alloc(e, out, n * 4));
+        MSE_CUDA(cudaMemcpy(*out, f.data(), n * 4, cudaMemcpyHostToDevice));
+    }
+    return MSE_OK;
+}
+
+int load_blocks(mse_encoder *e, const WeightFile &wf, TowerW &tw, int depth, bool vision) {
+    const size_t D = e->cfg[2], F = e->cfg[5];
+    tw.layers.resize(depth);
+    char nm[256];
+    for (int l = 0; l < depth; l++) {
+        LayerW &L = tw.layers[l];
+        auto N = [&](const char *vis_fmt, const char *txt_fmt) {
+            snprintf(nm, sizeof(nm), vision ? vis_fmt : txt_fmt, l);
+            return std::string(nm);
+        };
+        MSE_CHECK(upload(e, wf, N("visual.trunk.blocks.%d.norm1.weight", "text.transformer.resblocks.%d.ln_1.weight"), false, (void **)&L.ln1_g, D));
+        MSE_CHECK(upload(e, wf, N("visual.trunk.blocks.%d.norm1.bias", "text.transformer.resblocks.%d.ln_1.bias"), false, (void **)&L.ln1_b, D));
+        MSE_CHECK(upload(e, wf, N("visual.trunk.blocks.%d.attn.qkv.weight", "text.transformer.resblocks.%d.attn.in_proj_weight"), true, (void **)&L.qkv_w, 3 * D * D));
+        MSE_CHECK(upload(e, wf, N("visual.trunk.blocks.%d.attn.qkv.bias", "text.transformer.resblocks.%d.attn.in_proj_bias"), false, (void **)&L.qkv_b, 3 * D));
+        MSE_CHECK(upload(e, wf, N("visual.trunk.blocks.%d.attn.proj.weight", "text.transformer.resblocks.%d.attn.out_proj.weight"), true, (void **)&L.proj_w, D * D));
+        MSE_CHECK(upload(e, wf, N("visual.trunk.blocks.%d.attn.proj.bias", "text.transformer.resblocks.%d.attn.out_proj.bias"), false, (void **)&L.proj_b, D));
+        MSE_CHECK(upload(e, wf, N("visual.trunk.blocks.%d.norm2.weight", "text.transformer.resblocks.%d.ln_2.weight"), false, (void **)&L.ln2_g, D));
+        MSE_CHECK(upload(e, wf, N("visual.trunk.blocks.%d.norm2.bias", "text.transformer.resblocks.%d.ln_2.bias"), false, (void **)&L.ln2_b, D));
+        MSE_CHECK(upload(e, wf, N("visual.trunk.blocks.%d.mlp.fc1.weight", "text.transformer.resblocks.%d.mlp.c_fc.weight"), true, (void **)&L.fc1_w, F * D));
+        MSE_CHECK(upload(e, wf, N("visual.trunk.blocks.%d.mlp.fc1.bias", "text.transformer.resblocks.%d.mlp.c_fc.bias"), false, (void **)&L.fc1_b, F));
+        MSE_CHECK(upload(e, wf, N("visual.trunk.blocks.%d.mlp.fc2.weight", "text.transformer.resblocks.%d.mlp.c_proj.weight"), true, (void **)&L.fc2_w, D * F));
+        MSE_CHECK(upload(e, wf, N("visual.trunk.blocks.%d.mlp.fc2.bias", "text.transformer.resblocks.%d.mlp.c_proj.bias"), false, (void **)&L.fc2_b, D));
+    }
+    return MSE_OK;
+}
+
+int gemm(mse_encoder *e, const __half *A, const __half *W, uint32_t M, uint32_t N, uint32_t K, __half *C, const float *bias, int act,
+         const __half *res, uint32_t res_mod, cudaStream_t st) {
+    GemmOut o{};
+    o.c16 = C;
+    o.ldc = N;
+    o.bias = bias;
+    o.act = act;
+    o.res = res;
+    o.res_mod = res_mod;
+    return gemm_f16_tn_dev(e->device, A, W, M, N, K, K, K, o, st);
+}
+
+int layernorm(const __half *x, __half *y, const float *g, const float *b, uint32_t rows, uint32_t D, cudaStream_t st) {
+    k_layernorm<<<(rows * 32 + 255) / 256, 256, 0, st>>>(x, y, g, b, rows, D, 1e-6f, D, 0);
+    MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
+// the 27 pre-LN blocks shared by both towers (aitemplate/model.py:26-55)
+int run_blocks(mse_encoder *e, const TowerW &tw, int depth, uint32_t B, uint32_t S, cudaStream_t st) {
+    const uint32_t D = e->cfg[2], F = e->cfg[5], H = e->cfg[4], T = B * S;
+    const int act = e->cfg[8];
+    static bool attr_done = false;
+    if (!attr_done) {
+        MSE_CUDA(cudaFuncSetAttribute(attn::k_mha_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::Smem)));
+        attr_done = true;
+    }
+    const float scale_log2e = (1.0f / sqrtf((float)attn::kDH)) * 1.4426950408889634f;
+    for (int l = 0; l < depth; l++) {
+        const LayerW &L = tw.layers[l];
+        MSE_CHECK(layernorm(e->x, e->xn, L.ln1_g, L.ln1_b, T, D, st));
+        MSE_CHECK(gemm(e, e->xn, L.qkv_w, T, 3 * D, D, e->qkv, L.qkv_b, ACT_NONE, nullptr, 0, st));
+        attn::k_mha_fwd<<<dim3((S + attn::kBM - 1) / attn::kBM, H, B), attn::kThreads, sizeof(attn::Smem), st>>>(e->qkv, e->att, (int)S, (int)H,
+                                                                                                                   scale_log2e);
+        MSE_LAUNCH_OK();
+        MSE_CHECK(gemm(e, e->att, L.proj_w, T, D, D, e->x, L.proj_b, ACT_NONE, e->x, 0, st));
+        MSE_CHECK(layernorm(e->x, e->xn, L.ln2_g, L.ln2_b, T, D, st));
+        MSE_CHECK(gemm(e, e->xn, L.fc1_w, T, F, D, e->hbuf, L.fc1_b, act, nullptr, 0, st));
+        MSE_CHECK(gemm(e, e->hbuf, L.fc2_w, T, D, F, e->x, L.fc2_b, ACT_NONE, e->x, 0, st));
+    }
+    return MSE_OK;
+}
+
+// images already in e->img_dev (u8 HWC); result fp16 [B][D] in e->outb.  layer_stop >= 0: stop after that many blocks
+// and leave the token activations in e->x (debug / per-layer parity)
+int vision_forward(mse_encoder *e, uint32_t B, int layer_stop, cudaStream_t st) {
+    const uint32_t D = e->cfg[2], F = e->cfg[5], H = e->cfg[4], img = e->cfg[0], P = img / e->cfg[1], S = P * P, T = B * S, kpad = e->cfg[12];
+    const int act = e->cfg[8];
+    k_im2col_patch14<<<T, 256, 0, st>>>(e->img_dev, e->hbuf, (int)B, (int)img, (int)P, (int)kpad);
+    MSE_LAUNCH_OK();
+    MSE_CHECK(gemm(e, e->hbuf, e->patch_w, T, D, kpad, e->x, e->patch_b, ACT_NONE, e->pos_v, S, st));
+    const int depth = layer_stop >= 0 ? std::min(layer_stop, (int)e->cfg[3]) : (int)e->cfg[3];
+    MSE_CHECK(run_blocks(e, e->vis, depth, B, S, st));
+    if (layer_stop >= 0) return MSE_OK;
+    MSE_CHECK(layernorm(e->x, e->xn, e->vis.lnf_g, e->vis.lnf_b, T, D, st));
+    // MAP head (aitemplate/model.py:82-111)
+    MSE_CHECK(gemm(e, e->xn, e->kv_w, T, 2 * D, D, e->qkv, e->kv_b, ACT_NONE, nullptr, 0, st));
+    k_map_pool<<<dim3(H, B), 128, (S + attn::kDH + 8) * sizeof(float), st>>>(e->qkv, e->q_pool, e->pool, (int)S, (int)H,
+                                                                             1.0f / sqrtf((float)attn::kDH));
+    MSE_LAUNCH_OK();
+    MSE_CHECK(gemm(e, e->pool, e->pproj_w, B, D, D, e->y, e->pproj_b, ACT_NONE, nullptr, 0, st));
+    MSE_CHECK(layernorm(e->y, e->yn, e->pln_g, e->pln_b, B, D, st));
+    MSE_CHECK(gemm(e, e->yn, e->pfc1_w, B, F, D, e->hh, e->pfc1_b, act, nullptr, 0, st));
+    MSE_CHECK(gemm(e, e->hh, e->pfc2_w, B, D, F, e->z, e->pfc2_b, ACT_NONE, e->y, 0, st));
+    k_l2norm_f16<<<(B * 32 + 255) / 256, 256, 0, st>>>(e->z, e->outb, B, D);
+    MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
+int text_forward(mse_encoder *e, uint32_t B, int layer_stop, cudaStream_t st) {
+    const uint32_t D = e->cfg[2], S = e->cfg[7], T = B * S;
+    k_text_embed<<<(T * 32 + 255) / 256, 256, 0, st>>>(e->ids_dev, e->tok_emb, e->pos_t, e->x, T, S, D, (uint32_t)e->cfg[6]);
+    MSE_LAUNCH_OK();
+    const int depth = layer_stop >= 0 ? std::min(layer_stop, (int)e->cfg[11]) : (int)e->cfg[11];
+    MSE_CHECK(run_blocks(e, e->txt, depth, B, S, st));
+    if (layer_stop >= 0) return MSE_OK;
+    MSE_CHECK(layernorm(e->x, e->xn, e->txt.lnf_g, e->txt.lnf_b, T, D, st));
+    k_gather_token<<<B, 128, 0, st>>>(e->xn, e->pool, B, S, S - 1, D);
+    MSE_LAUNCH_OK();
+    MSE_CHECK(gemm(e, e->pool, e->tproj_w, B, D, D, e->z, e->tproj_b, ACT_NONE, nullptr, 0, st));
+    k_l2norm_f16<<<(B * 32 + 255) / 256, 256, 0, st>>>(e->z, e->outb, B, D);
+    MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+
+MSE_API void mse_encoder_destroy(mse_encoder *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void *p : e->allocs) cudaFree(p);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+MSE_API int mse_encoder_create(const char *weights_path, int device, int max_batch, mse_encoder **out) {
+    MSE_REQUIRE(out != nullptr && weights_path != nullptr, MSE_ERR_INVALID, "encoder_create: NULL argument");
+    *out = nullptr;
+    MSE_REQUIRE(max_batch >= 1 && max_batch <= 1024, MSE_ERR_INVALID, "encoder_create: max_batch=%d out of range [1,1024]", max_batch);
+    MSE_CHECK(use_device(device));
+    WeightFile wf;
+    MSE_CHECK(wf.load(weights_path));
+    const Tensor *cfgT = wf.find("config");
+    MSE_REQUIRE(cfgT && cfgT->dtype == 2 && cfgT->numel() >= 12, MSE_ERR_INVALID, "encoder_create: weights file lacks the i32 'config' tensor");
+    mse_encoder *e = new mse_encoder();
+    e->device = device;
+    e->max_batch = max_batch;
+    memcpy(e->cfg, cfgT->data, std::min<size_t>(cfgT->nbytes, sizeof(e->cfg)));
+    int rc = MSE_OK;
+    auto fail = [&](int code) { mse_encoder_destroy(e); return code; };
+    const int img = e->cfg[0], patch = e->cfg[1], D = e->cfg[2], depth_v = e->cfg[3], H = e->cfg[4], F = e->cfg[5], vocab = e->cfg[6],
+              ctx = e->cfg[7], act = e->cfg[8], has_v = e->cfg[9], has_t = e->cfg[10], depth_t = e->cfg[11];
+    if (!(patch == 14 && D == H * attn::kDH && D % 64 == 0 && D <= 2048 && F % 8 == 0 && (act == 1 || act == 2) && img % patch <= patch &&
+          img >= patch && ctx >= 1 && (has_v || has_t))) {
+        set_error("encoder_create: unsupported architecture (img %d patch %d dim %d heads %d mlp %d ctx %d act %d)", img, patch, D, H, F, ctx, act);
+        return fail(MSE_ERR_UNSUPPORTED);
+    }
+    const int kpad = 640;
+    e->cfg[12] = kpad;
+    const size_t P = img / patch, Sv = P * P;
+    do {
+        if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = MSE_ERR_CUDA; set_error("encoder_create: stream"); break; }
+        if (has_v) {
+            if ((rc = upload(e, wf, "visual.trunk.patch_embed.proj.weight", true, (void **)&e->patch_w, (size_t)D * 588, D, 588, kpad))) break;
+            if ((rc = upload(e, wf, "visual.trunk.patch_embed.proj.bias", false, (void **)&e->patch_b, D))) break;
+            if ((rc = upload(e, wf, "visual.trunk.pos_embed", true, (void **)&e->pos_v, Sv * D))) break;
+            if ((rc = load_blocks(e, wf, e->vis, depth_v, true))) break;
+            if ((rc = upload(e, wf, "visual.trunk.norm.weight", false, (void **)&e->vis.lnf_g, D))) break;
+            if ((rc = upload(e, wf, "visual.trunk.norm.bias", false, (void **)&e->vis.lnf_b, D))) break;
+            if ((rc = upload(e, wf, "visual.trunk.attn_pool.kv.weight", true, (void **)&e->kv_w, (size_t)2 * D * D))) break;
+            if ((rc = upload(e, wf, "visual.trunk.attn_pool.kv.bias", false, (void **)&e->kv_b, 2 * D))) break;
+            if ((rc = upload(e, wf, "visual.trunk.attn_pool.proj.weight", true, (void **)&e->pproj_w, (size_t)D * D))) break;
+            if ((rc = upload(e, wf, "visual.trunk.attn_pool.proj.bias", false, (void **)&e->pproj_b, D))) break;
+            if ((rc = upload(e, wf, "visual.trunk.attn_pool.norm.weight", false, (void **)&e->pln_g, D))) break;
+            if ((rc = upload(e, wf, "visual.trunk.attn_pool.norm.bias", false, (void **)&e->pln_b, D))) break;
+            if ((rc = upload(e, wf, "visual.trunk.attn_pool.mlp.fc1.weight", true, (void **)&e->pfc1_w, (size_t)F * D))) break;
+            if ((rc = upload(e, wf, "visual.trunk.attn_pool.mlp.fc1.bias", false, (void **)&e->pfc1_b, F))) break;
+            if ((rc = upload(e, wf, "visual.trunk.attn_pool.mlp.fc2.weight", true, (void **)&e->pfc2_w, (size_t)D * F))) break;
+            if ((rc = upload(e, wf, "visual.trunk.attn_pool.mlp.fc2.bias", false, (void **)&e->pfc2_b, D))) break;
+            // probe query q = Wq * latent + bq (aitemplate/model.py:99-100), once per weight load, fp32 on the host from the
+            // fp16-rounded weights the GPU uses
+            const Tensor *lat = wf.find("visual.trunk.attn_pool.latent"), *qw = wf.find("visual.trunk.attn_pool.q.weight"),
+                         *qb = wf.find("visual.trunk.attn_pool.q.bias");
+            if (!lat || !qw || !qb || lat->numel() != (size_t)D || qw->numel() != (size_t)D * D || qb->numel() != (size_t)D) {
+                set_error("encoder_create: attn_pool.latent / q.weight / q.bias missing or mis-shaped");
+                rc = MSE_ERR_INVALID;
+                break;
+            }
+            auto val = [&](const Tensor *T, size_t i) { return T->dtype == 0 ? ((const float *)T->data)[i] : h2f_host(((const uint16_t *)T->data)[i]); };
+            auto r16 = [&](float v) { return __half2float(__float2half_rn(v)); };
+            std::vector<float> qp(D);
+            for (int o = 0; o < D; o++) {
+                double acc = 0.0;
+                for (int i = 0; i < D; i++) acc += (double)r16(val(qw, (size_t)o * D + i)) * (double)r16(val(lat, i));
+                qp[o] = (float)acc + val(qb, o);
+            }
+            if ((rc = dev_alloc(e, (void **)&e->q_pool, (size_t)D * 4))) break;
+            if (cudaMemcpy(e->q_pool, qp.data(), (size_t)D * 4, cudaMemcpyHostToDevice) != cudaSuccess) { rc = MSE_ERR_CUDA; set_error("encoder_create: H2D"); break; }
+        }
+        if (has_t) {
+            if ((rc = upload(e, wf, "text.token_embedding.weight", true, (void **)&e->tok_emb, (size_t)vocab * D))) break;
+            if ((rc = upload(e, wf, "text.positional_embedding", true, (void **)&e->pos_t, (size_t)ctx * D))) break;
+            if ((rc = load_blocks(e, wf, e->txt, depth_t, false))) break;
+            if ((rc = upload(e, wf, "text.ln_final.weight", false, (void **)&e->txt.lnf_g, D))) break;
+            if ((rc = upload(e, wf, "text.ln_final.bias", false, (void **)&e->txt.lnf_b, D))) break;
+            if ((rc = upload(e, wf, "text.text_projection.weight", true, (void **)&e->tproj_w, (size_t)D * D))) break;
+            if ((rc = upload(e, wf, "text.text_projection.bias", false, (void **)&e->tproj_b, D))) break;
+        }
+        const size_t S_max = std::max<size_t>(has_v ? Sv : 0, has_t ? (size_t)ctx : 0);
+        const size_t T = (size_t)max_batch * S_max;
+        e->max_tokens = T;
+        if ((rc = dev_alloc(e, (void **)&e->x, T * D * 2))) break;
+        if ((rc = dev_alloc(e, (void **)&e->xn, T * D * 2))) break;
+        if ((rc = dev_alloc(e, (void **)&e->qkv, T * 3 * D * 2))) break;
+        if ((rc = dev_alloc(e, (void **)&e->att, T * D * 2))) break;
+        if ((rc = dev_alloc(e, (void **)&e->hbuf, T * std::max<size_t>(F, kpad) * 2))) break;
+        const size_t Bm = max_batch;
+        if ((rc = dev_alloc(e, (void **)&e->pool, Bm * D * 2))) break;
+        if ((rc = dev_alloc(e, (void **)&e->y, Bm * D * 2))) break;
+        if ((rc = dev_alloc(e, (void **)&e->yn, Bm * D * 2))) break;
+        if ((rc = dev_alloc(e, (void **)&e->hh, Bm * F * 2))) break;
+        if ((rc = dev_alloc(e, (void **)&e->z, Bm * D * 2))) break;
+        if ((rc = dev_alloc(e, (void **)&e->outb, Bm * D * 2))) break;
+        if (has_v && (rc = dev_alloc(e, (void **)&e->img_dev, Bm * img * img * 3))) break;
+        if (has_t && (rc = dev_alloc(e, (void **)&e->ids_dev, Bm * ctx * 4))) break;
+    } while (0);
+    if (rc != MSE_OK) return fail(rc);
+    *out = e;
+    return MSE_OK;
+}
+
+MSE_API int mse_encoder_config(const mse_encoder *e, int32_t out[16]) {
+    MSE_REQUIRE(e != nullptr && out != nullptr, MSE_ERR_INVALID, "encoder_config: NULL argument");
+    memcpy(out, e->cfg, sizeof(e->cfg));
+    return MSE_OK;
+}
+
+static int encode_images_impl(mse_encoder *e, const uint8_t *img, bool img_on_device, int batch, uint16_t *out, bool out_on_device,
+                              int layer_stop, cudaStream_t st) {
+    MSE_REQUIRE(e != nullptr, MSE_ERR_INVALID, "encode_images: NULL handle");
+    MSE_REQUIRE(e->cfg[9], MSE_ERR_STATE, "encode_images: this encoder was loaded without a vision tower");
+    MSE_REQUIRE(batch >= 0 && (batch == 0 || (img && out)), MSE_ERR_INVALID, "encode_images: bad argument");
+    MSE_REQUIRE(batch <= e->max_batch, MSE_ERR_INVALID, "encode_images: max batch size is %d", e->max_batch);  // clip_server.py:139
+    if (batch == 0) return MSE_OK;
+    MSE_CHECK(use_device(e->device));
+    const size_t D = e->cfg[2], img_px = (size_t)e->cfg[0] * e->cfg[0] * 3, P = e->cfg[0] / e->cfg[1];
+    MSE_CUDA(cudaMemcpyAsync(e->img_dev, img, (size_t)batch * img_px, img_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    MSE_CHECK(vision_forward(e, (uint32_t)batch, layer_stop, st));
+    if (layer_stop >= 0)
+        MSE_CUDA(cudaMemcpyAsync(out, e->x, (size_t)batch * P * P * D * 2, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    else
+        MSE_CUDA(cudaMemcpyAsync(out, e->outb, (size_t)batch * D * 2, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (!out_on_device) MSE_CUDA(cudaStreamSynchronize(st));
+    return MSE_OK;
+}
+
+static int encode_text_impl(mse_encoder *e, const int32_t *ids, bool ids_on_device, int batch, uint16_t *out, bool out_on_device,
+                            int layer_stop, cudaStream_t st) {
+    MSE_REQUIRE(e != nullptr, MSE_ERR_INVALID, "encode_text: NULL handle");
+    MSE_REQUIRE(e->cfg[10], MSE_ERR_STATE, "encode_text: this encoder was loaded without a text tower");
+    MSE_REQUIRE(batch >= 0 && (batch == 0 || (ids && out)), MSE_ERR_INVALID, "encode_text: bad argument");
+    MSE_REQUIRE(batch <= e->max_batch, MSE_ERR_INVALID, "encode_text: max batch size is %d", e->max_batch);  // clip_server.py:136
+    if (batch == 0) return MSE_OK;
+    MSE_CHECK(use_device(e->device));
+    const size_t D = e->cfg[2], S = e->cfg[7];
+    MSE_CUDA(cudaMemcpyAsync(e->ids_dev, ids, (size_t)batch * S * 4, ids_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    MSE_CHECK(text_forward(e, (uint32_t)batch, layer_stop, st));
+    if (layer_stop >= 0)
+        MSE_CUDA(cudaMemcpyAsync(out, e->x, (size_t)batch * S * D * 2, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    else
+        MSE_CUDA(cudaMemcpyAsync(out, e->outb, (size_t)batch * D * 2, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (!out_on_device) MSE_CUDA(cudaStreamSynchronize(st));
+    return MSE_OK;
+}
+
+MSE_API int mse_encode_images_u8(mse_encoder *e, const uint8_t *rgb_hwc, int batch, uint16_t *out_f16) {
+    return encode_images_impl(e, rgb_hwc, false, batch, out_f16, false, -1, e ? e->stream : nullptr);
+}
+MSE_API int mse_encode_images_u8_dev(mse_encoder *e, const uint8_t *d_rgb_hwc, int batch, uint16_t *d_out_f16, void *stream) {
+    return encode_images_impl(e, d_rgb_hwc, true, batch, d_out_f16, true, -1, (cudaStream_t)stream);
+}
+MSE_API int mse_encode_text_ids(mse_encoder *e, const int32_t *ids, int batch, uint16_t *out_f16) {
+    return encode_text_impl(e, ids, false, batch, out_f16, false, -1, e ? e->stream : nullptr);
+}
+MSE_API int mse_encode_text_ids_dev(mse_encoder *e, const int32_t *d_ids, int batch, uint16_t *d_out_f16, void *stream) {
+    return encode_text_impl(e, d_ids, true, batch, d_out_f16, true, -1, (cudaStream_t)stream);
+}
+MSE_API int mse_encode_images_hidden(mse_encoder *e, const uint8_t *rgb_hwc, int batch, int n_blocks, uint16_t *out_tokens_f16) {
+    MSE_REQUIRE(n_blocks >= 0, MSE_ERR_INVALID, "encode_images_hidden: n_blocks must be >= 0");
+    return encode_images_impl(e, rgb_hwc, false, batch, out_tokens_f16, false, n_blocks, e ? e->stream : nullptr);
+}
+MSE_API int mse_encode_text_hidden(mse_encoder *e, const int32_t *ids, int batch, int n_blocks, uint16_t *out_tokens_f16) {
+    MSE_REQUIRE(n_blocks >= 0, MSE_ERR_INVALID, "encode_text_hidden: n_blocks must be >= 0");
+    return encode_text_impl(e, ids, false, batch, out_tokens_f16, false, n_blocks, e ? e->stream : nullptr);
+}

@@ -42,7 +42,13 @@ int gemm_f16_tn_dev(int device, const __half *dA, const __half *dB, uint32_t M, 
     epi.o = out;
     epi.M = M;
     epi.N = N;
-    if (N % 256 == 0 || N > 1024) return launch_gemm<256>(device, dA, dB, M, N, K, lda, ldb, epi, st);
+    // tile width: least padded columns wins, ties go to the wider tile (fewer A re-reads per flop)
+    auto waste = [&](uint32_t bn) { return (N + bn - 1) / bn * bn - N; };
+    uint32_t best = 256;
+    if (waste(192) < waste(best)) best = 192;
+    if (waste(128) < waste(best)) best = 128;
+    if (best == 256) return launch_gemm<256>(device, dA, dB, M, N, K, lda, ldb, epi, st);
+    if (best == 192) return launch_gemm<192>(device, dA, dB, M, N, K, lda, ldb, epi, st);
     return launch_gemm<128>(device, dA, dB, M, N, K, lda, ldb, epi, st);
 }
 

@@ -24,7 +24,7 @@ static constexpr int kGemmThreads = 192;
 
 template <int BN>
 struct GemmCfg {
-    static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+    static constexpr int kStages = BN >= 256 ? 4 : (BN >= 192 ? 5 : 6);
     static constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;
     static constexpr uint32_t kBBytes = BN * kGemmBK * 2;
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
