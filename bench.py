@@ -1,17 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- one JSON line per run (contract: the task prompt's bench section).
 
-Workload (config.workload = "flat_top100"): BASELINE.json configs[2] -- 1024 f32 queries, top-100 by inner
-product over a 10M x 1152 fp16 index resident in HBM, id-range sharded over --gpus N (strong scaling: the
-index is fixed at --rows rows in total).  A step = one batch of 1024 queries through the whole hot path
-(fp16 cast + certificate prep, tcgen05 scoring GEMM with in-epilogue threshold filter, per-chunk select,
-fp64 rerank, finalize; for N > 1 one all-gather of per-shard top-k + merge).
+Headline workload (config.workload = "siglip_image_tower_b256"): BASELINE.json configs[1] -- the SigLIP
+ViT-SO400M-14/384 image tower, batch 256, fp16 storage / fp32 accumulate, one B200; a step = one batch of 256
+synthetic 384x384 u8 images through im2col+normalise, patch-embed GEMM, 27 blocks (LN, QKV GEMM, attention,
+out-proj GEMM, LN, MLP GEMMs), final LN, MAP head and L2 normalisation.  Random-init weights of that architecture.
+For --gpus N each rank encodes its own batch of 256 (data parallel, weights replicated, no collective): weak scaling.
 
-  value  queries/s, queries and index resident in HBM (device pointers into the C ABI)
-  e2e    queries/s through the host-pointer C-ABI call: pinned host queries -> H2D -> search -> D2H ids+scores
+  value  images/s with the u8 images resident in HBM (device pointers into the C ABI)
+  e2e    images/s through the host-pointer C-ABI call: pinned host u8 images -> H2D -> towers -> D2H fp16 features
 
---impl reference times the CPU restatement of the reference's path (oracle/, AVX2 + OpenMP on all host cores)
-on a bounded sample of the same workload; the reference itself (Rust nightly + faiss) cannot be built here.
+The same run also measures BASELINE.json configs[2] (1024 f32 queries, top-100 over a 10M x 1152 fp16 index,
+id-range sharded over the ranks, strong scaling, one all-gather + merge) and reports it under "search".
+
+--impl reference times the CPU stand-ins of the reference's path on the host cores (bounded samples): transformers
+SiglipVisionModel fp32 for clip_server.py device=cpu, and the C restatement of the flat scan (oracle/, AVX2+OpenMP).
+The reference itself (open_clip + Rust nightly + faiss) cannot be installed or built in this image.
 """
 from __future__ import annotations
 
@@ -20,6 +24,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -28,7 +33,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 D = 1152
-METRIC = "queries/sec (flat top-100, 1024 queries x 10M x 1152 fp16 index)"
+METRIC = "SigLIP ViT-SO400M-14/384 images/sec (image tower, batch 256 fp16)"
+SEARCH_METRIC = "queries/sec (flat top-100, 1024 queries x 10M x 1152 fp16 index)"
+FLOP_PER_IMAGE = 670.35e9  # 27 layers 665.46 + patch-embed 0.99 + MAP head 3.90 GFLOP
 
 
 def peaks():
@@ -69,24 +76,42 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
+        sm, mx, pw, reasons = [], 0.0, 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                sm.append(float(r[0])); mx = max(mx, float(r[1])); pw = max(pw, float(r[2]))
             except Exception:
                 continue
             for n, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "power_w_max": pw or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_flat(rows_total: int, nq_full: int, k: int, steps: int, warmup: int, sample_rows: int, sample_q: int):
-    """The reference's flat path on the host cores: fp16 rows x f32 query, f32 accumulate (AVX2), top-k heap,
-    OpenMP over rows (oracle mode 1).  Bounded sample: sample_q queries over a sample_rows slice; throughput is
-    scaled to the full index by rows (a scan is linear in rows)."""
+# ---------------------------------------------------------------- CPU stand-ins of the reference (bounded samples)
+
+def cpu_reference_tower(batch: int, steps: int, warmup: int):
+    import numpy as np
+    import torch
+    from oracle import towers as T
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = T.build_vision(depth=27, seed=42)
+    imgs = T.synthetic_images(1, batch)
+    for _ in range(warmup):
+        T.encode_image(m, imgs[:1])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        T.encode_image(m, imgs)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return batch / dt, dt, os.cpu_count()
+
+
+def cpu_reference_flat(rows_total: int, k: int, steps: int, warmup: int, sample_rows: int, sample_q: int):
+    """fp16 rows x f32 query, f32 accumulate (AVX2), top-k heap, OpenMP over rows (oracle mode 1); a scan is linear in rows,
+    so throughput on a sample_rows slice is scaled by sample_rows / rows_total."""
     import numpy as np
     from oracle import oracle as O
     O.build()
@@ -103,9 +128,42 @@ def cpu_reference_flat(rows_total: int, nq_full: int, k: int, steps: int, warmup
     for _ in range(steps):
         O.flat_search(q, x16, k, mode=1)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    qps_sample = sample_q / dt
-    qps_full = qps_sample * sample_rows / rows_total
-    return qps_full, dt, os.cpu_count()
+    return (sample_q / dt) * sample_rows / rows_total, dt, os.cpu_count()
+
+
+# ---------------------------------------------------------------- synthetic weights (random init of the named architecture)
+
+def random_openclip_state_dict(dev, depth_v=27, seed=42):
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    F = 4304
+
+    def mat(*shape, std=0.02):
+        return (torch.randn(shape, generator=g, device=dev) * std).to(torch.float16).cpu().numpy()
+
+    def vec(n, base=0.0, std=0.02):
+        return (base + std * torch.randn((n,), generator=g, device=dev)).float().cpu().numpy()
+
+    sd = {"visual.trunk.patch_embed.proj.weight": mat(D, 3, 14, 14, std=0.03), "visual.trunk.patch_embed.proj.bias": vec(D),
+          "visual.trunk.pos_embed": mat(1, 729, D, std=D ** -0.5)}
+    for i in range(depth_v):
+        p = f"visual.trunk.blocks.{i}."
+        sd[p + "norm1.weight"], sd[p + "norm1.bias"] = vec(D, 1.0, 0.05), vec(D)
+        sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"] = mat(3 * D, D), vec(3 * D)
+        sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"] = mat(D, D), vec(D)
+        sd[p + "norm2.weight"], sd[p + "norm2.bias"] = vec(D, 1.0, 0.05), vec(D)
+        sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"] = mat(F, D), vec(F)
+        sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"] = mat(D, F), vec(D)
+    sd["visual.trunk.norm.weight"], sd["visual.trunk.norm.bias"] = vec(D, 1.0, 0.05), vec(D)
+    p = "visual.trunk.attn_pool."
+    sd[p + "latent"] = mat(1, 1, D, std=D ** -0.5)
+    sd[p + "q.weight"], sd[p + "q.bias"] = mat(D, D), vec(D)
+    sd[p + "kv.weight"], sd[p + "kv.bias"] = mat(2 * D, D), vec(2 * D)
+    sd[p + "proj.weight"], sd[p + "proj.bias"] = mat(D, D), vec(D)
+    sd[p + "norm.weight"], sd[p + "norm.bias"] = vec(D, 1.0, 0.05), vec(D)
+    sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"] = mat(F, D), vec(F)
+    sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"] = mat(D, F), vec(D)
+    return sd
 
 
 def main():
@@ -114,11 +172,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows", type=int, default=10_000_000, help="total index rows (all shards)")
+    ap.add_argument("--workloads", default="tower,flat", help="comma list of tower, flat")
+    ap.add_argument("--batch", type=int, default=256, help="images per rank per step")
+    ap.add_argument("--rows", type=int, default=10_000_000, help="flat: total index rows (all shards)")
     ap.add_argument("--queries", type=int, default=1024)
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=32)
+    ap.add_argument("--cpu-sample-images", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -126,23 +187,29 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     steps, warmup = args.steps, max(args.warmup, 0)
-    workload = {"workload": "flat_top100", "queries": args.queries, "k": args.k, "index_rows": args.rows, "dim": D,
-                "index_dtype": "fp16", "query_dtype": "f32", "sharding": f"id-range x{world}",
-                "l2_policy": "inputs larger than L2 (index shard >> 126 MB)"}
+    wl = [w for w in args.workloads.split(",") if w]
+    tower_cfg = {"workload": "siglip_image_tower_b256", "model": "ViT-SO400M-14-SigLIP-384 image tower (random init)", "batch_per_gpu": args.batch,
+                 "image": "384x384x3 u8", "storage": "fp16", "accumulate": "fp32", "parallelism": f"dp{world}",
+                 "l2_policy": "inputs larger than L2 (per-layer activations 430 MB - 1.6 GB >> 126 MB)"}
+    flat_cfg = {"workload": "flat_top100", "queries": args.queries, "k": args.k, "index_rows": args.rows, "dim": D, "index_dtype": "fp16",
+                "query_dtype": "f32", "sharding": f"id-range x{world}", "l2_policy": "inputs larger than L2 (index shard >> 126 MB)"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        qps, dt, cores = cpu_reference_flat(args.rows, args.queries, args.k, max(1, min(steps, 3)), min(warmup, 1),
-                                            args.cpu_sample_rows, args.cpu_sample_queries)
-        sample = f"{args.cpu_sample_queries} queries x {args.cpu_sample_rows}-row slice per step, scaled by rows to {args.rows}"
-        print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (AVX2) over fp16 rows",
-            "data": "synthetic", "config": workload,
-            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+        ips, dt, cores = cpu_reference_tower(args.cpu_sample_images, max(1, min(steps, 2)), min(warmup, 1))
+        sample = f"{args.cpu_sample_images} images per step (full 27-block tower, transformers SiglipVisionModel fp32, torch threads = all cores)"
+        out = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+               "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (CPU)",
+               "data": "synthetic", "config": tower_cfg,
+               "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+               "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        if "flat" in wl:
+            qps, fdt, _ = cpu_reference_flat(args.rows, args.k, 1, 1, args.cpu_sample_rows, args.cpu_sample_queries)
+            out["search"] = {"metric": SEARCH_METRIC, "value": qps, "unit": "queries/s", "ms_per_step": fdt * 1e3, "config": flat_cfg,
+                             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                                              "sample": f"{args.cpu_sample_queries} queries x {args.cpu_sample_rows}-row slice, scaled by rows to {args.rows}"}}
+        print(json.dumps(out))
         return
 
     import numpy as np
@@ -156,57 +223,8 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
-
-    # ---- synthetic shard: id range [row_lo, row_hi) of the global index, generated on the device (Philox, seed 2)
-    rows_total, nq, k = args.rows, args.queries, args.k
-    row_lo = rows_total * rank // world
-    row_hi = rows_total * (rank + 1) // world
-    n_local = row_hi - row_lo
-    ix = mse_b200.FlatIndex(D, device=local_rank, id_base=row_lo)
-    ix.reserve(n_local)
-    gen = torch.Generator(device=dev)
-    chunk = 1 << 19
     stream = torch.cuda.current_stream().cuda_stream
-    for c0 in range(row_lo, row_hi, chunk):
-        m = min(chunk, row_hi - c0)
-        gen.manual_seed(2 * 1_000_003 + c0)  # chunk-addressable so every shard layout yields the same global index
-        xb = torch.randn((m, D), generator=gen, device=dev, dtype=torch.float32)
-        xb = (xb / xb.norm(dim=1, keepdim=True)).to(torch.float16).contiguous()
-        ix.add_f16_dev(xb.data_ptr(), m, stream)
-        del xb
-    assert ix.ntotal == n_local
-    gq = torch.Generator(device="cpu")
-    gq.manual_seed(3)
-    q_host = torch.randn((nq, D), generator=gq, dtype=torch.float32)
-    q_host = (q_host / q_host.norm(dim=1, keepdim=True)).contiguous().pin_memory()
-    q_dev = q_host.to(dev)
-    ids_dev = torch.empty((nq, k), dtype=torch.int32, device=dev)
-    sc_dev = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    if world > 1:
-        all_ids = torch.empty((world, nq, k), dtype=torch.int32, device=dev)
-        all_sc = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
-        out_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
-        out_sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    ids_host = torch.empty((nq, k), dtype=torch.int32).pin_memory()
-    sc_host = torch.empty((nq, k), dtype=torch.float32).pin_memory()
-
-    def step_resident():
-        ix.search_dev(q_dev.data_ptr(), nq, k, ids_dev.data_ptr(), sc_dev.data_ptr(), stream)
-        if world > 1:
-            dist.all_gather_into_tensor(all_ids, ids_dev)
-            dist.all_gather_into_tensor(all_sc, sc_dev)
-            mse_b200.merge_topk(local_rank, all_ids.data_ptr(), all_sc.data_ptr(), world, nq, k, out_ids.data_ptr(), out_sc.data_ptr(), stream)
-
-    def step_e2e():
-        if world == 1:
-            # the reference-facing call: host pointers in, host pointers out (H2D + D2H inside)
-            mse_b200.check(mse_b200.lib().mse_search_flat(ix._h, q_host.data_ptr(), nq, k, ids_host.data_ptr(), sc_host.data_ptr()), "mse_search_flat")
-        else:
-            q_dev.copy_(q_host, non_blocking=True)
-            step_resident()
-            ids_host.copy_(out_ids, non_blocking=True)
-            sc_host.copy_(out_sc, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+    pk = peaks()
 
     def barrier():
         if world > 1:
@@ -232,50 +250,156 @@ def main():
             ms = float(t.item())
         return ms / n_steps, launches
 
-    with ClockSampler(local_rank) as cs:
-        ms_step, launches = timed(step_resident, warmup, steps)
-    clocks = cs.summary()
-    ms_e2e, _ = timed(step_e2e, min(warmup, 2), steps)
+    result = {}
 
-    # ---- roofline of the dominant kernel (k_gemm_tn<256, FlatEpilogue>): CUDA events around every scoring launch
-    ix.profile(True)
-    prof_ns, prof_launches = 0, 0
-    for _ in range(3):
-        ix.search_dev(q_dev.data_ptr(), nq, k, ids_dev.data_ptr(), sc_dev.data_ptr(), stream)
+    # ============================================================ tower (headline)
+    if "tower" in wl:
+        B = args.batch
+        wpath = os.path.join(tempfile.gettempdir(), f"mse_bench_vision27_rank{rank}.msew")
+        sd = random_openclip_state_dict(dev)
+        mse_b200.weights.save_weights(wpath, sd, mse_b200.weights.config_for(sd))
+        del sd
+        enc = mse_b200.Encoder(wpath, device=local_rank, max_batch=B)
+        os.remove(wpath)
+        g = torch.Generator(device=dev).manual_seed(1 + rank)
+        imgs_dev = torch.randint(0, 256, (B, 384, 384, 3), generator=g, device=dev, dtype=torch.uint8)
+        imgs_host = imgs_dev.cpu().pin_memory()
+        feat_dev = torch.empty((B, D), dtype=torch.float16, device=dev)
+        feat_host = torch.empty((B, D), dtype=torch.float16).pin_memory()
+
+        def tower_resident():
+            enc.encode_image_dev(imgs_dev.data_ptr(), B, feat_dev.data_ptr(), stream)
+
+        def tower_e2e():
+            mse_b200.check(mse_b200.lib().mse_encode_images_u8(enc._h, imgs_host.data_ptr(), B, feat_host.data_ptr()), "mse_encode_images_u8")
+
+        with ClockSampler(local_rank) as cs:
+            ms_step, launches = timed(tower_resident, warmup, steps)
+        clocks = cs.summary()
+        ms_e2e, _ = timed(tower_e2e, min(warmup, 2), steps)
+        enc.profile(True)
+        tower_resident()
+        st = enc.stats()
+        enc.profile(False)
+        torch.cuda.synchronize()
+        f = feat_dev.float()
+        assert torch.isfinite(f).all() and (f.norm(dim=1) - 1).abs().max() < 5e-3, "tower output is not unit-norm finite"
+        gemm_tf = st["gemm_mflop"] * 1e6 / (st["gemm_ns"] * 1e-9) / 1e12 if st["gemm_ns"] else None
+        attn_flop = 27 * 4.0 * 729 * 729 * 72 * 16 * B
+        roof = {"kernel": "k_gemm_tn<BN,LinearEpilogue> (all GEMM launches of one step)", "bound": "tensor", "achieved": gemm_tf,
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sustained"] if gemm_tf else None,
+                "peak_source": pk["src"] + " (sustained bf16 cuBLAS)", "frac_of_burst": gemm_tf / pk["tf_burst"] if gemm_tf else None,
+                "launches_per_step": st["gemm_launches"], "kernel_ms_per_step": st["gemm_ns"] * 1e-6,
+                "kernel_share_of_step": st["gemm_ns"] * 1e-6 / ms_step, "traffic": None,
+                "attention": {"kernel": "k_mha_fwd (mma.sync)", "ms_per_step": st["attn_ns"] * 1e-6, "launches": st["attn_launches"],
+                              "achieved_tflops": attn_flop / (st["attn_ns"] * 1e-9) / 1e12 if st["attn_ns"] else None,
+                              "share_of_step": st["attn_ns"] * 1e-6 / ms_step},
+                "whole_step": {"achieved_tflops": FLOP_PER_IMAGE * B / (ms_step * 1e-3) / 1e12,
+                               "frac": FLOP_PER_IMAGE * B / (ms_step * 1e-3) / 1e12 / pk["tf_sustained"]}}
+        result = {"metric": METRIC, "value": world * B / (ms_step * 1e-3), "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+                  "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                  "dtype": "fp16 storage, fp32 accumulate (tcgen05 kind::f16)", "data": "synthetic", "config": tower_cfg, "clocks": clocks,
+                  "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * 384 * 384 * 3, "d2h_bytes_per_step": B * D * 2,
+                          "ms_per_step": ms_e2e},
+                  "gpu_launches": launches, "roofline": roof}
+        enc.close()
+        del imgs_dev, feat_dev
+        torch.cuda.empty_cache()
+
+    # ============================================================ flat search
+    if "flat" in wl:
+        rows_total, nq, k = args.rows, args.queries, args.k
+        row_lo, row_hi = rows_total * rank // world, rows_total * (rank + 1) // world
+        n_local = row_hi - row_lo
+        ix = mse_b200.FlatIndex(D, device=local_rank, id_base=row_lo)
+        ix.reserve(n_local)
+        gen = torch.Generator(device=dev)
+        chunk = 1 << 19
+        for c0 in range(row_lo, row_hi, chunk):
+            m = min(chunk, row_hi - c0)
+            gen.manual_seed(2 * 1_000_003 + c0)
+            xb = torch.randn((m, D), generator=gen, device=dev, dtype=torch.float32)
+            xb = (xb / xb.norm(dim=1, keepdim=True)).to(torch.float16).contiguous()
+            ix.add_f16_dev(xb.data_ptr(), m, stream)
+            del xb
+        gq = torch.Generator(device="cpu").manual_seed(3)
+        q_host = torch.randn((nq, D), generator=gq, dtype=torch.float32)
+        q_host = (q_host / q_host.norm(dim=1, keepdim=True)).contiguous().pin_memory()
+        q_dev = q_host.to(dev)
+        ids_dev = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        sc_dev = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        if world > 1:
+            all_ids = torch.empty((world, nq, k), dtype=torch.int32, device=dev)
+            all_sc = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
+            out_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+            out_sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        ids_host = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+        sc_host = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+
+        def flat_resident():
+            ix.search_dev(q_dev.data_ptr(), nq, k, ids_dev.data_ptr(), sc_dev.data_ptr(), stream)
+            if world > 1:
+                dist.all_gather_into_tensor(all_ids, ids_dev)
+                dist.all_gather_into_tensor(all_sc, sc_dev)
+                mse_b200.merge_topk(local_rank, all_ids.data_ptr(), all_sc.data_ptr(), world, nq, k, out_ids.data_ptr(), out_sc.data_ptr(), stream)
+
+        def flat_e2e():
+            if world == 1:
+                mse_b200.check(mse_b200.lib().mse_search_flat(ix._h, q_host.data_ptr(), nq, k, ids_host.data_ptr(), sc_host.data_ptr()), "mse_search_flat")
+            else:
+                q_dev.copy_(q_host, non_blocking=True)
+                flat_resident()
+                ids_host.copy_(out_ids, non_blocking=True)
+                sc_host.copy_(out_sc, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+        with ClockSampler(local_rank) as cs:
+            ms_step, launches = timed(flat_resident, warmup, steps)
+        fclocks = cs.summary()
+        ms_e2e, _ = timed(flat_e2e, min(warmup, 2), steps)
+        ix.profile(True)
+        for _ in range(2):
+            ix.search_dev(q_dev.data_ptr(), nq, k, ids_dev.data_ptr(), sc_dev.data_ptr(), stream)
         st = ix.stats()
-        prof_ns, prof_launches = st["scoring_ns"], st["scoring_launches"]
-    ix.profile(False)
-    stats = ix.stats()
-    pk = peaks()
-    nq_pad = (nq + 127) // 128 * 128
-    flops = 2.0 * nq_pad * n_local * D           # per step, this rank (padded query rows are computed too)
-    tf = flops / (prof_ns * 1e-9) / 1e12 if prof_ns else None
-    hbm_gbs = n_local * D * 2 / (prof_ns * 1e-9) / 1e9 if prof_ns else None
-    ai = nq_pad  # flop per HBM byte = nq_pad
-    bound = "tensor" if ai > pk["tf_sustained"] * 1e12 / (pk["hbm"] * 1e9) else "hbm"
-    roofline = {"kernel": "k_gemm_tn<256,FlatEpilogue> (all chunk launches of one step)", "bound": bound,
-                "achieved": tf if bound == "tensor" else hbm_gbs, "peak": pk["tf_sustained"] if bound == "tensor" else pk["hbm"],
-                "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
-                "frac": (tf / pk["tf_sustained"]) if (bound == "tensor" and tf) else ((hbm_gbs / pk["hbm"]) if hbm_gbs else None),
-                "peak_source": pk["src"] + (" (sustained bf16 cuBLAS)" if bound == "tensor" else " (copy)"),
-                "frac_of_burst": (tf / pk["tf_burst"]) if tf else None, "hbm_gbs": hbm_gbs, "launches_per_step": prof_launches,
-                "kernel_ms_per_step": prof_ns * 1e-6, "kernel_share_of_step": (prof_ns * 1e-6 / ms_step) if ms_step else None,
-                "traffic": None}
+        ix.profile(False)
+        nq_pad = (nq + 127) // 128 * 128
+        tf = 2.0 * nq_pad * n_local * D / (st["scoring_ns"] * 1e-9) / 1e12 if st["scoring_ns"] else None
+        search = {"metric": SEARCH_METRIC, "value": nq / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world, "ms_per_step": ms_step,
+                  "higher_is_better": True, "scaling": "strong", "dtype": "fp16 x fp16 -> fp32 (tcgen05) + fp64 rerank", "config": flat_cfg,
+                  "clocks": fclocks,
+                  "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * D * 4, "d2h_bytes_per_step": nq * k * 8,
+                          "ms_per_step": ms_e2e},
+                  "gpu_launches": launches,
+                  "roofline": {"kernel": "k_gemm_tn<256,FlatEpilogue> (all chunk launches of one step)", "bound": "tensor", "achieved": tf,
+                               "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"] if tf else None,
+                               "peak_source": pk["src"] + " (sustained bf16 cuBLAS)", "frac_of_burst": tf / pk["tf_burst"] if tf else None,
+                               "hbm_gbs": n_local * D * 2 / (st["scoring_ns"] * 1e-9) / 1e9 if st["scoring_ns"] else None,
+                               "launches_per_step": st["scoring_launches"], "kernel_ms_per_step": st["scoring_ns"] * 1e-6,
+                               "kernel_share_of_step": st["scoring_ns"] * 1e-6 / ms_step, "traffic": None},
+                  "search_stats": st}
+        if result:
+            result["search"] = search
+        else:
+            result = dict(search, steps=steps, warmup=warmup, vs_baseline=None, data="synthetic")
+        ix.close()
 
-    # ---- sanity inside the bench: a few result rows against the oracle on rank 0 would need the whole index on the
-    # host; parity is the test suite's job (tests/test_flat_gpu.py).  Here only: certificate/overflow counters.
     if rank == 0:
-        out = {"metric": METRIC, "value": nq / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-               "dtype": "fp16 x fp16 -> fp32 (tcgen05) + fp64 rerank", "data": "synthetic", "config": workload, "clocks": clocks,
-               "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * D * 4, "d2h_bytes_per_step": nq * k * 8,
-                       "ms_per_step": ms_e2e},
-               "gpu_launches": launches, "roofline": roofline, "search_stats": stats}
         if world == 1 and not args.no_cpu_baseline:
-            qps, dt, cores = cpu_reference_flat(rows_total, nq, k, 1, 1, args.cpu_sample_rows, args.cpu_sample_queries)
-            out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                                   "sample": f"{args.cpu_sample_queries} queries x {args.cpu_sample_rows}-row slice, scaled by rows to {rows_total}"}
-        print(json.dumps(out))
+            cores = os.cpu_count()
+            if "tower" in wl:
+                ips, dt, cores = cpu_reference_tower(args.cpu_sample_images, 1, 1)
+                result["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                                          "sample": f"{args.cpu_sample_images} images, full 27-block tower, transformers SiglipVisionModel fp32 "
+                                                    f"(stand-in for clip_server.py device=cpu; open_clip is not installable here)"}
+            if "flat" in wl:
+                qps, dt, cores = cpu_reference_flat(args.rows, args.k, 1, 1, args.cpu_sample_rows, args.cpu_sample_queries)
+                cb = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                      "sample": f"{args.cpu_sample_queries} queries x {args.cpu_sample_rows}-row slice, scaled by rows to {args.rows}"}
+                if "search" in result:
+                    result["search"]["cpu_baseline"] = cb
+                else:
+                    result["cpu_baseline"] = cb
+        print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
 

@@ -127,6 +127,11 @@ int mse_encode_text_ids_dev(mse_encoder *e, const int32_t *d_ids, int batch, uin
 /* per-layer parity hooks: token activations [batch*S][dim] fp16 after the embedding and the first n_blocks blocks */
 int mse_encode_images_hidden(mse_encoder *e, const uint8_t *rgb_hwc, int batch, int n_blocks, uint16_t *out_tokens_f16);
 int mse_encode_text_hidden(mse_encoder *e, const int32_t *ids, int batch, int n_blocks, uint16_t *out_tokens_f16);
+/* bracket every GEMM / attention launch with CUDA events on the launching stream (bench.py roofline) */
+int mse_encoder_profile(mse_encoder *e, int enable);
+/* last encode call (synchronises): out[0]=ns in GEMM kernels, out[1]=GEMM launches, out[2]=ns in attention kernels,
+ * out[3]=attention launches, out[4]=kernel launches, out[5]=algorithmic GEMM MFLOP (sum of 2*M*N*K) */
+int mse_encoder_stats(mse_encoder *e, uint64_t out[8]);
 void mse_encoder_destroy(mse_encoder *e);
 
 /* =====================================================================================

@@ -67,6 +67,8 @@ _SIGS = {
     "mse_encode_text_ids_dev": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "mse_encode_images_hidden": (_i32, [_vp, _vp, _i32, _i32, _vp]),
     "mse_encode_text_hidden": (_i32, [_vp, _vp, _i32, _i32, _vp]),
+    "mse_encoder_profile": (_i32, [_vp, _i32]),
+    "mse_encoder_stats": (_i32, [_vp, _vp]),
     "mse_encoder_destroy": (None, [_vp]),
     "mse_gemm_f16_tn": (_i32, [_i32, _vp, _vp, _u32, _u32, _u32, _vp, _i32, _vp]),
 }

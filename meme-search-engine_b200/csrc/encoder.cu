@@ -290,6 +290,13 @@ struct mse_encoder {
     int32_t *ids_dev = nullptr;
     cudaStream_t stream = nullptr;
     size_t max_tokens = 0;
+    // profiling (bench.py roofline): CUDA-event brackets around GEMM (class 0) and attention (class 1) launches
+    int profile = 0;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> ev_class;
+    size_t ev_used = 0;
+    uint64_t stats[8] = {0};
+    double gemm_flops = 0;
 };
 
 namespace {
@@ -365,8 +372,45 @@ int load_blocks(mse_encoder *e, const WeightFile &wf, TowerW &tw, int depth, boo
     return MSE_OK;
 }
 
+void prof_mark(mse_encoder *e, int cls, cudaStream_t st) {
+    if (!e->profile) return;
+    if (e->ev_used == e->ev.size()) {
+        cudaEvent_t x;
+        cudaEventCreate(&x);
+        e->ev.push_back(x);
+        e->ev_class.push_back(0);
+    }
+    e->ev_class[e->ev_used] = cls;
+    cudaEventRecord(e->ev[e->ev_used++], st);
+}
+
+void prof_begin(mse_encoder *e) {
+    e->ev_used = 0;
+    e->gemm_flops = 0;
+    memset(e->stats, 0, sizeof(e->stats));
+}
+
+void prof_collect(mse_encoder *e, uint64_t launches) {
+    e->stats[4] = launches;
+    if (!e->profile) return;
+    double ns[2] = {0, 0};
+    uint64_t cnt[2] = {0, 0};
+    for (size_t i = 0; i + 1 < e->ev_used; i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]) == cudaSuccess) {
+            ns[e->ev_class[i]] += (double)ms * 1e6;
+            cnt[e->ev_class[i]]++;
+        }
+    }
+    e->stats[0] = (uint64_t)ns[0]; e->stats[1] = cnt[0]; e->stats[2] = (uint64_t)ns[1]; e->stats[3] = cnt[1];
+    e->stats[5] = (uint64_t)(e->gemm_flops / 1e6);  // MFLOP, algorithmic (2*M*N*K, unpadded)
+}
+
 int gemm(mse_encoder *e, const __half *A, const __half *W, uint32_t M, uint32_t N, uint32_t K, __half *C, const float *bias, int act,
          const __half *res, uint32_t res_mod, cudaStream_t st) {
+    e->gemm_flops += 2.0 * M * N * (double)K;
+    prof_mark(e, 0, st);
+    struct Done { mse_encoder *e; cudaStream_t st; ~Done() { prof_mark(e, 0, st); } } done{e, st};
     GemmOut o{};
     o.c16 = C;
     o.ldc = N;
@@ -397,8 +441,10 @@ int run_blocks(mse_encoder *e, const TowerW &tw, int depth, uint32_t B, uint32_t
         const LayerW &L = tw.layers[l];
         MSE_CHECK(layernorm(e->x, e->xn, L.ln1_g, L.ln1_b, T, D, st));
         MSE_CHECK(gemm(e, e->xn, L.qkv_w, T, 3 * D, D, e->qkv, L.qkv_b, ACT_NONE, nullptr, 0, st));
+        prof_mark(e, 1, st);
         attn::k_mha_fwd<<<dim3((S + attn::kBM - 1) / attn::kBM, H, B), attn::kThreads, sizeof(attn::Smem), st>>>(e->qkv, e->att, (int)S, (int)H,
                                                                                                                    scale_log2e);
+        prof_mark(e, 1, st);
         MSE_LAUNCH_OK();
         MSE_CHECK(gemm(e, e->att, L.proj_w, T, D, D, e->x, L.proj_b, ACT_NONE, e->x, 0, st));
         MSE_CHECK(layernorm(e->x, e->xn, L.ln2_g, L.ln2_b, T, D, st));
@@ -459,6 +505,7 @@ MSE_API void mse_encoder_destroy(mse_encoder *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void *p : e->allocs) cudaFree(p);
+    for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -559,6 +606,22 @@ MSE_API int mse_encoder_create(const char *weights_path, int device, int max_bat
     return MSE_OK;
 }
 
+MSE_API int mse_encoder_profile(mse_encoder *e, int enable) {
+    MSE_REQUIRE(e != nullptr, MSE_ERR_INVALID, "encoder_profile: NULL handle");
+    e->profile = enable ? 1 : 0;
+    return MSE_OK;
+}
+
+// synchronises the device, then reports the last encode call
+MSE_API int mse_encoder_stats(mse_encoder *e, uint64_t out[8]) {
+    MSE_REQUIRE(e != nullptr && out != nullptr, MSE_ERR_INVALID, "encoder_stats: NULL argument");
+    MSE_CHECK(use_device(e->device));
+    MSE_CUDA(cudaDeviceSynchronize());
+    prof_collect(e, e->stats[4]);
+    memcpy(out, e->stats, sizeof(e->stats));
+    return MSE_OK;
+}
+
 MSE_API int mse_encoder_config(const mse_encoder *e, int32_t out[16]) {
     MSE_REQUIRE(e != nullptr && out != nullptr, MSE_ERR_INVALID, "encoder_config: NULL argument");
     memcpy(out, e->cfg, sizeof(e->cfg));
@@ -574,8 +637,11 @@ static int encode_images_impl(mse_encoder *e, const uint8_t *img, bool img_on_de
     if (batch == 0) return MSE_OK;
     MSE_CHECK(use_device(e->device));
     const size_t D = e->cfg[2], img_px = (size_t)e->cfg[0] * e->cfg[0] * 3, P = e->cfg[0] / e->cfg[1];
+    prof_begin(e);
+    const uint64_t l0 = g_launches.load();
     MSE_CUDA(cudaMemcpyAsync(e->img_dev, img, (size_t)batch * img_px, img_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     MSE_CHECK(vision_forward(e, (uint32_t)batch, layer_stop, st));
+    e->stats[4] = g_launches.load() - l0;
     if (layer_stop >= 0)
         MSE_CUDA(cudaMemcpyAsync(out, e->x, (size_t)batch * P * P * D * 2, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
     else
@@ -593,8 +659,11 @@ static int encode_text_impl(mse_encoder *e, const int32_t *ids, bool ids_on_devi
     if (batch == 0) return MSE_OK;
     MSE_CHECK(use_device(e->device));
     const size_t D = e->cfg[2], S = e->cfg[7];
+    prof_begin(e);
+    const uint64_t l0 = g_launches.load();
     MSE_CUDA(cudaMemcpyAsync(e->ids_dev, ids, (size_t)batch * S * 4, ids_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     MSE_CHECK(text_forward(e, (uint32_t)batch, layer_stop, st));
+    e->stats[4] = g_launches.load() - l0;
     if (layer_stop >= 0)
         MSE_CUDA(cudaMemcpyAsync(out, e->x, (size_t)batch * S * D * 2, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
     else

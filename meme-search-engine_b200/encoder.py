@@ -52,6 +52,15 @@ class Encoder:
     def encode_text_dev(self, ids_ptr: int, batch: int, out_ptr: int, stream: int = 0):
         check(lib().mse_encode_text_ids_dev(self._h, C.c_void_p(ids_ptr), batch, C.c_void_p(out_ptr), C.c_void_p(stream)), "mse_encode_text_ids_dev")
 
+    def profile(self, enable: bool = True):
+        check(lib().mse_encoder_profile(self._h, int(enable)), "mse_encoder_profile")
+
+    def stats(self) -> dict:
+        out = (C.c_uint64 * 8)()
+        check(lib().mse_encoder_stats(self._h, out), "mse_encoder_stats")
+        return {"gemm_ns": int(out[0]), "gemm_launches": int(out[1]), "attn_ns": int(out[2]), "attn_launches": int(out[3]),
+                "launches": int(out[4]), "gemm_mflop": int(out[5])}
+
     # per-layer parity hooks
     def image_hidden(self, images_u8: np.ndarray, n_blocks: int) -> np.ndarray:
         x = np.ascontiguousarray(images_u8, np.uint8)
