@@ -13,6 +13,8 @@
 #include "internal.h"
 #include "gemm_epilogues.cuh"
 #include "attention.cuh"
+#include "attention_tc.cuh"
+#include "gemm_sm100.cuh"
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -437,13 +439,34 @@ int run_blocks(mse_encoder *e, const TowerW &tw, int depth, uint32_t B, uint32_t
         attr_done = true;
     }
     const float scale_log2e = (1.0f / sqrtf((float)attn::kDH)) * 1.4426950408889634f;
+    // S >= 128: tcgen05 kernel (attention_tc.cuh); the 64-token text tower keeps the warp-level kernel (a 128-row tile would be half empty)
+    const bool use_tc = S >= 128 && getenv("MSE_ATTN_MMA_SYNC") == nullptr;
+    CUtensorMap tm64, tm16;
+    attn_tc::Params ap{};
+    if (use_tc) {
+        static bool tc_attr_done = false;
+        if (!tc_attr_done) {
+            MSE_CUDA(cudaFuncSetAttribute(attn_tc::k_mha_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc::kSmemBytes));
+            tc_attr_done = true;
+        }
+        MSE_CHECK(encode_tmap_3d(&tm64, e->qkv, attn::kDH, 3 * H, (uint64_t)T, attn::kDH * 2, (uint64_t)3 * D * 2, 64, attn_tc::kBM, 128));
+        MSE_CHECK(encode_tmap_3d(&tm16, e->qkv, attn::kDH, 3 * H, (uint64_t)T, attn::kDH * 2, (uint64_t)3 * D * 2, 16, attn_tc::kBM, 32));
+        ap.S = (int)S; ap.H = (int)H; ap.B = (int)B;
+        ap.q_items = (int)((S + 2 * attn_tc::kBM - 1) / (2 * attn_tc::kBM));
+        ap.n_blocks = (int)((S + attn_tc::kBN - 1) / attn_tc::kBN);
+        ap.n_items = (int)(B * H) * ap.q_items;
+        ap.scale_log2e = scale_log2e;
+    }
     for (int l = 0; l < depth; l++) {
         const LayerW &L = tw.layers[l];
         MSE_CHECK(layernorm(e->x, e->xn, L.ln1_g, L.ln1_b, T, D, st));
         MSE_CHECK(gemm(e, e->xn, L.qkv_w, T, 3 * D, D, e->qkv, L.qkv_b, ACT_NONE, nullptr, 0, st));
         prof_mark(e, 1, st);
-        attn::k_mha_fwd<<<dim3((S + attn::kBM - 1) / attn::kBM, H, B), attn::kThreads, sizeof(attn::Smem), st>>>(e->qkv, e->att, (int)S, (int)H,
-                                                                                                                   scale_log2e);
+        if (use_tc)
+            attn_tc::k_mha_tc<<<std::min(ap.n_items, sm_count(e->device)), attn_tc::kThreads, attn_tc::kSmemBytes, st>>>(tm64, tm16, e->att, ap);
+        else
+            attn::k_mha_fwd<<<dim3((S + attn::kBM - 1) / attn::kBM, H, B), attn::kThreads, sizeof(attn::Smem), st>>>(e->qkv, e->att, (int)S, (int)H,
+                                                                                                                       scale_log2e);
         prof_mark(e, 1, st);
         MSE_LAUNCH_OK();
         MSE_CHECK(gemm(e, e->att, L.proj_w, T, D, D, e->x, L.proj_b, ACT_NONE, e->x, 0, st));

@@ -6,7 +6,7 @@
 //   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage into one of two
 //               TMEM accumulators (2 x BN columns), frees the stage with tcgen05.commit -> empty[stage],
 //               and publishes the finished tile with tcgen05.commit -> tmem_full[acc]
-//   warps 2..5  epilogue: warp w may touch TMEM lanes 32*(w%4)..+31; each thread owns one output row,
+//   warps 2..9  epilogue: warp w may touch TMEM lanes 32*(w%4)..+31 (two warps per quadrant split the columns); each thread owns one output row,
 //               pulls 32 fp32 columns at a time with tcgen05.ld.32x32b.x32 and hands them to the Epilogue
 //               functor; the accumulator is released with tmem_empty[acc] so the next tile's MMAs overlap
 //
@@ -20,7 +20,8 @@ namespace mse {
 
 static constexpr int kGemmBM = 128;
 static constexpr int kGemmBK = 64;
-static constexpr int kGemmThreads = 192;
+static constexpr int kGemmEpiWarps = 8;   // two warps per TMEM lane quadrant, each draining half of the tile's columns
+static constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
 
 template <int BN>
 struct GemmCfg {
@@ -72,7 +73,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&tfull[a], 1);
-            ptx::mbar_init(&tempty[a], 4);  // one arrive per epilogue warp
+            ptx::mbar_init(&tempty[a], kGemmEpiWarps);  // one arrive per epilogue warp
         }
         ptx::fence_barrier_init();
     }
@@ -128,6 +129,9 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else {
         const uint32_t quad = warp & 3;
+        const uint32_t part = (uint32_t)(warp - 2) >> 2;                     // which slice of the columns this warp drains
+        constexpr uint32_t kChunks = BN / 32, kParts = kGemmEpiWarps / 4;
+        const uint32_t c_begin = part * kChunks / kParts, c_end = (part + 1) * kChunks / kParts;
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             uint32_t mt, nt;
@@ -138,7 +142,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t taddr = tmem_base + ((quad * 32) << 16) + acc * BN;
             epi.begin_tile(row, nt * BN);
 #pragma unroll 1
-            for (uint32_t c = 0; c < BN / 32; c++) {
+            for (uint32_t c = c_begin; c < c_end; c++) {
                 uint32_t v[32];
                 ptx::tmem_ld_32x32(taddr + c * 32, v);
                 ptx::tmem_ld_wait();
@@ -161,5 +165,8 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 // host: encode a 2D K-major tensor map (rows x K elements of 2 bytes), box = 64 x box_rows, SWIZZLE_128B
 int encode_tmap_2d(CUtensorMap *out, const void *base, uint64_t rows, uint64_t k, uint64_t row_stride_elems, uint32_t box_rows);
+
+int encode_tmap_3d(CUtensorMap *out, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                   uint64_t stride2_bytes, uint32_t b0, uint32_t b2, int swizzle);
 
 }  // namespace mse
