@@ -133,6 +133,8 @@ int mse_encoder_profile(mse_encoder *e, int enable);
  * out[3]=attention launches, out[4]=kernel launches, out[5]=algorithmic GEMM MFLOP (sum of 2*M*N*K) */
 int mse_encoder_stats(mse_encoder *e, uint64_t out[8]);
 void mse_encoder_destroy(mse_encoder *e);
+/* profiling aid, not part of the reference surface: average time (ms) of the attention kernel alone on random data */
+int mse_debug_attention(int device, int batch, int seq, int mode, int iters, float *ms_out);
 
 /* =====================================================================================
  * Dense GEMM building block (tcgen05 + TMA): C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]), fp16 in, fp32 accumulate

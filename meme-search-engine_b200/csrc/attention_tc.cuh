@@ -92,6 +92,7 @@ struct Params {
     int n_blocks;       // ceil(S / 128) key blocks
     int n_items;        // B * H * q_items
     float scale_log2e;
+    int debug;          // profiling only: 1 skip ex2, 2 skip P stores, 4 skip PV MMAs, 8 skip S MMAs, 16 skip K/V TMA loads
 };
 
 // tm64: box {64, 1, 128} SWIZZLE_128B; tm16: box {16, 1, 128} SWIZZLE_32B; both over qkv viewed as [B*S][3H][72]
@@ -152,6 +153,7 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                 for (int j = 0; j < nb; j++, kv_n++) {
                     const uint32_t st = kv_n % kKVStages, ph = (kv_n / kKVStages) & 1;
                     ptx::mbar_wait(&kv_empty[st], ph ^ 1);
+                    if (p.debug & 16) { ptx::mbar_arrive(&kv_full[st]); continue; }
                     ptx::mbar_expect_tx(&kv_full[st], kKVBytes);
                     uint8_t *kv = smem + kOffKV + st * kKVBytes;
                     const int key0 = tok0 + j * kBN;
@@ -188,9 +190,11 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                 ptx::mbar_wait(&s_empty[t], (bn & 1) ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t k_lo = kv_lo0 + st * (kKVBytes >> 4);
+                if (!(p.debug & 8)) {
 #pragma unroll
                 for (uint32_t k = 0; k < 4; k++) ptx::umma_f16(d_s, d64(q_lo + 2 * k, kHi128), d64(k_lo + 2 * k, kHi128), idesc_s, k != 0);
                 ptx::umma_f16(d_s, d64(q2_lo, kHi32), d64(k_lo + (kT64 >> 4), kHi32), idesc_s, 1u);
+                }
                 ptx::umma_commit(&s_full[t]);
             };
             // O_t += P_t(block) V(block): accumulates in TMEM across the key blocks of an item
@@ -200,6 +204,7 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                 if (first_block) ptx::mbar_wait(&o_empty[t], (itn & 1) ^ 1);  // previous item's output has been read out
                 ptx::tc_fence_after();
                 const uint32_t v_lo = kv_lo0 + st * (kKVBytes >> 4) + ((kT64 + kT16) >> 4), v2_lo = v_lo + (kT64 >> 4);
+                if (!(p.debug & 4))
 #pragma unroll
                 for (uint32_t ks = 0; ks < kBN / 16; ks++) {
                     const uint64_t pa = d64(p_lo + (ks >> 2) * (kT64 >> 4) + 2 * (ks & 3), kHi128);
@@ -273,12 +278,27 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                 }
                 const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
                 const bool grow = m_blk > m_ref + 8.0f;  // also true on the first block (m_ref = -inf)
+                const float f = grow ? ex2_approx(m_ref - m_blk) : 1.0f;  // rescale of O and l if the reference moves
+                if (grow) m_ref = m_blk;
+                const float neg_m = -m_ref;
+                // all 128 exponentials first, packed to fp16 in registers: none of this needs the P buffer or O, so it
+                // overlaps the P V MMAs of the previous block
+                uint32_t pk[kBN / 2];
+                float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < kBN / 2; i++) {
+                    float p0 = fmaf(__uint_as_float(v[2 * i]), sc, neg_m), p1 = fmaf(__uint_as_float(v[2 * i + 1]), sc, neg_m);
+                    if (!(p.debug & 1)) { p0 = ex2_approx(p0); p1 = ex2_approx(p1); }
+                    rs0 += p0;
+                    rs1 += p1;
+                    __half2 hh = __floats2half2_rn(p0, p1);
+                    pk[i] = *(uint32_t *)&hh;
+                }
                 if (j > 0) {
                     // P V of block j-1 must be complete before O is touched or the P buffer is overwritten
                     ptx::mbar_wait(&o_full[t], (bn - 1) & 1);
                     ptx::tc_fence_after();
                     if (__any_sync(0xffffffffu, grow)) {
-                        const float f = grow ? ex2_approx(m_ref - m_blk) : 1.0f;
                         uint32_t a[32], c2[32], d2[8];
                         ptx::tmem_ld_32x32(to, a);
                         ptx::tmem_ld_32x32(to + 32, c2);
@@ -294,33 +314,16 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                         tmem_st_32x32(to + 32, c2);
                         tmem_st_32x32_x8(to + 64, d2);
                         tmem_st_wait();
-                        l_run *= f;
                     }
                 }
-                if (grow) m_ref = m_blk;
-                const float neg_m = -m_ref;
-                float rs0 = 0.f, rs1 = 0.f;
+                l_run = fmaf(l_run, f, rs0 + rs1);
+                // 128 keys = 16 chunks of 8 halfs; chunk c8 lives in 64-key SW128 tile (c8 >> 3) at slot (c8 & 7) ^ (row & 7)
+                if (!(p.debug & 2))
 #pragma unroll
-                for (int c = 0; c < kBN / 32; c++) {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + 2 * i]), sc, neg_m));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + 2 * i + 1]), sc, neg_m));
-                        rs0 += p0;
-                        rs1 += p1;
-                        __half2 hh = __floats2half2_rn(p0, p1);
-                        pk[i] = *(uint32_t *)&hh;
-                    }
-                    // 32 keys = 4 chunks of 8 halfs; chunk index inside its 64-key SW128 tile: (c & 1) * 4 + q
-                    uint8_t *tile = pt + (c >> 1) * kT64;
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; q4++) {
-                        const uint32_t chunk = (uint32_t)((c & 1) * 4 + q4) ^ (row & 7);
-                        *(uint4 *)(tile + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-                    }
+                for (int c8 = 0; c8 < kBN / 8; c8++) {
+                    const uint32_t chunk = (uint32_t)(c8 & 7) ^ (row & 7);
+                    *(uint4 *)(pt + (c8 >> 3) * kT64 + chunk * 16) = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
                 }
-                l_run += rs0 + rs1;
                 // P written: make the generic-proxy stores (and the TMEM rescale) visible to the tensor core
                 ptx::tc_fence_before();
                 ptx::fence_proxy_async();

@@ -715,3 +715,44 @@ MSE_API int mse_encode_text_hidden(mse_encoder *e, const int32_t *ids, int batch
     MSE_REQUIRE(n_blocks >= 0, MSE_ERR_INVALID, "encode_text_hidden: n_blocks must be >= 0");
     return encode_text_impl(e, ids, false, batch, out_tokens_f16, false, n_blocks, e ? e->stream : nullptr);
 }
+
+// Profiling aid (not part of the reference surface): times the tcgen05 attention kernel alone on random data.
+// mode: attn_tc::Params::debug bits.  Returns the average kernel time in milliseconds.
+MSE_API int mse_debug_attention(int device, int B, int S, int mode, int iters, float *ms_out) {
+    MSE_CHECK(use_device(device));
+    const int H = 16, D = H * attn::kDH;
+    const size_t T = (size_t)B * S;
+    __half *qkv = nullptr, *out = nullptr;
+    MSE_CUDA(cudaMalloc(&qkv, T * 3 * D * 2));
+    MSE_CUDA(cudaMalloc(&out, T * D * 2));
+    std::vector<__half> h(T * 3 * D);
+    uint32_t x = 12345;
+    for (auto &v : h) { x = x * 1664525u + 1013904223u; v = __float2half(((int)(x >> 16) % 2001 - 1000) * 1e-3f); }
+    cudaMemcpy(qkv, h.data(), h.size() * 2, cudaMemcpyHostToDevice);
+    MSE_CUDA(cudaFuncSetAttribute(attn_tc::k_mha_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc::kSmemBytes));
+    CUtensorMap tm64, tm16;
+    MSE_CHECK(encode_tmap_3d(&tm64, qkv, attn::kDH, 3 * H, (uint64_t)T, attn::kDH * 2, (uint64_t)3 * D * 2, 64, attn_tc::kBM, 128));
+    MSE_CHECK(encode_tmap_3d(&tm16, qkv, attn::kDH, 3 * H, (uint64_t)T, attn::kDH * 2, (uint64_t)3 * D * 2, 16, attn_tc::kBM, 32));
+    attn_tc::Params ap{};
+    ap.S = S; ap.H = H; ap.B = B;
+    ap.q_items = (S + 2 * attn_tc::kBM - 1) / (2 * attn_tc::kBM);
+    ap.n_blocks = (S + attn_tc::kBN - 1) / attn_tc::kBN;
+    ap.n_items = B * H * ap.q_items;
+    ap.scale_log2e = (1.0f / sqrtf((float)attn::kDH)) * 1.4426950408889634f;
+    ap.debug = mode;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = std::min(ap.n_items, sm_count(device));
+    for (int i = 0; i < 2; i++) attn_tc::k_mha_tc<<<grid, attn_tc::kThreads, attn_tc::kSmemBytes>>>(tm64, tm16, out, ap);
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; i++) attn_tc::k_mha_tc<<<grid, attn_tc::kThreads, attn_tc::kSmemBytes>>>(tm64, tm16, out, ap);
+    cudaEventRecord(e1);
+    cudaError_t err = cudaDeviceSynchronize();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(qkv); cudaFree(out);
+    MSE_REQUIRE(err == cudaSuccess, MSE_ERR_CUDA, "debug_attention: %s", cudaGetErrorString(err));
+    *ms_out = ms / iters;
+    return MSE_OK;
+}
