@@ -103,6 +103,83 @@ int mse_merge_topk_dev(int device, const uint32_t *d_ids, const float *d_scores,
                        uint32_t k, uint32_t *d_out_ids, float *d_out_scores, void *stream);
 
 /* =====================================================================================
+ * Graph index -- the diskann crate's build/search entry points (diskann/src/lib.rs) and the packed-index search of
+ * src/query_disk_index.rs, batched over queries.  All of it is bit-exact against the CPU restatement given the same
+ * graph: ids, i64 scores and distance counters.
+ * ===================================================================================== */
+
+/* IndexBuildConfig (diskann/src/lib.rs:41-51); alpha / query_alpha are fixed-point x 2^16 */
+typedef struct mse_build_config {
+    uint64_t r, l, maxc;
+    int64_t alpha;
+    int32_t saturate_graph;
+    uint32_t query_breakpoint; /* ids >= this are query nodes (OOD-DiskANN); 0xFFFFFFFF = none */
+    uint64_t max_add_per_stitch_iter;
+    int64_t query_alpha;
+} mse_build_config;
+
+/* IndexGraph (lib.rs:16-39) as fixed-stride adjacency adj[n][stride] + deg[n]; `N.shard.bin` + offsets
+ * (generate_index_shard.rs:143-153) is the CSR form of the same lists */
+int mse_index_set_graph(mse_index *ix, const uint32_t *adj, const uint32_t *deg, uint32_t stride);
+int mse_index_get_graph(const mse_index *ix, uint32_t *adj, uint32_t *deg, uint32_t *stride_out);
+/* index.pq-codes.bin / index.descriptor-codes.bin (query_disk_index.rs:686-709) and `url.len() > 0` flags (:172) */
+int mse_index_set_pq_codes(mse_index *ix, const uint8_t *codes, uint32_t code_size);
+int mse_index_set_descriptors(mse_index *ix, const uint8_t *desc, uint32_t n_desc, const uint8_t *has_url);
+
+/* greedy_search (lib.rs:183-211) for nq queries: results are scratch.neighbour_buffer.ids (+ scores) [nq][L], best first,
+ * MSE_ID_NONE past len[q]; distances[q] = GreedySearchCounters.distances.  starts may be NULL (all start at `start`).
+ * visited_* (optional, [nq][visited_cap]) return scratch.visited_list in evaluation order. */
+int mse_search_graph(mse_index *ix, const uint16_t *q_f16, uint32_t nq, uint32_t L, const uint32_t *starts, uint32_t start,
+                     int base_vectors_only, uint32_t query_breakpoint, uint32_t *ids, int64_t *scores, uint32_t *len,
+                     uint64_t *distances, uint32_t *visited_ids, int64_t *visited_scores, uint32_t *visited_len,
+                     uint32_t visited_cap);
+/* greedy_search of query_disk_index.rs:144-212 (beam W, PQ ADC for candidates, exact score + descriptor bias for expanded
+ * nodes).  luts [nq][M*n_centroids] from mse_pq_preprocess_query; desc_scales [nq][n_desc] or NULL.  out_* [nq][out_cap]:
+ * expanded nodes in visit order with their exact scores (the caller sorts, :529); cmps / pq_cmps as :148-149. */
+int mse_search_beam(mse_index *ix, const uint16_t *q_f16, const float *luts, const float *desc_scales, uint32_t nq, uint32_t L,
+                    uint32_t W, const uint32_t *starts, uint32_t start, int disable_pq, uint32_t n_centroids, uint32_t *out_ids,
+                    int64_t *out_scores, uint32_t *out_len, uint32_t out_cap, uint64_t *cmps, uint64_t *pq_cmps);
+/* evaluator brute force (query_disk_index.rs:262-273): exact i64 score of one fp16 query against every row */
+int mse_scores_i64(mse_index *ix, const uint16_t *q_f16, int64_t *scores);
+
+/* robust_prune (lib.rs:227-285) of point p over explicit candidates; out holds <= cfg->r ids */
+int mse_robust_prune(mse_index *ix, uint32_t p, const uint32_t *cand_ids, const int64_t *cand_scores, uint32_t n_cand,
+                     const mse_build_config *cfg, uint32_t *out, uint32_t *out_len);
+/* IndexGraph::empty + random_fill_graph (lib.rs:22-31,376-387) */
+int mse_index_random_fill_graph(mse_index *ix, uint32_t r, uint64_t seed);
+/* medioid (lib.rs:54-68) */
+int mse_index_medioid(mse_index *ix, uint32_t *out);
+/* build_graph (lib.rs:287-324), batch-synchronous (see csrc/build.cu).  max_batch 0 = default.
+ * stats (optional, 4 values): batches, point searches, back-edge merges, distance evaluations of the searches */
+int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_build_config *cfg, uint64_t seed, uint32_t max_batch,
+                           uint64_t *stats);
+
+/* =====================================================================================
+ * Codecs -- ProductQuantizer (diskann/src/vector.rs:308-406, opq.msgpack from diskann/aopq_train.py:87-93) and the
+ * RabitQ experiment (diskann/rabitq.py:8-48, rabitq.msgpack :62-68)
+ * ===================================================================================== */
+typedef struct mse_pq mse_pq;
+int mse_pq_create(const float *centroids, const float *transform, uint32_t n_dims, uint32_t n_dims_per_code, uint32_t n_centroids,
+                  int device, mse_pq **out);
+int mse_pq_load(const uint8_t *msgpack, size_t len, int device, mse_pq **out); /* rmp_serde::from_slice::<ProductQuantizer> */
+int mse_pq_info(const mse_pq *pq, uint32_t out[4]);                            /* n_dims, n_dims_per_code, chunks, centroids */
+int mse_pq_apply_transform(mse_pq *pq, const float *x, uint64_t n, float *y);  /* vector.rs:319-329 */
+int mse_pq_encode(mse_pq *pq, const float *x, uint64_t n, uint8_t *codes);     /* quantize_batch :331-364 */
+int mse_pq_preprocess_query(mse_pq *pq, const float *q, uint32_t nq, float *lut); /* :367-384, lut [nq][chunks*centroids] */
+int mse_pq_adc(mse_pq *pq, const float *lut, const uint8_t *codes, uint64_t n, int64_t *scores); /* asymmetric_dot_product :387-405 */
+void mse_pq_destroy(mse_pq *pq);
+
+typedef struct mse_rabitq mse_rabitq;
+int mse_rabitq_create(const float *mean, const float *transform, uint32_t n_dims, uint32_t output_dims, int device, mse_rabitq **out);
+int mse_rabitq_load(const uint8_t *msgpack, size_t len, int device, mse_rabitq **out);
+/* quantize (rabitq.py:30-36): codes [n][output_dims/8] sign bits, norms [n] = |o - mean|, dots [n] = <o_bar, P o_hat> */
+int mse_rabitq_encode(mse_rabitq *r, const uint16_t *x_f16, uint64_t n, uint8_t *codes, float *norms, float *dots);
+/* approx_dot (rabitq.py:42-48) of one f32 query against n encoded vectors */
+int mse_rabitq_estimate(mse_rabitq *r, const float *q, const uint8_t *codes, const float *norms, const float *dots, uint64_t n,
+                        float *estimates);
+void mse_rabitq_destroy(mse_rabitq *r);
+
+/* =====================================================================================
  * Embedding towers -- clip_server.py (OpenCLIP ViT-SO400M-14-SigLIP-384, precision fp16)
  *   model creation            clip_server.py:23      -> mse_encoder_create
  *   preprocess + encode_image clip_server.py:140,114 -> mse_encode_images_u8   (u8 RGB HWC in, x/127.5-1 on device)

@@ -16,4 +16,5 @@ There is no CPU fallback anywhere in this package: every compute call goes to th
 from ._lib import MseError, build, check, lib, lib_path, last_error, launch_count, device_info  # noqa: F401
 from .flat import FlatIndex, merge_topk  # noqa: F401
 from .encoder import Encoder  # noqa: F401
+from . import diskann  # noqa: F401
 from . import weights  # noqa: F401

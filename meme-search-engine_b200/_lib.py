@@ -59,6 +59,30 @@ _SIGS = {
     "mse_search_flat_set_mode": (_i32, [_vp, _i32]),
     "mse_search_flat_profile": (_i32, [_vp, _i32]),
     "mse_merge_topk_dev": (_i32, [_i32, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "mse_index_set_graph": (_i32, [_vp, _vp, _vp, _u32]),
+    "mse_index_get_graph": (_i32, [_vp, _vp, _vp, _vp]),
+    "mse_index_set_pq_codes": (_i32, [_vp, _vp, _u32]),
+    "mse_index_set_descriptors": (_i32, [_vp, _vp, _u32, _vp]),
+    "mse_search_graph": (_i32, [_vp, _vp, _u32, _u32, _vp, _u32, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32]),
+    "mse_search_beam": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _u32, _i32, _u32, _vp, _vp, _vp, _u32, _vp, _vp]),
+    "mse_scores_i64": (_i32, [_vp, _vp, _vp]),
+    "mse_robust_prune": (_i32, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
+    "mse_index_random_fill_graph": (_i32, [_vp, _u32, _u64]),
+    "mse_index_medioid": (_i32, [_vp, _vp]),
+    "mse_index_build_vamana": (_i32, [_vp, _u32, _vp, _u64, _u32, _vp]),
+    "mse_pq_create": (_i32, [_vp, _vp, _u32, _u32, _u32, _i32, C.POINTER(_vp)]),
+    "mse_pq_load": (_i32, [_vp, C.c_size_t, _i32, C.POINTER(_vp)]),
+    "mse_pq_info": (_i32, [_vp, _vp]),
+    "mse_pq_apply_transform": (_i32, [_vp, _vp, _u64, _vp]),
+    "mse_pq_encode": (_i32, [_vp, _vp, _u64, _vp]),
+    "mse_pq_preprocess_query": (_i32, [_vp, _vp, _u32, _vp]),
+    "mse_pq_adc": (_i32, [_vp, _vp, _vp, _u64, _vp]),
+    "mse_pq_destroy": (None, [_vp]),
+    "mse_rabitq_create": (_i32, [_vp, _vp, _u32, _u32, _i32, C.POINTER(_vp)]),
+    "mse_rabitq_load": (_i32, [_vp, C.c_size_t, _i32, C.POINTER(_vp)]),
+    "mse_rabitq_encode": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp]),
+    "mse_rabitq_estimate": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "mse_rabitq_destroy": (None, [_vp]),
     "mse_encoder_create": (_i32, [C.c_char_p, _i32, _i32, C.POINTER(_vp)]),
     "mse_encoder_config": (_i32, [_vp, _vp]),
     "mse_encode_images_u8": (_i32, [_vp, _vp, _i32, _vp]),

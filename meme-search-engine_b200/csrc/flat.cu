@@ -704,6 +704,11 @@ MSE_API void mse_index_destroy(mse_index *ix) {
     for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);
     if (ix->x) cudaFree(ix->x);
     if (ix->max_norm) cudaFree(ix->max_norm);
+    if (ix->adj) cudaFree(ix->adj);
+    if (ix->deg) cudaFree(ix->deg);
+    if (ix->pq_codes) cudaFree(ix->pq_codes);
+    if (ix->desc) cudaFree(ix->desc);
+    if (ix->has_url) cudaFree(ix->has_url);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }

@@ -1,0 +1,614 @@
+// Vamana graph search on the GPU, batched over queries, bit-exact against the reference's sequential semantics.
+//
+//   k_greedy_search   diskann/src/lib.rs:183-211  (in-memory greedy_search, beam 1, exact fast_dot scores)
+//                     + NeighbourBuffer diskann/src/lib.rs:73-155
+//   k_beam_search     src/query_disk_index.rs:83-97,135-212 (beam-W search over the packed index: PQ ADC for frontier
+//                     candidates, exact fp16 dot + descriptor bias for expanded nodes; results = expanded nodes)
+//   k_brute_force_i64 src/query_disk_index.rs:262-273 (exact i64 scores of every node)
+//
+// One persistent CTA works on one query at a time.  The vectors, adjacency, PQ codes and descriptors live in HBM (the
+// reference reads 4 KiB node records from NVMe through io_uring: query_disk_index.rs:73-81); every hop gathers <= R rows of
+// 2304 B (exact) or 64 B codes (ADC).  All eight warps score candidates (one warp per row, fast_dot.cuh); warp 0 then
+// replays the reference's NeighbourBuffer inserts in the reference's order, so ids, i64 scores and distance counters match
+// the CPU oracle bit for bit.  The reference's HashSet<u32> is an open-addressing table in global memory (exact membership).
+#include "graph.cuh"
+#include "fastdot.cuh"
+#include <algorithm>
+
+namespace mse {
+
+static constexpr int kGsThreads = 256;
+static constexpr int kGsWarps = kGsThreads / 32;
+static constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+static constexpr int kMaxDeg = 256;   // largest adjacency list handled per expansion (merged graphs reach 2R = 128)
+
+struct NbView {
+    uint32_t *ids;
+    long long *scores;
+    uint8_t *vis;
+    int len, cap, nu;  // nu: next_unvisited or -1
+};
+
+// ---- NeighbourBuffer (lib.rs:73-155), executed by ONE warp; state scalars are kept uniform across the warp
+
+__device__ __forceinline__ void nb_insert(NbView &b, uint32_t id, long long score, int lane) {
+    if (b.cap == 0) return;
+    if (b.len == b.cap && b.scores[b.len - 1] > score) return;                     // :118
+    int g = 0, e = 0;                                                              // binary_search_by on the descending list
+    for (int i = lane; i < b.len; i += 32) {
+        long long s = b.scores[i];
+        g += s > score;
+        e += s == score;
+    }
+    for (int o = 16; o; o >>= 1) {
+        g += __shfl_xor_sync(0xffffffffu, g, o);
+        e += __shfl_xor_sync(0xffffffffu, e, o);
+    }
+    const int loc = e > 0 ? g + e - 1 : g;                                         // Ok(last equal) / Err(insertion point)
+    if (loc < b.len && b.ids[loc] == id) return;                                   // :127
+    // insert at loc, truncate to cap (:132-137): shift [loc, len) right by one, chunks from the top down
+    for (int c = (b.len - 1) >> 5; b.len > 0 && c >= (loc >> 5); c--) {
+        const int i = (c << 5) + lane;
+        const bool mv = i >= loc && i < b.len && i + 1 < b.cap;
+        uint32_t ti = 0; long long ts = 0; uint8_t tv = 0;
+        if (mv) { ti = b.ids[i]; ts = b.scores[i]; tv = b.vis[i]; }
+        __syncwarp();
+        if (mv) { b.ids[i + 1] = ti; b.scores[i + 1] = ts; b.vis[i + 1] = tv; }
+        __syncwarp();
+    }
+    if (lane == 0) { b.ids[loc] = id; b.scores[loc] = score; b.vis[loc] = 0; }
+    __syncwarp();
+    b.len = min(b.len + 1, b.cap);
+    b.nu = b.nu < 0 ? loc : min(loc, b.nu);                                        // :139-146
+}
+
+// lib.rs:93-107; returns the id or kEmpty when nothing is unvisited
+__device__ __forceinline__ uint32_t nb_next_unvisited(NbView &b, int lane) {
+    if (b.nu < 0) return kEmpty;
+    const int old = b.nu;
+    if (lane == 0) b.vis[old] = 1;
+    __syncwarp();
+    int cur = old;
+    for (;;) {  // first index >= old that is unvisited
+        const int i = cur + lane;
+        const bool unv = i < b.len && !b.vis[i];
+        const unsigned m = __ballot_sync(0xffffffffu, unv);
+        if (m) { cur += __ffs(m) - 1; break; }
+        cur += 32;
+        if (cur >= b.len) { cur = b.len; break; }
+    }
+    b.nu = cur >= b.len ? -1 : cur;
+    return b.ids[old];
+}
+
+// ---- HashSet<u32>::insert: true when newly inserted.  Open addressing, linear probing, capacity a power of two.
+__device__ __forceinline__ bool hs_insert(uint32_t *tab, uint32_t mask, uint32_t key, uint32_t *fill) {
+    uint32_t h = (key * 2654435761u) & mask;
+    for (uint32_t probes = 0; probes <= mask; probes++) {
+        const uint32_t old = atomicCAS(&tab[h], kEmpty, key);
+        if (old == kEmpty) { atomicAdd(fill, 1u); return true; }
+        if (old == key) return false;
+        h = (h + 1) & mask;
+    }
+    return false;  // table full: caller checks *fill against the capacity
+}
+
+// shared-memory layout helper
+struct GsSmem {
+    long long *nb_scores;
+    uint32_t *nb_ids;
+    uint8_t *nb_vis;
+    float *q;               // query as fp32 (exact fp16 values)
+    uint32_t *pre;          // candidate ids of the current expansion
+    long long *pre_scores;
+    uint32_t *raw;          // raw adjacency list of the expanded node
+    int *ctl;               // [0] n_pre  [1] pt  [2] scratch
+};
+
+__device__ __forceinline__ GsSmem carve(uint8_t *base, uint32_t L, uint32_t d) {
+    GsSmem s;
+    size_t o = 0;
+    s.nb_scores = (long long *)(base + o); o += (size_t)(L + 1) * 8;
+    s.pre_scores = (long long *)(base + o); o += (size_t)kMaxDeg * 8;
+    s.nb_ids = (uint32_t *)(base + o); o += (size_t)(L + 1) * 4;
+    s.pre = (uint32_t *)(base + o); o += (size_t)kMaxDeg * 4;
+    s.raw = (uint32_t *)(base + o); o += (size_t)kMaxDeg * 4;
+    s.q = (float *)(base + o); o += (size_t)d * 4;
+    s.ctl = (int *)(base + o); o += 16 * 4;
+    s.nb_vis = (uint8_t *)(base + o);
+    return s;
+}
+__host__ __device__ static size_t gs_smem_bytes(uint32_t L, uint32_t d) {
+    return (size_t)(L + 1) * 8 + kMaxDeg * 8 + (size_t)(L + 1) * 4 + kMaxDeg * 4 + kMaxDeg * 4 + (size_t)d * 4 + 64 + (L + 1) + 64;
+}
+
+// exact fast_dot of the shared-memory query against one row; whole warp, bit-identical to vector.rs:192-306
+__device__ __forceinline__ long long score_row(const float *q, const __half *row, uint32_t d, int lane) {
+    float p = 0.f;
+    for (uint32_t c = lane; c < d; c += 32) p = fmaf(q[c], __half2float(row[c]), p);
+    return fast_dot_fix(fast_dot_reduce(p));
+}
+
+// expanded node's out-neighbours -> s.pre (first occurrence of every not-yet-seen id, in list order), returns the count.
+// filter_from: ids >= filter_from are dropped AFTER being marked seen (lib.rs:196-199 base_vectors_only)
+__device__ __forceinline__ int collect_new_neighbours(const GraphArgs &g, GsSmem &s, uint32_t pt, uint32_t *htab, uint32_t hmask,
+                                                      uint32_t *hfill, uint32_t filter_from, int n_pre0) {
+    const uint32_t dg = min(g.deg[pt], (uint32_t)kMaxDeg);
+    const uint32_t *nbrs = g.adj + (size_t)pt * g.stride;
+    for (uint32_t i = threadIdx.x; i < dg; i += blockDim.x) s.raw[i] = nbrs[i];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int n_pre = n_pre0;
+        for (uint32_t base = 0; base < dg; base += 32) {
+            const uint32_t i = base + lane;
+            bool fresh = false;
+            uint32_t id = 0;
+            if (i < dg) {
+                id = s.raw[i];
+                bool dup = false;
+                for (uint32_t j = 0; j < i; j++) dup |= s.raw[j] == id;     // an earlier copy in this list wins
+                if (!dup) fresh = hs_insert(htab, hmask, id, hfill) && id < filter_from;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, fresh);
+            if (fresh) s.pre[n_pre + __popc(m & ((1u << lane) - 1))] = id;
+            n_pre += __popc(m);
+        }
+        if (lane == 0) s.ctl[0] = n_pre;
+    }
+    __syncthreads();
+    return s.ctl[0];
+}
+
+// ------------------------------------------------------------------ in-memory greedy search (lib.rs:183-211)
+
+__global__ void __launch_bounds__(kGsThreads) k_greedy_search(GraphArgs g, const __half *__restrict__ queries, const uint32_t *__restrict__ q_rows, uint32_t nq,
+                                                              const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L,
+                                                              uint32_t filter_from, uint32_t *htabs, uint32_t hcap, GreedyOut out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    GsSmem s = carve(smem_raw, L, g.d);
+    uint32_t *htab = htabs + (size_t)blockIdx.x * hcap;
+    const uint32_t hmask = hcap - 1;
+    __shared__ uint32_t hfill;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (uint32_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < hcap; i += blockDim.x) htab[i] = kEmpty;
+        const size_t qrow = q_rows ? q_rows[qi] : qi;
+        for (uint32_t i = threadIdx.x; i < g.d; i += blockDim.x) s.q[i] = __half2float(queries[qrow * g.d + i]);
+        if (threadIdx.x == 0) hfill = 0;
+        __syncthreads();
+        NbView nb{s.nb_ids, s.nb_scores, s.nb_vis, 0, (int)L, -1};
+        const uint32_t start = starts ? starts[qi] : start_all;
+        unsigned long long distances = 0;
+        uint32_t n_eval = 0;
+        if (warp == 0) {
+            const long long sc = score_row(s.q, g.x + (size_t)start * g.d, g.d, lane);
+            nb_insert(nb, start, sc, lane);                                          // :188
+            if (lane == 0) hs_insert(htab, hmask, start, &hfill);                    // :189
+        }
+        __syncthreads();
+        for (;;) {
+            if (warp == 0) {
+                const uint32_t pt = nb_next_unvisited(nb, lane);
+                if (lane == 0) s.ctl[1] = (int)pt;
+            }
+            __syncthreads();
+            const uint32_t pt = (uint32_t)s.ctl[1];
+            if (pt == kEmpty || hfill * 4 > hcap * 3) break;
+            const int n_pre = collect_new_neighbours(g, s, pt, htab, hmask, &hfill, filter_from, 0);
+            for (int i = warp; i < n_pre; i += kGsWarps) {                           // :201-204, one warp per row
+                const long long sc = score_row(s.q, g.x + (size_t)s.pre[i] * g.d, g.d, lane);
+                if (lane == 0) s.pre_scores[i] = sc;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // rows that cannot enter a full buffer are rejected exactly as :118 would (the tail score only grows)
+                const bool full0 = nb.len == nb.cap;
+                const long long last0 = full0 ? nb.scores[nb.len - 1] : 0;
+                for (int i = 0; i < n_pre; i++) {
+                    const long long sc = s.pre_scores[i];
+                    if (!(full0 && last0 > sc)) nb_insert(nb, s.pre[i], sc, lane);
+                }
+                if (out.vl_ids) {
+                    for (int i = lane; i < n_pre; i += 32) {
+                        const uint32_t slot = n_eval + i;
+                        if (slot < out.vl_cap) {
+                            out.vl_ids[(size_t)qi * out.vl_cap + slot] = s.pre[i];
+                            out.vl_scores[(size_t)qi * out.vl_cap + slot] = s.pre_scores[i];
+                        }
+                    }
+                }
+                n_eval += n_pre;
+                distances += n_pre;
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            for (uint32_t i = lane; i < L; i += 32) {
+                out.ids[(size_t)qi * L + i] = (int)i < nb.len ? nb.ids[i] : kEmpty;
+                out.scores[(size_t)qi * L + i] = (int)i < nb.len ? nb.scores[i] : 0;
+            }
+            if (lane == 0) {
+                out.len[qi] = nb.len;
+                out.distances[qi] = distances;
+                if (out.vl_len) out.vl_len[qi] = n_eval;
+                out.status[qi] = (hfill * 4 > hcap * 3) ? 1u : 0u;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ beam search over the packed index (query_disk_index.rs:144-212)
+
+struct BeamArgs {
+    const uint8_t *codes;     // [n][M] PQ codes
+    uint32_t M, C;            // chunks per code, centroids per chunk (LUT is [M][C] f32)
+    const uint8_t *desc;      // [n][n_desc] or NULL
+    const uint8_t *has_url;   // [n] or NULL: query_disk_index.rs:172 `node.url.len() > 0`
+    uint32_t n_desc;
+    int disable_pq;
+};
+struct BeamOut {
+    uint32_t *ids;            // [nq][cap] expanded-and-recorded nodes in visit order
+    long long *scores;        // [nq][cap] exact scores
+    uint32_t *len;            // [nq]
+    uint32_t cap;
+    unsigned long long *cmps, *pq_cmps;  // [nq]
+    uint32_t *status;
+};
+
+// descriptor_product (query_disk_index.rs:135-142): sum_j trunc(scale_j * code_j * 2^32)
+__device__ __forceinline__ long long descriptor_product(const BeamArgs &b, const float *scales, uint32_t id) {
+    long long r = 0;
+    for (uint32_t j = 0; j < b.n_desc; j++) r += fast_dot_fix(scales[j] * (float)b.desc[(size_t)id * b.n_desc + j]);
+    return r;
+}
+
+__global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArgs ba, const __half *__restrict__ queries,
+                                                            const float *__restrict__ luts, const float *__restrict__ desc_scales,
+                                                            uint32_t nq, const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L,
+                                                            uint32_t W, uint32_t *htabs, uint32_t hcap, BeamOut out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    GsSmem s = carve(smem_raw, L, g.d);
+    float *lut = (float *)(smem_raw + ((gs_smem_bytes(L, g.d) + 15) & ~(size_t)15));
+    // two exact sets like the reference: visited_adjacent (seen as a neighbour) and visited (expanded)
+    uint32_t *hadj = htabs + (size_t)blockIdx.x * 2 * hcap, *hvis = hadj + hcap;
+    const uint32_t hmask = hcap - 1;
+    __shared__ uint32_t fill_adj, fill_vis;
+    __shared__ uint32_t pts[64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lut_n = ba.M * ba.C;
+
+    for (uint32_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < 2 * hcap; i += blockDim.x) hadj[i] = kEmpty;
+        for (uint32_t i = threadIdx.x; i < g.d; i += blockDim.x) s.q[i] = __half2float(queries[(size_t)qi * g.d + i]);
+        for (uint32_t i = threadIdx.x; i < lut_n; i += blockDim.x) lut[i] = luts[(size_t)qi * lut_n + i];
+        if (threadIdx.x == 0) { fill_adj = 0; fill_vis = 0; }
+        __syncthreads();
+        const float *scales = desc_scales ? desc_scales + (size_t)qi * ba.n_desc : nullptr;
+        NbView nb{s.nb_ids, s.nb_scores, s.nb_vis, 0, (int)L, -1};
+        const uint32_t start = starts ? starts[qi] : start_all;
+        unsigned long long cmps = 0, pq_cmps = 0;
+        uint32_t n_out = 0;
+        if (warp == 0) {
+            nb_insert(nb, start, 0, lane);                                           // :153 seeds with score 0
+            if (lane == 0) hs_insert(hadj, hmask, start, &fill_adj);
+        }
+        __syncthreads();
+        for (;;) {
+            if (warp == 0) {                                                         // next_several_unvisited :83-97
+                uint32_t np = 0;
+                while (np < W) {
+                    const uint32_t pt = nb_next_unvisited(nb, lane);
+                    if (pt == kEmpty) break;
+                    if (lane == 0) pts[np] = pt;
+                    np++;
+                }
+                if (lane == 0) s.ctl[2] = (int)np;
+            }
+            __syncthreads();
+            const uint32_t np = (uint32_t)s.ctl[2];
+            if (np == 0 || fill_adj * 4 > hcap * 3) break;
+            for (uint32_t b = 0; b < np; b++) {
+                const uint32_t id = pts[b];
+                // exact score of the expanded node (+ descriptor bias) :169-170
+                if (warp == 0) {
+                    long long sc = score_row(s.q, g.x + (size_t)id * g.d, g.d, lane);
+                    if (ba.n_desc) sc += descriptor_product(ba, scales, id);
+                    if (lane == 0) {
+                        cmps++;
+                        if (hs_insert(hvis, hmask, id, &fill_vis) && (!ba.has_url || ba.has_url[id])) {  // :172
+                            if (n_out < out.cap) {
+                                out.ids[(size_t)qi * out.cap + n_out] = id;
+                                out.scores[(size_t)qi * out.cap + n_out] = sc;
+                            }
+                            n_out++;
+                        }
+                    }
+                    n_out = __shfl_sync(0xffffffffu, n_out, 0);
+                }
+                // new neighbours -> ADC (or exact) -> inserts.  The pre-buffer is cleared per expanded node; the reference
+                // clears it once per beam iteration (:157), which only re-scores earlier nodes' neighbours
+                const int n_pre = collect_new_neighbours(g, s, id, hadj, hmask, &fill_adj, 0xFFFFFFFFu, 0);
+                if (ba.disable_pq) {
+                    for (int i = warp; i < n_pre; i += kGsWarps) {
+                        long long sc = score_row(s.q, g.x + (size_t)s.pre[i] * g.d, g.d, lane);
+                        if (lane == 0) s.pre_scores[i] = sc;
+                    }
+                } else {
+                    for (int i = threadIdx.x; i < n_pre; i += blockDim.x) {        // asymmetric_dot_product vector.rs:387-405
+                        const uint8_t *code = ba.codes + (size_t)s.pre[i] * ba.M;
+                        float acc = 0.f;
+                        for (uint32_t m = 0; m < ba.M; m++) acc += lut[m * ba.C + code[m]];  // f32, chunk order
+                        s.pre_scores[i] = fast_dot_fix(acc);
+                    }
+                }
+                __syncthreads();
+                if (ba.n_desc) {
+                    for (int i = threadIdx.x; i < n_pre; i += blockDim.x) s.pre_scores[i] += descriptor_product(ba, scales, s.pre[i]);
+                    __syncthreads();
+                }
+                if (warp == 0) {
+                    const bool full0 = nb.len == nb.cap;
+                    const long long last0 = full0 ? nb.scores[nb.len - 1] : 0;
+                    for (int i = 0; i < n_pre; i++) {
+                        const long long sc = s.pre_scores[i];
+                        if (!(full0 && last0 > sc)) nb_insert(nb, s.pre[i], sc, lane);
+                    }
+                    if (!ba.disable_pq) pq_cmps += n_pre;
+                }
+                __syncthreads();
+            }
+        }
+        if (warp == 0 && lane == 0) {
+            out.len[qi] = n_out;
+            out.cmps[qi] = cmps;
+            out.pq_cmps[qi] = pq_cmps;
+            out.status[qi] = (fill_adj * 4 > hcap * 3) ? 1u : 0u;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ evaluator brute force (query_disk_index.rs:262-273)
+
+__global__ void __launch_bounds__(256) k_scores_i64(const __half *__restrict__ x, uint64_t n, uint32_t d, const __half *__restrict__ q,
+                                                    long long *__restrict__ out) {
+    extern __shared__ float sq[];
+    for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) sq[i] = __half2float(q[i]);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < n; r += nw) {
+        const long long sc = score_row(sq, x + r * d, d, lane);
+        if (lane == 0) out[r] = sc;
+    }
+}
+
+uint32_t greedy_hash_capacity(uint32_t L, uint32_t stride) {
+    uint64_t v = (uint64_t)(L > 64 ? L : 64) * stride * 8;
+    uint32_t p = 1024;
+    while (p < v && p < (1u << 30)) p <<= 1;
+    return p;
+}
+uint32_t greedy_grid(const mse_index *ix, uint32_t nq) { return std::min<uint32_t>(nq, (uint32_t)sm_count(ix->device) * 2); }
+
+int greedy_search_launch(mse_index *ix, const __half *d_queries, const uint32_t *d_q_rows, uint32_t nq, const uint32_t *d_starts,
+                         uint32_t start, uint32_t L, uint32_t filter_from, uint32_t *d_htabs, uint32_t hcap, uint32_t grid, GreedyOut o,
+                         cudaStream_t st) {
+    const size_t smem = gs_smem_bytes(L, ix->d);
+    MSE_REQUIRE(smem <= 200 * 1024, MSE_ERR_UNSUPPORTED, "greedy_search: L=%u does not fit shared memory", L);
+    MSE_CUDA(cudaFuncSetAttribute(k_greedy_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GraphArgs g{ix->x, ix->adj, ix->deg, ix->graph_stride, ix->d, ix->n};
+    k_greedy_search<<<grid, kGsThreads, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, d_htabs, hcap, o);
+    MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
+}  // namespace mse
+
+using namespace mse;
+
+// ================================================================== C ABI
+
+static int require_graph(const mse_index *ix, const char *who) {
+    MSE_REQUIRE(ix != nullptr, MSE_ERR_INVALID, "%s: NULL handle", who);
+    MSE_REQUIRE(ix->adj != nullptr && ix->deg != nullptr, MSE_ERR_STATE, "%s: the index has no graph (mse_index_set_graph / mse_index_build_vamana first)", who);
+    MSE_REQUIRE(ix->d % 64 == 0, MSE_ERR_UNSUPPORTED, "%s: fast_dot needs d %% 64 == 0 (vector.rs:197), d=%u", who, ix->d);
+    return MSE_OK;
+}
+
+static uint32_t pow2_at_least(uint64_t v) {
+    uint32_t p = 1024;
+    while (p < v && p < (1u << 30)) p <<= 1;
+    return p;
+}
+
+MSE_API int mse_index_set_graph(mse_index *ix, const uint32_t *adj, const uint32_t *deg, uint32_t stride) {
+    MSE_REQUIRE(ix != nullptr && adj != nullptr && deg != nullptr && stride >= 1, MSE_ERR_INVALID, "index_set_graph: bad argument");
+    MSE_REQUIRE(stride <= (uint32_t)kMaxDeg, MSE_ERR_UNSUPPORTED, "index_set_graph: stride %u exceeds %d", stride, kMaxDeg);
+    MSE_CHECK(use_device(ix->device));
+    if (ix->adj) cudaFree(ix->adj);
+    if (ix->deg) cudaFree(ix->deg);
+    ix->adj = nullptr; ix->deg = nullptr;
+    MSE_CUDA(cudaMalloc(&ix->adj, std::max<size_t>(ix->n * stride * 4, 16)));
+    MSE_CUDA(cudaMalloc(&ix->deg, std::max<size_t>(ix->n * 4, 16)));
+    MSE_CUDA(cudaMemcpy(ix->adj, adj, ix->n * stride * 4, cudaMemcpyHostToDevice));
+    MSE_CUDA(cudaMemcpy(ix->deg, deg, ix->n * 4, cudaMemcpyHostToDevice));
+    ix->graph_stride = stride;
+    return MSE_OK;
+}
+
+MSE_API int mse_index_get_graph(const mse_index *ix, uint32_t *adj, uint32_t *deg, uint32_t *stride_out) {
+    MSE_CHECK(require_graph(ix, "index_get_graph"));
+    MSE_CHECK(use_device(ix->device));
+    if (stride_out) *stride_out = ix->graph_stride;
+    if (adj) MSE_CUDA(cudaMemcpy(adj, ix->adj, ix->n * ix->graph_stride * 4, cudaMemcpyDeviceToHost));
+    if (deg) MSE_CUDA(cudaMemcpy(deg, ix->deg, ix->n * 4, cudaMemcpyDeviceToHost));
+    return MSE_OK;
+}
+
+MSE_API int mse_index_set_pq_codes(mse_index *ix, const uint8_t *codes, uint32_t code_size) {
+    MSE_REQUIRE(ix != nullptr && codes != nullptr && code_size >= 1, MSE_ERR_INVALID, "index_set_pq_codes: bad argument");
+    MSE_CHECK(use_device(ix->device));
+    if (ix->pq_codes) cudaFree(ix->pq_codes);
+    ix->pq_codes = nullptr;
+    MSE_CUDA(cudaMalloc(&ix->pq_codes, std::max<size_t>(ix->n * code_size, 16)));
+    MSE_CUDA(cudaMemcpy(ix->pq_codes, codes, ix->n * code_size, cudaMemcpyHostToDevice));
+    ix->code_size = code_size;
+    return MSE_OK;
+}
+
+MSE_API int mse_index_set_descriptors(mse_index *ix, const uint8_t *desc, uint32_t n_desc, const uint8_t *has_url) {
+    MSE_REQUIRE(ix != nullptr, MSE_ERR_INVALID, "index_set_descriptors: NULL handle");
+    MSE_CHECK(use_device(ix->device));
+    if (ix->desc) cudaFree(ix->desc);
+    if (ix->has_url) cudaFree(ix->has_url);
+    ix->desc = nullptr; ix->has_url = nullptr; ix->n_desc = 0;
+    if (desc && n_desc) {
+        MSE_CUDA(cudaMalloc(&ix->desc, std::max<size_t>(ix->n * n_desc, 16)));
+        MSE_CUDA(cudaMemcpy(ix->desc, desc, ix->n * n_desc, cudaMemcpyHostToDevice));
+        ix->n_desc = n_desc;
+    }
+    if (has_url) {
+        MSE_CUDA(cudaMalloc(&ix->has_url, std::max<size_t>(ix->n, 16)));
+        MSE_CUDA(cudaMemcpy(ix->has_url, has_url, ix->n, cudaMemcpyHostToDevice));
+    }
+    return MSE_OK;
+}
+
+// greedy_search (lib.rs:183-211) for nq queries.  Host pointers.  ids/scores: [nq][L]; len/distances/status: [nq].
+// starts may be NULL (every query starts at `start`).  base_vectors_only + query_breakpoint as lib.rs:196-197.
+// visited_*: optional visited_list outputs ([nq][visited_cap]) -- what build_graph feeds to robust_prune.
+MSE_API int mse_search_graph(mse_index *ix, const uint16_t *q_f16, uint32_t nq, uint32_t L, const uint32_t *starts, uint32_t start,
+                             int base_vectors_only, uint32_t query_breakpoint, uint32_t *ids, int64_t *scores, uint32_t *len,
+                             uint64_t *distances, uint32_t *visited_ids, int64_t *visited_scores, uint32_t *visited_len,
+                             uint32_t visited_cap) {
+    MSE_CHECK(require_graph(ix, "search_graph"));
+    MSE_REQUIRE(q_f16 && ids && scores && len && distances, MSE_ERR_INVALID, "search_graph: NULL buffer");
+    MSE_REQUIRE(L >= 1 && L <= 4096, MSE_ERR_UNSUPPORTED, "search_graph: L=%u out of range [1,4096]", L);
+    if (nq == 0) return MSE_OK;
+    MSE_CHECK(use_device(ix->device));
+    const uint32_t grid = greedy_grid(ix, nq);
+    const uint32_t hcap = greedy_hash_capacity(L, ix->graph_stride);
+    DevBuf b_q, b_ids, b_sc, b_len, b_dist, b_st, b_h, b_starts, b_vi, b_vs, b_vl;
+    int rc = MSE_OK;
+    std::vector<uint32_t> status(nq);
+    do {
+        if ((rc = b_q.ensure((size_t)nq * ix->d * 2)) || (rc = b_ids.ensure((size_t)nq * L * 4)) || (rc = b_sc.ensure((size_t)nq * L * 8)) ||
+            (rc = b_len.ensure((size_t)nq * 4)) || (rc = b_dist.ensure((size_t)nq * 8)) || (rc = b_st.ensure((size_t)nq * 4)) ||
+            (rc = b_h.ensure((size_t)grid * hcap * 4)))
+            break;
+        if (starts && (rc = b_starts.ensure((size_t)nq * 4))) break;
+        const bool want_vl = visited_ids && visited_scores && visited_len && visited_cap;
+        if (want_vl && ((rc = b_vi.ensure((size_t)nq * visited_cap * 4)) || (rc = b_vs.ensure((size_t)nq * visited_cap * 8)) ||
+                        (rc = b_vl.ensure((size_t)nq * 4))))
+            break;
+        cudaMemcpy(b_q.p, q_f16, (size_t)nq * ix->d * 2, cudaMemcpyHostToDevice);
+        if (starts) cudaMemcpy(b_starts.p, starts, (size_t)nq * 4, cudaMemcpyHostToDevice);
+        GreedyOut o{b_ids.as<uint32_t>(), b_sc.as<long long>(), b_len.as<uint32_t>(), b_dist.as<unsigned long long>(),
+                    want_vl ? b_vi.as<uint32_t>() : nullptr, want_vl ? b_vs.as<long long>() : nullptr, want_vl ? b_vl.as<uint32_t>() : nullptr,
+                    want_vl ? visited_cap : 0, b_st.as<uint32_t>()};
+        if ((rc = greedy_search_launch(ix, b_q.as<__half>(), nullptr, nq, starts ? b_starts.as<uint32_t>() : nullptr, start, L,
+                                       base_vectors_only ? query_breakpoint : 0xFFFFFFFFu, b_h.as<uint32_t>(), hcap, grid, o, nullptr)))
+            break;
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { set_error("search_graph: %s", cudaGetErrorString(e)); rc = MSE_ERR_CUDA; break; }
+        cudaMemcpy(ids, b_ids.p, (size_t)nq * L * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(scores, b_sc.p, (size_t)nq * L * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(len, b_len.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(distances, b_dist.p, (size_t)nq * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(status.data(), b_st.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
+        if (want_vl) {
+            cudaMemcpy(visited_ids, b_vi.p, (size_t)nq * visited_cap * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(visited_scores, b_vs.p, (size_t)nq * visited_cap * 8, cudaMemcpyDeviceToHost);
+            cudaMemcpy(visited_len, b_vl.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
+        }
+        for (uint32_t i = 0; i < nq; i++)
+            if (status[i]) { set_error("search_graph: visited-set table overflowed for query %u (L=%u too large for the table)", i, L); rc = MSE_ERR_UNSUPPORTED; break; }
+    } while (0);
+    b_q.release(); b_ids.release(); b_sc.release(); b_len.release(); b_dist.release(); b_st.release(); b_h.release(); b_starts.release();
+    b_vi.release(); b_vs.release(); b_vl.release();
+    return rc;
+}
+
+// Beam search over the packed index (query_disk_index.rs:144-212).  luts: [nq][M*C] f32 from mse_pq_preprocess_query;
+// desc_scales: [nq][n_desc] or NULL.  out_ids/out_scores: [nq][out_cap] expanded nodes in visit order (the caller sorts by
+// score as :529 does); out_len/cmps/pq_cmps: [nq].
+MSE_API int mse_search_beam(mse_index *ix, const uint16_t *q_f16, const float *luts, const float *desc_scales, uint32_t nq, uint32_t L,
+                            uint32_t W, const uint32_t *starts, uint32_t start, int disable_pq, uint32_t n_centroids, uint32_t *out_ids,
+                            int64_t *out_scores, uint32_t *out_len, uint32_t out_cap, uint64_t *cmps, uint64_t *pq_cmps) {
+    MSE_CHECK(require_graph(ix, "search_beam"));
+    MSE_REQUIRE(q_f16 && out_ids && out_scores && out_len && cmps && pq_cmps && out_cap >= 1, MSE_ERR_INVALID, "search_beam: NULL buffer");
+    MSE_REQUIRE(disable_pq || (ix->pq_codes && luts && n_centroids), MSE_ERR_STATE, "search_beam: PQ codes / LUTs missing (mse_index_set_pq_codes)");
+    MSE_REQUIRE(L >= 1 && L <= 4096 && W >= 1 && W <= 64, MSE_ERR_UNSUPPORTED, "search_beam: L=%u W=%u out of range", L, W);
+    MSE_REQUIRE(!ix->n_desc || desc_scales, MSE_ERR_INVALID, "search_beam: the index has descriptors but desc_scales is NULL");
+    if (nq == 0) return MSE_OK;
+    MSE_CHECK(use_device(ix->device));
+    const uint32_t M = ix->code_size, C = n_centroids;
+    const size_t lut_bytes = disable_pq ? 16 : (size_t)M * C * 4;
+    const size_t smem = ((gs_smem_bytes(L, ix->d) + 15) & ~(size_t)15) + lut_bytes;
+    MSE_REQUIRE(smem <= 220 * 1024, MSE_ERR_UNSUPPORTED, "search_beam: L=%u with a %zu-byte LUT does not fit shared memory", L, lut_bytes);
+    MSE_CUDA(cudaFuncSetAttribute(k_beam_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t grid = std::min<uint32_t>(nq, (uint32_t)sm_count(ix->device) * 2);
+    const uint32_t hcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * ix->graph_stride * 8);
+    DevBuf b_q, b_lut, b_ds, b_ids, b_sc, b_len, b_c, b_p, b_st, b_h, b_starts;
+    int rc = MSE_OK;
+    std::vector<uint32_t> status(nq);
+    do {
+        if ((rc = b_q.ensure((size_t)nq * ix->d * 2)) || (rc = b_lut.ensure(std::max<size_t>((size_t)nq * M * C * 4, 16))) ||
+            (rc = b_ids.ensure((size_t)nq * out_cap * 4)) || (rc = b_sc.ensure((size_t)nq * out_cap * 8)) || (rc = b_len.ensure((size_t)nq * 4)) ||
+            (rc = b_c.ensure((size_t)nq * 8)) || (rc = b_p.ensure((size_t)nq * 8)) || (rc = b_st.ensure((size_t)nq * 4)) ||
+            (rc = b_h.ensure((size_t)grid * 2 * hcap * 4)))
+            break;
+        if (starts && (rc = b_starts.ensure((size_t)nq * 4))) break;
+        if (ix->n_desc && (rc = b_ds.ensure((size_t)nq * ix->n_desc * 4))) break;
+        cudaMemcpy(b_q.p, q_f16, (size_t)nq * ix->d * 2, cudaMemcpyHostToDevice);
+        if (!disable_pq) cudaMemcpy(b_lut.p, luts, (size_t)nq * M * C * 4, cudaMemcpyHostToDevice);
+        if (starts) cudaMemcpy(b_starts.p, starts, (size_t)nq * 4, cudaMemcpyHostToDevice);
+        if (ix->n_desc) cudaMemcpy(b_ds.p, desc_scales, (size_t)nq * ix->n_desc * 4, cudaMemcpyHostToDevice);
+        GraphArgs g{ix->x, ix->adj, ix->deg, ix->graph_stride, ix->d, ix->n};
+        BeamArgs ba{ix->pq_codes, M, C, ix->desc, ix->has_url, ix->n_desc, disable_pq};
+        BeamOut o{b_ids.as<uint32_t>(), b_sc.as<long long>(), b_len.as<uint32_t>(), out_cap, b_c.as<unsigned long long>(),
+                  b_p.as<unsigned long long>(), b_st.as<uint32_t>()};
+        k_beam_search<<<grid, kGsThreads, smem>>>(g, ba, b_q.as<__half>(), b_lut.as<float>(), ix->n_desc ? b_ds.as<float>() : nullptr, nq,
+                                                 starts ? b_starts.as<uint32_t>() : nullptr, start, L, W, b_h.as<uint32_t>(), hcap, o);
+        count_launch();
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { set_error("search_beam: %s", cudaGetErrorString(e)); rc = MSE_ERR_CUDA; break; }
+        cudaMemcpy(out_ids, b_ids.p, (size_t)nq * out_cap * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(out_scores, b_sc.p, (size_t)nq * out_cap * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(out_len, b_len.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(cmps, b_c.p, (size_t)nq * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(pq_cmps, b_p.p, (size_t)nq * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(status.data(), b_st.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
+        for (uint32_t i = 0; i < nq; i++)
+            if (status[i]) { set_error("search_beam: visited-set table overflowed for query %u", i); rc = MSE_ERR_UNSUPPORTED; break; }
+    } while (0);
+    b_q.release(); b_lut.release(); b_ds.release(); b_ids.release(); b_sc.release(); b_len.release(); b_c.release(); b_p.release();
+    b_st.release(); b_h.release(); b_starts.release();
+    return rc;
+}
+
+// exact i64 scores of one fp16 query against every row of the index (query_disk_index.rs:262-273 without the sort)
+MSE_API int mse_scores_i64(mse_index *ix, const uint16_t *q_f16, int64_t *scores) {
+    MSE_REQUIRE(ix != nullptr && q_f16 && scores, MSE_ERR_INVALID, "scores_i64: NULL argument");
+    MSE_REQUIRE(ix->d % 64 == 0, MSE_ERR_UNSUPPORTED, "scores_i64: d %% 64 != 0");
+    if (ix->n == 0) return MSE_OK;
+    MSE_CHECK(use_device(ix->device));
+    DevBuf bq, bs;
+    int rc = MSE_OK;
+    do {
+        if ((rc = bq.ensure(ix->d * 2)) || (rc = bs.ensure(ix->n * 8))) break;
+        cudaMemcpy(bq.p, q_f16, ix->d * 2, cudaMemcpyHostToDevice);
+        uint32_t blocks = (uint32_t)std::min<uint64_t>((ix->n + 7) / 8, (uint64_t)sm_count(ix->device) * 8);
+        k_scores_i64<<<blocks, 256, ix->d * 4>>>(ix->x, ix->n, ix->d, bq.as<__half>(), bs.as<long long>());
+        count_launch();
+        cudaError_t e = cudaMemcpy(scores, bs.p, ix->n * 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("scores_i64: %s", cudaGetErrorString(e)); rc = MSE_ERR_CUDA; }
+    } while (0);
+    bq.release(); bs.release();
+    return rc;
+}

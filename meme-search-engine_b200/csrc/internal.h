@@ -36,6 +36,13 @@ struct mse_index {
     uint64_t cap = 0;    // rows allocated
     __half *x = nullptr; // [cap][d] fp16 rows in HBM
     float *max_norm = nullptr;  // device scalar: max_i |x_i|_2 (upper bound; feeds the certificate)
+    // graph + packed-index side arrays (IndexGraph lib.rs:16-39; index.pq-codes.bin / index.descriptor-codes.bin)
+    uint32_t *adj = nullptr, *deg = nullptr;   // fixed stride adjacency [n][graph_stride], degrees [n]
+    uint32_t graph_stride = 0;
+    uint8_t *pq_codes = nullptr;               // [n][code_size]
+    uint32_t code_size = 0;
+    uint8_t *desc = nullptr, *has_url = nullptr;  // [n][n_desc], [n]
+    uint32_t n_desc = 0;
     int flat_mode = 0;
     int profile = 0;                 // time the scoring kernels with CUDA events (bench.py roofline)
     std::vector<cudaEvent_t> prof_ev; // start/stop pairs, reused
