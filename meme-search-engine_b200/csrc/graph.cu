@@ -284,7 +284,8 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
     for (uint32_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
         for (uint32_t i = threadIdx.x; i < 2 * hcap; i += blockDim.x) hadj[i] = kEmpty;
         for (uint32_t i = threadIdx.x; i < g.d; i += blockDim.x) s.q[i] = __half2float(queries[(size_t)qi * g.d + i]);
-        for (uint32_t i = threadIdx.x; i < lut_n; i += blockDim.x) lut[i] = luts[(size_t)qi * lut_n + i];
+        if (!ba.disable_pq)
+            for (uint32_t i = threadIdx.x; i < lut_n; i += blockDim.x) lut[i] = luts[(size_t)qi * lut_n + i];
         if (threadIdx.x == 0) { fill_adj = 0; fill_vis = 0; }
         __syncthreads();
         const float *scales = desc_scales ? desc_scales + (size_t)qi * ba.n_desc : nullptr;
