@@ -339,8 +339,8 @@ def main():
         def flat_resident():
             ix.search_dev(q_dev.data_ptr(), nq, k, ids_dev.data_ptr(), sc_dev.data_ptr(), stream)
             if world > 1:
-                dist.all_gather_into_tensor(all_ids, ids_dev)
-                dist.all_gather_into_tensor(all_sc, sc_dev)
+                dist.all_gather_into_tensor(all_ids.view(-1, k), ids_dev)
+                dist.all_gather_into_tensor(all_sc.view(-1, k), sc_dev)
                 mse_b200.merge_topk(local_rank, all_ids.data_ptr(), all_sc.data_ptr(), world, nq, k, out_ids.data_ptr(), out_sc.data_ptr(), stream)
 
         def flat_e2e():

@@ -1,0 +1,129 @@
+"""CPU tests of the clip_server boundary (routes, msgpack shapes, error behaviour, metrics names) with a test double in place
+of the GPU towers, and of the query-assembly helpers."""
+import asyncio
+import base64
+import io
+
+import msgpack
+import numpy as np
+import pytest
+from prometheus_client import CollectorRegistry
+
+
+class FakeEncoder:
+    """Stands in for mse_b200.Encoder in CPU tests only: deterministic unit vectors, no model."""
+    image_size, dim, ctx = 384, 1152, 64
+
+    def encode_image(self, images):
+        assert images.dtype == np.uint8 and images.shape[1:] == (384, 384, 3)
+        f = np.stack([np.full(1152, float(im.mean()) + 1.0, np.float32) for im in images])
+        return (f / np.linalg.norm(f, axis=1, keepdims=True)).astype(np.float16)
+
+    def encode_text(self, ids):
+        assert ids.shape[1] == 64
+        f = np.stack([np.arange(1152, dtype=np.float32) + float(t.sum()) for t in ids])
+        return (f / np.linalg.norm(f, axis=1, keepdims=True)).astype(np.float16)
+
+
+class FakeTokenizer:
+    def __call__(self, texts):
+        out = np.ones((len(texts), 64), np.int32)
+        for i, t in enumerate(texts):
+            out[i, : len(t)] = [ord(c) % 100 + 2 for c in t][:64]
+        return out
+
+
+def _bmp(seed):
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    buf = io.BytesIO()
+    Image.fromarray(rng.integers(0, 256, (384, 384, 3), dtype=np.uint8)).save(buf, format="BMP")
+    return buf.getvalue()
+
+
+@pytest.fixture
+def server(mse):
+    from mse_b200.clip_server import ClipServer
+    cfg = {"device": "cuda:0", "model": "ViT-SO400M-14-SigLIP-384", "model_name": "siglip-so400m-14-384", "max_batch_size": 4, "port": 0}
+    s = ClipServer(cfg, encoder=FakeEncoder(), tokenizer=FakeTokenizer(), registry=CollectorRegistry())
+    s.start_threads()
+    yield s
+    s.stop_threads()
+
+
+def _run(server, coro_fn):
+    from aiohttp.test_utils import TestClient, TestServer
+
+    async def go():
+        async with TestClient(TestServer(server.app)) as client:
+            return await coro_fn(client)
+    return asyncio.new_event_loop().run_until_complete(go())
+
+
+def test_routes_and_wire_format(server):
+    async def scenario(c):
+        r = await c.get("/")
+        assert r.status == 204
+        r = await c.get("/config")
+        cfg = msgpack.loads(await r.read())
+        assert cfg == {"model": "ViT-SO400M-14-SigLIP-384", "batch": 4, "image_size": [384, 384], "embedding_size": 1152}
+        r = await c.post("/", data=msgpack.dumps({"images": [_bmp(1), _bmp(2)]}))
+        assert r.status == 200 and r.content_type == "application/msgpack"
+        out = msgpack.loads(await r.read())
+        assert len(out) == 2 and all(isinstance(x, bytes) and len(x) == 2304 for x in out)
+        v = np.frombuffer(out[0], "<f2").astype(np.float32)
+        assert abs(np.linalg.norm(v) - 1) < 2e-3
+        r = await c.post("/", data=msgpack.dumps({"text": ["a meme", "another"], "images": [_bmp(3)]}))  # text wins
+        out = msgpack.loads(await r.read())
+        assert r.status == 200 and len(out) == 2
+        r = await c.post("/", data=msgpack.dumps({"text": "bare string"}))  # src/get_embedding.py:21 sends a bare str
+        assert r.status == 200 and len(msgpack.loads(await r.read())) == 1
+        r = await c.get("/metrics")
+        m = (await r.read()).decode()
+        assert 'modelserver_total_items_total{modality="image",model="siglip-so400m-14-384"} 2.0' in m
+        assert "modelserver_inftime" in m and "modelserver_batchcount_total" in m
+    _run(server, scenario)
+
+
+def test_error_behaviour(server):
+    async def scenario(c):
+        r = await c.post("/", data=msgpack.dumps({"images": [_bmp(i) for i in range(5)]}))
+        assert r.status == 500 and msgpack.loads(await r.read()) == "max batch size is 4"       # clip_server.py:139
+        r = await c.post("/", data=msgpack.dumps({"text": ["x"] * 5}))
+        assert r.status == 500 and msgpack.loads(await r.read()) == "max batch size is 4"       # :136
+        r = await c.post("/", data=msgpack.dumps({"images": []}))
+        assert r.status == 500 and msgpack.loads(await r.read()) == "images or text required"   # :142
+        r = await c.post("/", data=msgpack.dumps({"images": [b"not an image"]}))
+        assert r.status == 500
+    _run(server, scenario)
+
+
+def test_cpu_device_is_refused(mse):
+    from mse_b200.clip_server import ClipServer
+    with pytest.raises(RuntimeError) as e:
+        ClipServer({"device": "cpu", "model": "m", "model_name": "m", "max_batch_size": 1, "port": 0, "model_path": "/nonexistent"},
+                   registry=CollectorRegistry())
+    assert "no CPU path" in str(e.value)
+
+
+def test_get_total_embedding_and_select_shard(mse):
+    from mse_b200.query import get_total_embedding, select_shard
+    rng = np.random.default_rng(0)
+    e_img = rng.standard_normal(1152).astype(np.float16)
+    e_txt = rng.standard_normal(1152).astype(np.float16)
+    raw = rng.standard_normal(1152).astype(np.float32)
+    pre = {"nsfw": rng.standard_normal(1152).astype(np.float32)}
+
+    def server(batch):
+        return [e_img.tobytes()] * len(batch["images"]) if "images" in batch else [e_txt.tobytes()] * len(batch["text"])
+
+    terms = [{"image": base64.b64encode(b"img").decode(), "weight": 0.5}, {"text": "cat"}, {"embedding": raw.tolist(), "weight": -2.0},
+             {"predefined_embedding": "nsfw", "weight": 0.25}, {"predefined_embedding": "missing"}]
+    got = get_total_embedding(terms, 1152, server, predefined_embeddings=pre)
+    want = raw * np.float32(-2.0) + pre["nsfw"] * np.float32(0.25) + e_img.astype(np.float32) * np.float32(0.5) + e_txt.astype(np.float32)
+    assert np.allclose(got, want, atol=1e-6)
+    assert abs(np.linalg.norm(got) - 1) > 0.1  # not renormalised (common.rs:215-274)
+    cents = [(rng.standard_normal(1152).astype(np.float32), 10 * i) for i in range(5)]
+    q = cents[3][0] * 2 + 0.01
+    assert select_shard(cents, q) == 3
+    assert select_shard([(cents[0][0], 1), (cents[0][0], 2)], q) == 1  # ties keep the last maximum
