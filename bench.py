@@ -220,6 +220,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("MSE_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)

@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(256) k_im2col_patch14(const uint8_t *__restric
     }
 }
 
-// LayerNorm over the last dim (D % 8 == 0, D <= 2048), fp32 statistics, one warp per row
+// LayerNorm over the last dim (D % 8 == 0, D <= 256 * NV), fp32 statistics, one warp per row; NV = 16-byte pieces per lane
+template <int NV>
 __global__ void __launch_bounds__(256) k_layernorm(const __half *__restrict__ x, __half *__restrict__ y, const float *__restrict__ g,
                                                    const float *__restrict__ bta, uint32_t rows, uint32_t D, float eps,
                                                    uint32_t in_stride, uint32_t in_offset) {
@@ -57,13 +58,19 @@ __global__ void __launch_bounds__(256) k_layernorm(const __half *__restrict__ x,
     if (row >= rows) return;
     const uint4 *xr = (const uint4 *)(x + (size_t)row * in_stride + in_offset);
     const uint32_t nv = D >> 3;
-    float v[8][8];
+    float v[NV][8];
     float s = 0.f;
+    uint4 raw[NV];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < NV; i++) {
+        uint32_t p = lane + 32 * i;
+        raw[i] = p < nv ? __ldg(xr + p) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
         uint32_t p = lane + 32 * i;
         if (p < nv) {
-            uint4 u = xr[p];
+            uint4 u = raw[i];
             const __half2 *h = (const __half2 *)&u;
 #pragma unroll
             for (int e = 0; e < 4; e++) {
@@ -77,7 +84,7 @@ __global__ void __launch_bounds__(256) k_layernorm(const __half *__restrict__ x,
     const float mean = s / (float)D;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < NV; i++) {
         uint32_t p = lane + 32 * i;
         if (p < nv) {
 #pragma unroll
@@ -88,7 +95,7 @@ __global__ void __launch_bounds__(256) k_layernorm(const __half *__restrict__ x,
     const float rstd = rsqrtf(q / (float)D + eps);
     uint4 *yr = (uint4 *)(y + (size_t)row * D);
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < NV; i++) {
         uint32_t p = lane + 32 * i;
         if (p < nv) {
             const float4 g0 = __ldg((const float4 *)(g + p * 8)), g1 = __ldg((const float4 *)(g + p * 8 + 4));
@@ -424,7 +431,8 @@ int gemm(mse_encoder *e, const __half *A, const __half *W, uint32_t M, uint32_t 
 }
 
 int layernorm(const __half *x, __half *y, const float *g, const float *b, uint32_t rows, uint32_t D, cudaStream_t st) {
-    k_layernorm<<<(rows * 32 + 255) / 256, 256, 0, st>>>(x, y, g, b, rows, D, 1e-6f, D, 0);
+    if (D <= 5 * 256) k_layernorm<5><<<(rows * 32 + 255) / 256, 256, 0, st>>>(x, y, g, b, rows, D, 1e-6f, D, 0);
+    else k_layernorm<8><<<(rows * 32 + 255) / 256, 256, 0, st>>>(x, y, g, b, rows, D, 1e-6f, D, 0);
     MSE_LAUNCH_OK();
     return MSE_OK;
 }

@@ -164,7 +164,10 @@ class ProductQuantizer:
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().mse_pq_destroy(self._h)
+            try:
+                lib().mse_pq_destroy(self._h)
+            except Exception:  # interpreter shutdown
+                pass
             self._h = C.c_void_p()
 
     __del__ = close
@@ -236,7 +239,10 @@ class RabitQ:
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().mse_rabitq_destroy(self._h)
+            try:
+                lib().mse_rabitq_destroy(self._h)
+            except Exception:
+                pass
             self._h = C.c_void_p()
 
     __del__ = close

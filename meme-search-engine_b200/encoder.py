@@ -23,7 +23,10 @@ class Encoder:
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().mse_encoder_destroy(self._h)
+            try:
+                lib().mse_encoder_destroy(self._h)
+            except Exception:  # interpreter shutdown
+                pass
             self._h = C.c_void_p()
 
     __del__ = close

@@ -34,7 +34,10 @@ class FlatIndex:
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().mse_index_destroy(self._h)
+            try:
+                lib().mse_index_destroy(self._h)
+            except Exception:  # interpreter shutdown
+                pass
             self._h = C.c_void_p()
 
     __del__ = close
