@@ -212,6 +212,7 @@ int mse_encoder_stats(mse_encoder *e, uint64_t out[8]);
 void mse_encoder_destroy(mse_encoder *e);
 /* profiling aid, not part of the reference surface: average time (ms) of the attention kernel alone on random data */
 int mse_debug_attention(int device, int batch, int seq, int mode, int iters, float *ms_out);
+int mse_debug_gemm(int device, uint32_t M, uint32_t N, uint32_t K, int bn, int mode, int iters, float *ms_out);
 
 /* =====================================================================================
  * Dense GEMM building block (tcgen05 + TMA): C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]), fp16 in, fp32 accumulate

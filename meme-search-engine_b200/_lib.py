@@ -94,6 +94,7 @@ _SIGS = {
     "mse_encoder_profile": (_i32, [_vp, _i32]),
     "mse_encoder_stats": (_i32, [_vp, _vp]),
     "mse_encoder_destroy": (None, [_vp]),
+    "mse_debug_gemm": (_i32, [_i32, _u32, _u32, _u32, _i32, _i32, _i32, _vp]),
     "mse_debug_attention": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp]),
     "mse_gemm_f16_tn": (_i32, [_i32, _vp, _vp, _u32, _u32, _u32, _vp, _i32, _vp]),
 }

@@ -16,6 +16,12 @@ namespace mse {
 static constexpr int kFlatBN = 256;
 
 struct FlatEpilogue {
+    static constexpr bool kTmaStore = false;
+    __device__ __forceinline__ void compute(uint32_t, uint32_t, uint32_t (&)[32]) {}
+    __device__ __forceinline__ const __half *staged_residual() const { return nullptr; }
+    __device__ __forceinline__ uint32_t ldc() const { return 0; }
+    __device__ __forceinline__ uint32_t rows() const { return 0; }
+    __device__ __forceinline__ uint32_t cols() const { return 0; }
     const float *thr;
     uint64_t *cand;
     uint32_t *count;
@@ -83,7 +89,7 @@ int flat_tc_score_chunk(mse_index *ix, uint32_t nq, uint64_t row0, uint64_t nrow
     epi.th = 0.f;
     const uint32_t ntiles = shp.tiles_m * shp.tiles_n;
     const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)sm_count(ix->device));
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmq, *(const CUtensorMap *)ix->tmap_x, shp, epi);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmq, *(const CUtensorMap *)ix->tmap_x, tmq, shp, epi);
     MSE_LAUNCH_OK();
     return MSE_OK;
 }

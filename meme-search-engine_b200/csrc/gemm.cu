@@ -5,22 +5,25 @@
 #include "gemm_sm100.cuh"
 #include "gemm_epilogues.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace mse {
 
 template <int BN, class Epi>
 static int launch_gemm(int device, const void *dA, const void *dB, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb,
                        Epi epi, cudaStream_t st) {
-    using Cfg = GemmCfg<BN>;
+    constexpr uint32_t kSmem = gemm_smem_bytes<BN, Epi>();
     auto kern = k_gemm_tn<BN, 0, Epi>;
     static bool attr_done = false;
     if (!attr_done) {
-        MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+        MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
         attr_done = true;
     }
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
     MSE_CHECK(encode_tmap_2d(&tmA, dA, M, K, lda, kGemmBM));
     MSE_CHECK(encode_tmap_2d(&tmB, dB, N, K, ldb, BN));
+    if (Epi::kTmaStore) MSE_CHECK(encode_tmap_2d(&tmC, epi.o.c16, M, N, epi.o.ldc, 32));  // per-warp 32-row slabs
+    else tmC = tmA;
     GemmShape shp;
     shp.M = M; shp.N = N; shp.K = K;
     shp.tiles_m = (M + kGemmBM - 1) / kGemmBM;
@@ -29,19 +32,42 @@ static int launch_gemm(int device, const void *dA, const void *dB, uint32_t M, u
     shp.a_row0 = 0; shp.b_row0 = 0;
     const uint32_t ntiles = shp.tiles_m * shp.tiles_n;
     const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)sm_count(device));
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, shp, epi);
+    kern<<<grid, kGemmThreads, kSmem, st>>>(tmA, tmB, tmC, shp, epi);
     MSE_LAUNCH_OK();
     return MSE_OK;
 }
+
+static int force_bn = 0;  // profiling only (mse_debug_gemm)
 
 int gemm_f16_tn_dev(int device, const __half *dA, const __half *dB, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb,
                     const GemmOut &out, cudaStream_t st) {
     MSE_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, MSE_ERR_UNSUPPORTED, "gemm: K, lda, ldb must be multiples of 8");
     MSE_REQUIRE(M > 0 && N > 0 && K > 0, MSE_ERR_INVALID, "gemm: empty shape");
+    // fp16 output with 16-byte aligned rows: 256-wide tiles, staged through shared memory and written by TMA
+    // (in-place residual -> TMA reduce-add).  Measured (tools/gemm_ablation.py): direct per-thread stores cost 25-50 %.
+    if (out.c16 && !out.c32 && out.ldc % 8 == 0 && ((uintptr_t)out.c16 & 15) == 0 && !out.debug_no_store && force_bn != 128 && force_bn != 192 &&
+        getenv("MSE_GEMM_DIRECT_STORE") == nullptr) {
+        LinearEpilogueT<true> e2;
+        e2.o = out;
+        e2.o.res_in_place = (out.res == out.c16 && out.res_mod == 0) ? 1 : 0;
+        e2.M = M;
+        e2.N = N;
+        // 192-wide tiles when they divide N with less padding (1152 = 6 x 192, 3456 = 18 x 192): padded columns are wasted
+        // MMAs, and the towers run against the board's power cap
+        const uint32_t w256 = (N + 255) / 256 * 256 - N, w192 = (N + 191) / 192 * 192 - N;
+        const char *bn_env = getenv("MSE_GEMM_BN");  // profiling only
+        const bool allow192 = !(bn_env && atoi(bn_env) == 256);
+        if (w192 < w256 && force_bn != 256 && allow192) return launch_gemm<192>(device, dA, dB, M, N, K, lda, ldb, e2, st);
+        return launch_gemm<256>(device, dA, dB, M, N, K, lda, ldb, e2, st);
+    }
     LinearEpilogue epi;
     epi.o = out;
+    epi.o.res_in_place = 0;
     epi.M = M;
     epi.N = N;
+    if (force_bn == 256) return launch_gemm<256>(device, dA, dB, M, N, K, lda, ldb, epi, st);
+    if (force_bn == 192) return launch_gemm<192>(device, dA, dB, M, N, K, lda, ldb, epi, st);
+    if (force_bn == 128) return launch_gemm<128>(device, dA, dB, M, N, K, lda, ldb, epi, st);
     // tile width: least padded columns wins, ties go to the wider tile (fewer A re-reads per flop)
     auto waste = [&](uint32_t bn) { return (N + bn - 1) / bn * bn - N; };
     uint32_t best = 256;
@@ -93,4 +119,45 @@ MSE_API int mse_gemm_f16_tn(int device, const uint16_t *a, const uint16_t *b, ui
     } while (0);
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dbias);
     return rc;
+}
+
+// Profiling aid (not part of the reference surface): average time (ms) of one fp16-output linear-layer GEMM on random data.
+// bn: 0 auto / 128 / 192 / 256; mode bit 0: skip the global stores, bit 1: + bias, bit 2: + erf GELU, bit 3: + residual
+MSE_API int mse_debug_gemm(int device, uint32_t M, uint32_t N, uint32_t K, int bn, int mode, int iters, float *ms_out) {
+    MSE_CHECK(use_device(device));
+    __half *dA = nullptr, *dB = nullptr, *dC = nullptr, *dR = nullptr;
+    float *dbias = nullptr;
+    MSE_CUDA(cudaMalloc(&dA, (size_t)M * K * 2));
+    MSE_CUDA(cudaMalloc(&dB, (size_t)N * K * 2));
+    MSE_CUDA(cudaMalloc(&dC, (size_t)M * N * 2));
+    MSE_CUDA(cudaMalloc(&dR, (size_t)M * N * 2));
+    MSE_CUDA(cudaMalloc(&dbias, (size_t)N * 4));
+    cudaMemset(dA, 0x11, (size_t)M * K * 2);
+    cudaMemset(dB, 0x11, (size_t)N * K * 2);
+    cudaMemset(dR, 0, (size_t)M * N * 2);
+    cudaMemset(dbias, 0, (size_t)N * 4);
+    GemmOut o{};
+    o.c16 = dC; o.ldc = N;
+    o.debug_no_store = mode & 1;
+    if (mode & 2) o.bias = dbias;
+    if (mode & 4) o.act = ACT_GELU_ERF;
+    if (mode & 8) o.res = dR;
+    force_bn = bn;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int rc = MSE_OK;
+    for (int i = 0; i < 2 && rc == MSE_OK; i++) rc = gemm_f16_tn_dev(device, dA, dB, M, N, K, K, K, o, nullptr);
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters && rc == MSE_OK; i++) rc = gemm_f16_tn_dev(device, dA, dB, M, N, K, K, K, o, nullptr);
+    cudaEventRecord(e1);
+    cudaError_t err = cudaDeviceSynchronize();
+    force_bn = 0;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dR); cudaFree(dbias);
+    MSE_CHECK(rc);
+    MSE_REQUIRE(err == cudaSuccess, MSE_ERR_CUDA, "debug_gemm: %s", cudaGetErrorString(err));
+    *ms_out = ms / iters;
+    return MSE_OK;
 }

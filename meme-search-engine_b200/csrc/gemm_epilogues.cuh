@@ -16,18 +16,79 @@ struct GemmOut {
     const __half *res;     // residual [res_rows][ldc] fp16 added after activation, or NULL
     uint32_t res_mod;      // residual row = row % res_mod (position embeddings); 0 = row
     int act;
+    int debug_no_store;    // profiling only: run the epilogue math but skip the global stores
+    int res_in_place;      // TMA-store path: residual == output buffer -> TMA reduce-add instead of a register add
 };
 
+// (a MUFU-based erf -- Abramowitz-Stegun 7.1.26, rcp + ex2 -- was measured 35 % SLOWER here than the FMA-only library erff: the
+// epilogue shares the 16/clk MUFU pipe across eight warps)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_tanh(float x) {
     const float k0 = 0.7978845608028654f, k1 = 0.044715f;
     return 0.5f * x * (1.0f + tanhf(k0 * (x + k1 * x * x * x)));
 }
 
-struct LinearEpilogue {
+template <bool TMA_STORE>
+struct LinearEpilogueT {
+    static constexpr bool kTmaStore = TMA_STORE;
     GemmOut o;
     uint32_t M, N;
     __device__ __forceinline__ void begin_tile(uint32_t, uint32_t) {}
+    // TMA-store path ------------------------------------------------------------------------------------------------------
+    // residual that equals the output buffer (x += linear(...)): staged through shared memory by the kernel
+    __device__ __forceinline__ const __half *staged_residual() const { return o.res_in_place ? o.res : nullptr; }
+    __device__ __forceinline__ uint32_t ldc() const { return o.ldc; }
+    __device__ __forceinline__ uint32_t rows() const { return M; }
+    __device__ __forceinline__ uint32_t cols() const { return N; }
+    // bias / activation / (position-embedding style residual) applied in place on 32 fp32 accumulators
+    __device__ __forceinline__ void compute(uint32_t row, uint32_t col0, uint32_t (&v)[32]) {
+        const bool fullc = col0 + 32 <= N;
+        if (o.bias) {
+            if (fullc) {
+                const float4 *b4 = (const float4 *)(o.bias + col0);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 b = __ldg(b4 + j);
+                    v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + b.x);
+                    v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+                    v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+                    v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (col0 + j < N) v[j] = __float_as_uint(__uint_as_float(v[j]) + o.bias[col0 + j]);
+            }
+        }
+        if (o.act == ACT_GELU_ERF) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = __float_as_uint(gelu_erf(__uint_as_float(v[j])));
+        } else if (o.act == ACT_GELU_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = __float_as_uint(gelu_tanh(__uint_as_float(v[j])));
+        }
+        if (o.res && !o.res_in_place && row < M) {
+            const uint32_t rr = o.res_mod ? row % o.res_mod : row;
+            const __half *rp = o.res + (size_t)rr * o.ldc + col0;
+            if (fullc && o.ldc % 8 == 0) {
+                const uint4 *r4 = (const uint4 *)rp;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint4 u = __ldg(r4 + j);
+                    const __half2 *h = (const __half2 *)&u;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float2 t = __half22float2(h[e]);
+                        v[8 * j + 2 * e] = __float_as_uint(__uint_as_float(v[8 * j + 2 * e]) + t.x);
+                        v[8 * j + 2 * e + 1] = __float_as_uint(__uint_as_float(v[8 * j + 2 * e + 1]) + t.y);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (col0 + j < N) v[j] = __float_as_uint(__uint_as_float(v[j]) + __half2float(rp[j]));
+            }
+        }
+    }
+    // direct-store path ---------------------------------------------------------------------------------------------------
     __device__ __forceinline__ void columns(uint32_t row, uint32_t col0, const uint32_t (&v)[32]) {
         if (row >= M || col0 >= N) return;
         float f[32];
@@ -76,6 +137,7 @@ struct LinearEpilogue {
                 for (int j = 0; j < 32; j++) if (col0 + j < N) f[j] += __half2float(rp[j]);
             }
         }
+        if (o.debug_no_store) { if (f[0] == 123456.789f) o.c16[0] = __float2half(f[1]); return; }
         if (o.c16) {
             __half *cp = o.c16 + (size_t)row * o.ldc + col0;
             if (full) {
@@ -106,6 +168,8 @@ struct LinearEpilogue {
         }
     }
 };
+
+using LinearEpilogue = LinearEpilogueT<false>;
 
 int gemm_f16_tn_dev(int device, const __half *dA, const __half *dB, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb,
                     const GemmOut &out, cudaStream_t st);

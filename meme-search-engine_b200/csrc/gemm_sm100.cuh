@@ -23,14 +23,17 @@ static constexpr int kGemmBK = 64;
 static constexpr int kGemmEpiWarps = 8;   // two warps per TMEM lane quadrant, each draining half of the tile's columns
 static constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
 
-template <int BN>
+static constexpr uint32_t kGemmCStageBytes = kGemmEpiWarps * 2 * 32 * 128;  // TMA-store epilogue: per warp two [32 rows][64 halfs] SW128 buffers
+
+template <int BN, bool TMA_STORE = false>
 struct GemmCfg {
-    static constexpr int kStages = BN >= 256 ? 4 : (BN >= 192 ? 5 : 6);
+    // stage ring sized to what is left of the 227 KB after the optional 64 KB of C staging
+    static constexpr int kStages = TMA_STORE ? (BN >= 256 ? 3 : 4) : (BN >= 256 ? 4 : (BN >= 192 ? 5 : 6));
     static constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;
     static constexpr uint32_t kBBytes = BN * kGemmBK * 2;
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
     static constexpr uint32_t kBarBytes = 256;
-    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + slack for 1024-B alignment
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + (TMA_STORE ? kGemmCStageBytes : 0) + kBarBytes + 1024;  // + slack for 1024-B alignment
     static constexpr uint32_t kTmemCols = 512;
 };
 
@@ -46,13 +49,19 @@ __device__ __forceinline__ void gemm_tile_coords(const GemmShape &s, uint32_t ti
     else { nt = tile % s.tiles_n; mt = tile / s.tiles_n; }
 }
 
+template <int BN, class Epilogue>
+constexpr uint32_t gemm_smem_bytes() { return GemmCfg<BN, Epilogue::kTmaStore>::kSmemBytes; }
+
 template <int BN, int BF16, class Epilogue>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape shp, Epilogue epi) {
-    using Cfg = GemmCfg<BN>;
+k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+          const GemmShape shp, Epilogue epi) {
+    using Cfg = GemmCfg<BN, Epilogue::kTmaStore>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = (uint64_t *)(smem + Cfg::kStages * Cfg::kStageBytes);
+    // [stage ring][C staging (TMA-store epilogue only; 1024-aligned for SWIZZLE_128B)][barriers]
+    uint8_t *cstage = smem + Cfg::kStages * Cfg::kStageBytes;
+    uint64_t *bars = (uint64_t *)(cstage + (Epilogue::kTmaStore ? kGemmCStageBytes : 0));
     uint64_t *full = bars;
     uint64_t *empty = bars + Cfg::kStages;
     uint64_t *tfull = bars + 2 * Cfg::kStages;
@@ -131,8 +140,10 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t quad = warp & 3;
         const uint32_t part = (uint32_t)(warp - 2) >> 2;                     // which slice of the columns this warp drains
         constexpr uint32_t kChunks = BN / 32, kParts = kGemmEpiWarps / 4;
-        const uint32_t c_begin = part * kChunks / kParts, c_end = (part + 1) * kChunks / kParts;
-        uint32_t acc = 0, acc_phase = 0;
+        // direct-store epilogues split the columns evenly; the TMA-store epilogue works in 64-column units (128 columns per half)
+        const uint32_t c_begin = Epilogue::kTmaStore ? min(part * 4u, kChunks) : part * kChunks / kParts;
+        const uint32_t c_end = Epilogue::kTmaStore ? min((part + 1) * 4u, kChunks) : (part + 1) * kChunks / kParts;
+        uint32_t acc = 0, acc_phase = 0, store_n = 0;
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             uint32_t mt, nt;
             gemm_tile_coords(shp, tile, mt, nt);
@@ -141,19 +152,98 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t row = mt * kGemmBM + quad * 32 + lane;
             const uint32_t taddr = tmem_base + ((quad * 32) << 16) + acc * BN;
             epi.begin_tile(row, nt * BN);
+            if constexpr (Epilogue::kTmaStore) {
+                // fp16 tile -> per-warp SW128 staging slab (32 rows x 64 columns) -> TMA store.  The 32 lanes of a warp own 32
+                // different rows, so direct stores would touch 32 cache lines per instruction; each warp instead runs its own
+                // double-buffered store pipeline (no cross-warp barriers): a slab is reused only after the store issued two
+                // chunks earlier has finished reading it.
+                static_assert(!Epilogue::kTmaStore || (BN % 64 == 0 && BN <= 256 && kGemmEpiWarps == 8), "TMA-store epilogue: 64-column units, two column halves");
+                uint8_t *cw = cstage + (warp - 2) * (2 * 32 * 128);
+                if (c_begin >= c_end) {  // this half has no columns in a narrow tile: just release the accumulator
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+                }
 #pragma unroll 1
-            for (uint32_t c = c_begin; c < c_end; c++) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(taddr + c * 32, v);
-                ptx::tmem_ld_wait();
-                epi.columns(row, nt * BN + c * 32, v);
+                for (uint32_t c = c_begin; c < c_end; c += 2) {
+                    uint32_t v0[32], v1[32];
+                    ptx::tmem_ld_32x32(taddr + c * 32, v0);
+                    ptx::tmem_ld_32x32(taddr + c * 32 + 32, v1);
+                    ptx::tmem_ld_wait();
+                    if (c + 2 >= c_end) {  // last TMEM read of this tile: hand the accumulator back before the stores
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+                    }
+                    const uint32_t col0 = nt * BN + c * 32;
+                    epi.compute(row, col0, v0);        // bias / activation / small residuals, in place (fp32 bit patterns)
+                    epi.compute(row, col0 + 32, v1);
+                    uint8_t *buf = cw + (store_n & 1) * (32 * 128);
+                    store_n++;
+                    if (lane == 0) ptx::tma_store_wait_read1();  // the store that used this slab two chunks ago is done reading
+                    __syncwarp();
+                    uint8_t *myrow = buf + lane * 128;
+                    if (const __half *res = epi.staged_residual()) {
+                        // in-place residual (x += linear(...)): stage this warp's 32 rows x 64 columns of x through the slab with
+                        // coalesced 128-byte row segments, then every lane picks up its own row
+                        const uint32_t ldc = epi.ldc(), Mrows = epi.rows(), Ncols = epi.cols();
+#pragma unroll
+                        for (uint32_t it = 0; it < 8; it++) {
+                            const uint32_t rr = it * 4 + (lane >> 3), ch = lane & 7;
+                            const uint32_t grow = mt * kGemmBM + quad * 32 + rr, gcol = col0 + ch * 8;
+                            uint4 val = make_uint4(0, 0, 0, 0);
+                            if (grow < Mrows && gcol + 8 <= Ncols) val = *(const uint4 *)(res + (size_t)grow * ldc + gcol);
+                            *(uint4 *)(buf + rr * 128 + ((ch ^ (rr & 7)) << 4)) = val;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (uint32_t q = 0; q < 8; q++) {
+                            const uint4 u = *(const uint4 *)(myrow + ((q ^ (lane & 7)) << 4));
+                            const __half2 *h = (const __half2 *)&u;
+                            uint32_t *dst = q < 4 ? &v0[q * 8] : &v1[(q - 4) * 8];
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const float2 t = __half22float2(h[e]);
+                                dst[2 * e] = __float_as_uint(__uint_as_float(dst[2 * e]) + t.x);
+                                dst[2 * e + 1] = __float_as_uint(__uint_as_float(dst[2 * e + 1]) + t.y);
+                            }
+                        }
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (uint32_t q = 0; q < 8; q++) {
+                        const uint32_t *src = q < 4 ? &v0[q * 8] : &v1[(q - 4) * 8];
+                        uint4 u;
+                        __half2 *h = (__half2 *)&u;
+#pragma unroll
+                        for (int e = 0; e < 4; e++) h[e] = __floats2half2_rn(__uint_as_float(src[2 * e]), __uint_as_float(src[2 * e + 1]));
+                        *(uint4 *)(myrow + ((q ^ (lane & 7)) << 4)) = u;
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tmC, buf, (int32_t)col0, (int32_t)(mt * kGemmBM + quad * 32));
+                        ptx::tma_store_commit();
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t c = c_begin; c < c_end; c++) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(taddr + c * 32, v);
+                    ptx::tmem_ld_wait();
+                    epi.columns(row, nt * BN + c * 32, v);
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+    }
+    if constexpr (Epilogue::kTmaStore) {
+        if (warp >= 2 && lane == 0) ptx::tma_store_wait_all();
     }
     ptx::tc_fence_before();
     __syncthreads();
