@@ -9,11 +9,11 @@
 
 namespace mse {
 
-template <int BN, class Epi>
+template <int BN, class Epi, int CG = 1>
 static int launch_gemm(int device, const void *dA, const void *dB, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb,
                        Epi epi, cudaStream_t st) {
-    constexpr uint32_t kSmem = gemm_smem_bytes<BN, Epi>();
-    auto kern = k_gemm_tn<BN, 0, Epi>;
+    constexpr uint32_t kSmem = gemm_smem_bytes<BN, Epi, CG>();
+    auto kern = k_gemm_tn<BN, 0, Epi, CG>;
     static bool attr_done = false;
     if (!attr_done) {
         MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
@@ -21,18 +21,32 @@ static int launch_gemm(int device, const void *dA, const void *dB, uint32_t M, u
     }
     CUtensorMap tmA, tmB, tmC;
     MSE_CHECK(encode_tmap_2d(&tmA, dA, M, K, lda, kGemmBM));
-    MSE_CHECK(encode_tmap_2d(&tmB, dB, N, K, ldb, BN));
+    MSE_CHECK(encode_tmap_2d(&tmB, dB, N, K, ldb, BN / CG));
     if (Epi::kTmaStore) MSE_CHECK(encode_tmap_2d(&tmC, epi.o.c16, M, N, epi.o.ldc, 32));  // per-warp 32-row slabs
     else tmC = tmA;
     GemmShape shp;
     shp.M = M; shp.N = N; shp.K = K;
-    shp.tiles_m = (M + kGemmBM - 1) / kGemmBM;
+    shp.tiles_m = (M + kGemmBM * CG - 1) / (kGemmBM * CG);
     shp.tiles_n = (N + BN - 1) / BN;
     shp.m_fastest = 0;
     shp.a_row0 = 0; shp.b_row0 = 0;
     const uint32_t ntiles = shp.tiles_m * shp.tiles_n;
-    const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)sm_count(device));
-    kern<<<grid, kGemmThreads, kSmem, st>>>(tmA, tmB, tmC, shp, epi);
+    const uint32_t units = std::min<uint32_t>(ntiles, (uint32_t)sm_count(device) / CG);
+    if (CG == 1) {
+        kern<<<units, kGemmThreads, kSmem, st>>>(tmA, tmB, tmC, shp, epi);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(units * CG);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = kSmem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MSE_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, shp, epi));
+    }
     MSE_LAUNCH_OK();
     return MSE_OK;
 }
@@ -57,6 +71,8 @@ int gemm_f16_tn_dev(int device, const __half *dA, const __half *dB, uint32_t M, 
         const uint32_t w256 = (N + 255) / 256 * 256 - N, w192 = (N + 191) / 192 * 192 - N;
         const char *bn_env = getenv("MSE_GEMM_BN");  // profiling only
         const bool allow192 = !(bn_env && atoi(bn_env) == 256);
+        const char *cg_env = getenv("MSE_GEMM_CG");  // profiling only: 1 forces single-CTA tiles
+        if (!(cg_env && atoi(cg_env) == 1)) return launch_gemm<256, LinearEpilogueT<true>, 2>(device, dA, dB, M, N, K, lda, ldb, e2, st);
         if (w192 < w256 && force_bn != 256 && allow192) return launch_gemm<192>(device, dA, dB, M, N, K, lda, ldb, e2, st);
         return launch_gemm<256>(device, dA, dB, M, N, K, lda, ldb, e2, st);
     }

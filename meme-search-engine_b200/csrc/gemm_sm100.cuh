@@ -25,12 +25,14 @@ static constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
 
 static constexpr uint32_t kGemmCStageBytes = kGemmEpiWarps * 2 * 32 * 128;  // TMA-store epilogue: per warp two [32 rows][64 halfs] SW128 buffers
 
-template <int BN, bool TMA_STORE = false>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2 (cta_group::2): a CTA pair per 256 x BN tile; each CTA stages its own 128 rows of A
+// and HALF of the B tile, so shared-memory and L2 traffic per flop drop by a third.
+template <int BN, bool TMA_STORE = false, int CG = 1>
 struct GemmCfg {
-    // stage ring sized to what is left of the 227 KB after the optional 64 KB of C staging
-    static constexpr int kStages = TMA_STORE ? (BN >= 256 ? 3 : 4) : (BN >= 256 ? 4 : (BN >= 192 ? 5 : 6));
     static constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;
-    static constexpr uint32_t kBBytes = BN * kGemmBK * 2;
+    static constexpr uint32_t kBBytes = (BN / CG) * kGemmBK * 2;
+    // stage ring sized to what is left of the 227 KB after the optional 64 KB of C staging
+    static constexpr int kStages = ((TMA_STORE ? 160 : 224) * 1024) / (kABytes + kBBytes) > 6 ? 6 : ((TMA_STORE ? 160 : 224) * 1024) / (kABytes + kBBytes);
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
     static constexpr uint32_t kBarBytes = 256;
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + (TMA_STORE ? kGemmCStageBytes : 0) + kBarBytes + 1024;  // + slack for 1024-B alignment
@@ -49,14 +51,17 @@ __device__ __forceinline__ void gemm_tile_coords(const GemmShape &s, uint32_t ti
     else { nt = tile % s.tiles_n; mt = tile / s.tiles_n; }
 }
 
-template <int BN, class Epilogue>
-constexpr uint32_t gemm_smem_bytes() { return GemmCfg<BN, Epilogue::kTmaStore>::kSmemBytes; }
+template <int BN, class Epilogue, int CG = 1>
+constexpr uint32_t gemm_smem_bytes() { return GemmCfg<BN, Epilogue::kTmaStore, CG>::kSmemBytes; }
 
-template <int BN, int BF16, class Epilogue>
+template <int BN, int BF16, class Epilogue, int CG = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
           const GemmShape shp, Epilogue epi) {
-    using Cfg = GemmCfg<BN, Epilogue::kTmaStore>;
+    using Cfg = GemmCfg<BN, Epilogue::kTmaStore, CG>;
+    constexpr int kTileM = kGemmBM * CG;  // rows of C per tile (shp.tiles_m counts these)
+    const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0;  // 0 = leader (issues the MMAs)
+    const uint32_t unit = blockIdx.x / CG, n_units = gridDim.x / CG;   // a unit = the CTA or CTA pair that owns a tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     // [stage ring][C staging (TMA-store epilogue only; 1024-aligned for SWIZZLE_128B)][barriers]
@@ -82,40 +87,50 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&tfull[a], 1);
-            ptx::mbar_init(&tempty[a], kGemmEpiWarps);  // one arrive per epilogue warp
+            ptx::mbar_init(&tempty[a], kGemmEpiWarps * CG);  // one arrive per epilogue warp (of both CTAs of a pair, on the leader)
         }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
-        ptx::tmem_relinquish();
+        if constexpr (CG == 2) { ptx::tmem_alloc_pair(tmem_slot, Cfg::kTmemCols); ptx::tmem_relinquish_pair(); }
+        else { ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync();  // the peer's barriers must exist before remote arrives / TMA signals reach them
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (uint32_t tile = unit; tile < ntiles; tile += n_units) {
                 uint32_t mt, nt;
                 gemm_tile_coords(shp, tile, mt, nt);
+                const int32_t a_row = shp.a_row0 + (int32_t)(mt * kTileM + cta_rank * kGemmBM);
+                const int32_t b_row = shp.b_row0 + (int32_t)(nt * BN + cta_rank * (BN / CG));
                 for (uint32_t kb = 0; kb < nkb; kb++) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
-                    ptx::mbar_expect_tx(&full[stage], Cfg::kStageBytes);
                     uint8_t *sa = smem + stage * Cfg::kStageBytes;
-                    ptx::tma_load_2d(sa, &tmA, &full[stage], (int32_t)(kb * kGemmBK), shp.a_row0 + (int32_t)(mt * kGemmBM));
-                    ptx::tma_load_2d(sa + Cfg::kABytes, &tmB, &full[stage], (int32_t)(kb * kGemmBK), shp.b_row0 + (int32_t)(nt * BN));
+                    if constexpr (CG == 2) {
+                        // both CTAs load their halves; all bytes are accounted on the leader's barrier, which only the leader arms
+                        if (cta_rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+                        ptx::tma_load_2d_pair(sa, &tmA, &full[stage], (int32_t)(kb * kGemmBK), a_row);
+                        ptx::tma_load_2d_pair(sa + Cfg::kABytes, &tmB, &full[stage], (int32_t)(kb * kGemmBK), b_row);
+                    } else {
+                        ptx::mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+                        ptx::tma_load_2d(sa, &tmA, &full[stage], (int32_t)(kb * kGemmBK), a_row);
+                        ptx::tma_load_2d(sa + Cfg::kABytes, &tmB, &full[stage], (int32_t)(kb * kGemmBK), b_row);
+                    }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc_f16(kGemmBM, BN, BF16);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_f16(kTileM, BN, BF16);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (uint32_t tile = unit; tile < ntiles; tile += n_units) {
                 ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -126,12 +141,16 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint64_t a_desc = ptx::smem_desc_sw128(sa);
                     const uint64_t b_desc = ptx::smem_desc_sw128(sa + Cfg::kABytes);
 #pragma unroll
-                    for (uint32_t k = 0; k < kGemmBK / 16; k++)
-                        ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    ptx::umma_commit(&empty[stage]);
+                    for (uint32_t k = 0; k < kGemmBK / 16; k++) {
+                        if constexpr (CG == 2) ptx::umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    if constexpr (CG == 2) ptx::umma_commit_pair(&empty[stage], 3);  // frees the stage in both CTAs
+                    else ptx::umma_commit(&empty[stage]);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tfull[acc]);
+                if constexpr (CG == 2) ptx::umma_commit_pair(&tfull[acc], 3);
+                else ptx::umma_commit(&tfull[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -144,12 +163,17 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t c_begin = Epilogue::kTmaStore ? min(part * 4u, kChunks) : part * kChunks / kParts;
         const uint32_t c_end = Epilogue::kTmaStore ? min((part + 1) * 4u, kChunks) : (part + 1) * kChunks / kParts;
         uint32_t acc = 0, acc_phase = 0, store_n = 0;
-        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        auto release_acc = [&](uint32_t a) {  // hand the accumulator back to the (leader's) MMA issuer
+            if constexpr (CG == 2) ptx::mbar_arrive_remote(&tempty[a], 0);
+            else ptx::mbar_arrive(&tempty[a]);
+        };
+        for (uint32_t tile = unit; tile < ntiles; tile += n_units) {
             uint32_t mt, nt;
             gemm_tile_coords(shp, tile, mt, nt);
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tc_fence_after();
-            const uint32_t row = mt * kGemmBM + quad * 32 + lane;
+            const uint32_t row0 = mt * kTileM + cta_rank * kGemmBM;   // first C row of this CTA's half of the tile
+            const uint32_t row = row0 + quad * 32 + lane;
             const uint32_t taddr = tmem_base + ((quad * 32) << 16) + acc * BN;
             epi.begin_tile(row, nt * BN);
             if constexpr (Epilogue::kTmaStore) {
@@ -162,7 +186,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if (c_begin >= c_end) {  // this half has no columns in a narrow tile: just release the accumulator
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+                    if (lane == 0) release_acc(acc);
                 }
 #pragma unroll 1
                 for (uint32_t c = c_begin; c < c_end; c += 2) {
@@ -173,7 +197,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if (c + 2 >= c_end) {  // last TMEM read of this tile: hand the accumulator back before the stores
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+                        if (lane == 0) release_acc(acc);
                     }
                     const uint32_t col0 = nt * BN + c * 32;
                     epi.compute(row, col0, v0);        // bias / activation / small residuals, in place (fp32 bit patterns)
@@ -190,7 +214,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                         for (uint32_t it = 0; it < 8; it++) {
                             const uint32_t rr = it * 4 + (lane >> 3), ch = lane & 7;
-                            const uint32_t grow = mt * kGemmBM + quad * 32 + rr, gcol = col0 + ch * 8;
+                            const uint32_t grow = row0 + quad * 32 + rr, gcol = col0 + ch * 8;
                             uint4 val = make_uint4(0, 0, 0, 0);
                             if (grow < Mrows && gcol + 8 <= Ncols) val = *(const uint4 *)(res + (size_t)grow * ldc + gcol);
                             *(uint4 *)(buf + rr * 128 + ((ch ^ (rr & 7)) << 4)) = val;
@@ -222,7 +246,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        ptx::tma_store_2d(&tmC, buf, (int32_t)col0, (int32_t)(mt * kGemmBM + quad * 32));
+                        ptx::tma_store_2d(&tmC, buf, (int32_t)col0, (int32_t)(row0 + quad * 32));
                         ptx::tma_store_commit();
                     }
                 }
@@ -236,7 +260,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+                if (lane == 0) release_acc(acc);
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -246,10 +270,12 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (warp >= 2 && lane == 0) ptx::tma_store_wait_all();
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync();  // neither CTA may exit (or free TMEM) while its partner can still signal it
+    else __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if constexpr (CG == 2) ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+        else ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
