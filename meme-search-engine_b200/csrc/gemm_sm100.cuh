@@ -167,6 +167,26 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if constexpr (CG == 2) ptx::mbar_arrive_remote(&tempty[a], 0);
             else ptx::mbar_arrive(&tempty[a]);
         };
+        // in-place residual (x += linear(...)): this warp's 32 rows x 64 columns of x are fetched one 64-column step AHEAD
+        // (also across tiles) with coalesced 128-byte row segments, so the HBM latency hides behind a whole step
+        uint4 resv[8];
+        auto prefetch_residual = [&](uint32_t t, uint32_t c) {
+            if constexpr (Epilogue::kTmaStore) {
+                const __half *res = epi.staged_residual();
+                if (res == nullptr || t >= ntiles) return;
+                uint32_t pm, pn;
+                gemm_tile_coords(shp, t, pm, pn);
+                const uint32_t ldc = epi.ldc(), Mrows = epi.rows(), Ncols = epi.cols();
+                const uint32_t prow = pm * kTileM + cta_rank * kGemmBM + quad * 32 + (lane >> 3), pcol = pn * BN + c * 32 + (lane & 7) * 8;
+                const __half *src = res + (size_t)prow * ldc + pcol;
+#pragma unroll
+                for (uint32_t it = 0; it < 8; it++) {
+                    resv[it] = make_uint4(0, 0, 0, 0);
+                    if (prow + it * 4 < Mrows && pcol + 8 <= Ncols) resv[it] = *(const uint4 *)(src + (size_t)(it * 4) * ldc);
+                }
+            }
+        };
+        if (c_begin < c_end) prefetch_residual(unit, c_begin);
         for (uint32_t tile = unit; tile < ntiles; tile += n_units) {
             uint32_t mt, nt;
             gemm_tile_coords(shp, tile, mt, nt);
@@ -207,18 +227,15 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if (lane == 0) ptx::tma_store_wait_read1();  // the store that used this slab two chunks ago is done reading
                     __syncwarp();
                     uint8_t *myrow = buf + lane * 128;
-                    if (const __half *res = epi.staged_residual()) {
-                        // in-place residual (x += linear(...)): stage this warp's 32 rows x 64 columns of x through the slab with
-                        // coalesced 128-byte row segments, then every lane picks up its own row
-                        const uint32_t ldc = epi.ldc(), Mrows = epi.rows(), Ncols = epi.cols();
+                    if (epi.staged_residual() != nullptr) {
+                        // the prefetched rows of x go through the slab, then every lane picks up its own row
 #pragma unroll
                         for (uint32_t it = 0; it < 8; it++) {
                             const uint32_t rr = it * 4 + (lane >> 3), ch = lane & 7;
-                            const uint32_t grow = row0 + quad * 32 + rr, gcol = col0 + ch * 8;
-                            uint4 val = make_uint4(0, 0, 0, 0);
-                            if (grow < Mrows && gcol + 8 <= Ncols) val = *(const uint4 *)(res + (size_t)grow * ldc + gcol);
-                            *(uint4 *)(buf + rr * 128 + ((ch ^ (rr & 7)) << 4)) = val;
+                            *(uint4 *)(buf + rr * 128 + ((ch ^ (rr & 7)) << 4)) = resv[it];
                         }
+                        if (c + 2 < c_end) prefetch_residual(tile, c + 2);
+                        else prefetch_residual(tile + n_units, c_begin);
                         __syncwarp();
 #pragma unroll
                         for (uint32_t q = 0; q < 8; q++) {
