@@ -292,7 +292,7 @@ def main():
                 "peak_source": pk["src"] + " (sustained bf16 cuBLAS)", "frac_of_burst": gemm_tf / pk["tf_burst"] if gemm_tf else None,
                 "launches_per_step": st["gemm_launches"], "kernel_ms_per_step": st["gemm_ns"] * 1e-6,
                 "kernel_share_of_step": st["gemm_ns"] * 1e-6 / ms_step, "traffic": None,
-                "attention": {"kernel": "k_mha_fwd (mma.sync)", "ms_per_step": st["attn_ns"] * 1e-6, "launches": st["attn_launches"],
+                "attention": {"kernel": "k_mha_tc (tcgen05 flash attention)", "ms_per_step": st["attn_ns"] * 1e-6, "launches": st["attn_launches"],
                               "achieved_tflops": attn_flop / (st["attn_ns"] * 1e-9) / 1e12 if st["attn_ns"] else None,
                               "share_of_step": st["attn_ns"] * 1e-6 / ms_step},
                 "whole_step": {"achieved_tflops": FLOP_PER_IMAGE * B / (ms_step * 1e-3) / 1e12,

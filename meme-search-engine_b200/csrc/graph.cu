@@ -240,6 +240,160 @@ __global__ void __launch_bounds__(kGsThreads) k_greedy_search(GraphArgs g, const
     }
 }
 
+// ------------------------------------------------------------------ greedy search, one WARP per query (batch mode)
+//
+// Same algorithm, same order of every insert, same outputs as k_greedy_search; the difference is the schedule.  A hop of
+// one query is a chain (pop -> adjacency -> visited set -> <= R row gathers -> inserts) with no parallelism across hops, so
+// a large batch is served best by many independent chains per SM: each warp owns one query and never waits at a CTA
+// barrier, 16 warps per SM keep >= 36 (two rows: 72) 64-byte row loads in flight each, which is what hides the
+// HBM gather latency.  The query slice of lane p (elements d = p mod 32, vector.rs:212-238) lives in registers.
+
+static constexpr int kWqWarps = 4;   // warps (queries in flight) per CTA
+
+__host__ __device__ static size_t wq_warp_bytes(uint32_t L, uint32_t stride, uint32_t d, bool q_in_smem) {
+    size_t o = (size_t)(L + 1) * 8 + (size_t)stride * 8 + (size_t)(L + 1) * 4 + (size_t)stride * 4 + (size_t)stride * 4 + (q_in_smem ? (size_t)d * 4 : 0) + (L + 1);
+    return (o + 15) & ~(size_t)15;
+}
+
+// HashSet<u32>::insert without the fill counter (the warp counts with a ballot)
+__device__ __forceinline__ bool hs_insert_nc(uint32_t *tab, uint32_t mask, uint32_t key) {
+    uint32_t h = (key * 2654435761u) & mask;
+    for (uint32_t probes = 0; probes <= mask; probes++) {
+        const uint32_t old = atomicCAS(&tab[h], kEmpty, key);
+        if (old == kEmpty) return true;
+        if (old == key) return false;
+        h = (h + 1) & mask;
+    }
+    return false;
+}
+
+template <int NC>
+__device__ __forceinline__ void wq_score2(const float (&qr)[NC > 0 ? NC : 1], const float *qs, const __half *__restrict__ r0,
+                                          const __half *__restrict__ r1, uint32_t d, int lane, long long &s0, long long &s1) {
+    float p0 = 0.f, p1 = 0.f;
+    if constexpr (NC > 0) {
+        float a[NC], b[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) { a[c] = __half2float(r0[32 * c + lane]); b[c] = __half2float(r1[32 * c + lane]); }
+#pragma unroll
+        for (int c = 0; c < NC; c++) { p0 = fmaf(qr[c], a[c], p0); p1 = fmaf(qr[c], b[c], p1); }
+    } else {
+#pragma unroll 4
+        for (uint32_t c = lane; c < d; c += 32) { const float qv = qs[c]; p0 = fmaf(qv, __half2float(r0[c]), p0); p1 = fmaf(qv, __half2float(r1[c]), p1); }
+    }
+    s0 = fast_dot_fix(fast_dot_reduce(p0));
+    s1 = fast_dot_fix(fast_dot_reduce(p1));
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kWqWarps * 32, 4) k_greedy_search_wq(GraphArgs g, const __half *__restrict__ queries, const uint32_t *__restrict__ q_rows,
+                                                                       uint32_t nq, const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L,
+                                                                       uint32_t filter_from, uint32_t *htabs, uint32_t hcap, GreedyOut out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t S = g.stride;
+    uint8_t *base = smem_raw + (size_t)warp * wq_warp_bytes(L, S, g.d, NC == 0);
+    long long *nb_scores = (long long *)base;
+    long long *pre_scores = nb_scores + (L + 1);
+    uint32_t *nb_ids = (uint32_t *)(pre_scores + S);
+    uint32_t *pre = nb_ids + (L + 1);
+    uint32_t *raw = pre + S;
+    float *qs = (float *)(raw + S);
+    uint8_t *nb_vis = (uint8_t *)(qs + (NC == 0 ? g.d : 0));
+    const uint32_t gw = blockIdx.x * kWqWarps + warp, nw = gridDim.x * kWqWarps;
+    uint32_t *htab = htabs + (size_t)gw * hcap;
+    const uint32_t hmask = hcap - 1;
+    const unsigned full = 0xffffffffu;
+
+    for (uint32_t qi = gw; qi < nq; qi += nw) {
+        {
+            uint4 *t4 = (uint4 *)htab;
+            const uint4 e4 = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+            for (uint32_t i = lane; i < hcap / 4; i += 32) t4[i] = e4;
+        }
+        const size_t qrow = q_rows ? q_rows[qi] : qi;
+        float qr[NC > 0 ? NC : 1];
+        if constexpr (NC > 0) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) qr[c] = __half2float(queries[qrow * g.d + 32 * c + lane]);
+        } else {
+            for (uint32_t c = lane; c < g.d; c += 32) qs[c] = __half2float(queries[qrow * g.d + c]);
+        }
+        __syncwarp();
+        NbView nb{nb_ids, nb_scores, nb_vis, 0, (int)L, -1};
+        const uint32_t start = starts ? starts[qi] : start_all;
+        unsigned long long distances = 0;
+        uint32_t n_eval = 0, hfill = 1;
+        {
+            long long sc, sc_dup;
+            const __half *r = g.x + (size_t)start * g.d;
+            wq_score2<NC>(qr, qs, r, r, g.d, lane, sc, sc_dup);
+            nb_insert(nb, start, sc, lane);                                          // :188
+            if (lane == 0) hs_insert_nc(htab, hmask, start);                         // :189
+            __syncwarp();
+        }
+        for (;;) {
+            const uint32_t pt = nb_next_unvisited(nb, lane);
+            if (pt == kEmpty || hfill * 4 > hcap * 3) break;
+            // out-neighbours not seen before, first occurrence first (:193-200)
+            const uint32_t dg = min(g.deg[pt], S);
+            const uint32_t *nbrs = g.adj + (size_t)pt * S;
+            int n_pre = 0;
+            for (uint32_t b0 = 0; b0 < dg; b0 += 32) {
+                const uint32_t i = b0 + lane;
+                const bool have = i < dg;
+                const uint32_t id = have ? nbrs[i] : kEmpty;
+                const unsigned same = __match_any_sync(full, id);
+                bool ins = false;
+                if (have && (same & ((1u << lane) - 1)) == 0) ins = hs_insert_nc(htab, hmask, id);   // a copy in a lower lane wins
+                const bool fresh = ins && id < filter_from;
+                hfill += __popc(__ballot_sync(full, ins));
+                const unsigned m = __ballot_sync(full, fresh);
+                if (fresh) pre[n_pre + __popc(m & ((1u << lane) - 1))] = id;
+                n_pre += __popc(m);
+                __syncwarp();
+            }
+            // exact scores, two rows per pass (:201-204)
+            for (int i = 0; i < n_pre; i += 2) {
+                const int j = i + 1 < n_pre ? i + 1 : i;
+                long long s0, s1;
+                wq_score2<NC>(qr, qs, g.x + (size_t)pre[i] * g.d, g.x + (size_t)pre[j] * g.d, g.d, lane, s0, s1);
+                if (lane == 0) { pre_scores[i] = s0; pre_scores[j] = s1; }
+            }
+            __syncwarp();
+            const bool full0 = nb.len == nb.cap;
+            const long long last0 = full0 ? nb.scores[nb.len - 1] : 0;
+            for (int i = 0; i < n_pre; i++) {
+                const long long sc = pre_scores[i];
+                if (!(full0 && last0 > sc)) nb_insert(nb, pre[i], sc, lane);
+            }
+            if (out.vl_ids) {
+                for (int i = lane; i < n_pre; i += 32) {
+                    const uint32_t slot = n_eval + i;
+                    if (slot < out.vl_cap) {
+                        out.vl_ids[(size_t)qi * out.vl_cap + slot] = pre[i];
+                        out.vl_scores[(size_t)qi * out.vl_cap + slot] = pre_scores[i];
+                    }
+                }
+            }
+            n_eval += n_pre;
+            distances += n_pre;
+            __syncwarp();
+        }
+        for (uint32_t i = lane; i < L; i += 32) {
+            out.ids[(size_t)qi * L + i] = (int)i < nb.len ? nb.ids[i] : kEmpty;
+            out.scores[(size_t)qi * L + i] = (int)i < nb.len ? nb.scores[i] : 0;
+        }
+        if (lane == 0) {
+            out.len[qi] = nb.len;
+            out.distances[qi] = distances;
+            if (out.vl_len) out.vl_len[qi] = n_eval;
+            out.status[qi] = (hfill * 4 > hcap * 3) ? 1u : 0u;
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------ beam search over the packed index (query_disk_index.rs:144-212)
 
 struct BeamArgs {
