@@ -133,12 +133,36 @@ int mse_search_graph(mse_index *ix, const uint16_t *q_f16, uint32_t nq, uint32_t
                      int base_vectors_only, uint32_t query_breakpoint, uint32_t *ids, int64_t *scores, uint32_t *len,
                      uint64_t *distances, uint32_t *visited_ids, int64_t *visited_scores, uint32_t *visited_len,
                      uint32_t visited_cap);
+/* the same with every buffer already in HBM (device pointers), asynchronous on `stream`; no visited lists.  The
+ * per-query visited-set overflow status is read back by mse_search_graph_check (which synchronises the device). */
+int mse_search_graph_dev(mse_index *ix, const uint16_t *d_q_f16, uint32_t nq, uint32_t L, const uint32_t *d_starts, uint32_t start,
+                         int base_vectors_only, uint32_t query_breakpoint, uint32_t *d_ids, int64_t *d_scores, uint32_t *d_len,
+                         uint64_t *d_distances, void *stream);
+int mse_search_graph_check(mse_index *ix, uint32_t nq);
+/* schedule of greedy_search on the GPU: 0 automatic, 1 one CTA per query (small batches), 2 one warp per query (large
+ * batches).  Both replay lib.rs:183-211 insert for insert; results are identical. */
+int mse_search_graph_set_mode(int mode);
 /* greedy_search of query_disk_index.rs:144-212 (beam W, PQ ADC for candidates, exact score + descriptor bias for expanded
  * nodes).  luts [nq][M*n_centroids] from mse_pq_preprocess_query; desc_scales [nq][n_desc] or NULL.  out_* [nq][out_cap]:
  * expanded nodes in visit order with their exact scores (the caller sorts, :529); cmps / pq_cmps as :148-149. */
 int mse_search_beam(mse_index *ix, const uint16_t *q_f16, const float *luts, const float *desc_scales, uint32_t nq, uint32_t L,
                     uint32_t W, const uint32_t *starts, uint32_t start, int disable_pq, uint32_t n_centroids, uint32_t *out_ids,
                     int64_t *out_scores, uint32_t *out_len, uint32_t out_cap, uint64_t *cmps, uint64_t *pq_cmps);
+/* The same traversal with candidates ranked by  f32(sum of LUT entries) * code_scale[id] + code_bias[q]: the RabitQ
+ * estimator (diskann/rabitq.py:42-48) with luts / code_bias from mse_rabitq_preprocess_query, codes from mse_rabitq_encode
+ * (mse_index_set_pq_codes) and code_scale[id] = norms[id] * dots[id] (mse_index_set_code_scales). */
+int mse_search_beam_scaled(mse_index *ix, const uint16_t *q_f16, const float *luts, const float *code_bias, const float *desc_scales,
+                           uint32_t nq, uint32_t L, uint32_t W, const uint32_t *starts, uint32_t start, uint32_t n_centroids,
+                           uint32_t *out_ids, int64_t *out_scores, uint32_t *out_len, uint32_t out_cap, uint64_t *cmps, uint64_t *pq_cmps);
+int mse_index_set_code_scales(mse_index *ix, const float *scales);
+/* Beam search with every buffer in HBM, asynchronous on `stream`; the best `topk` expanded nodes are selected on the device
+ * ((score desc, visit order asc): the stable sort of query_disk_index.rs:303).  Candidate scores: d_luts ([nq][M*n_centroids],
+ * PQ ADC) or, when d_qtm is given ([nq][output_dims+1] from mse_rabitq_query_dev), RabitQ byte tables built in shared memory.
+ * mse_search_graph_check(ix, nq) afterwards reports visited-set / visit-list overflows. */
+int mse_search_beam_dev(mse_index *ix, const uint16_t *d_q_f16, const float *d_luts, const float *d_qtm, uint32_t rabitq_output_dims,
+                        uint32_t rabitq_n_dims, const float *d_desc_scales, uint32_t nq, uint32_t L, uint32_t W, const uint32_t *d_starts,
+                        uint32_t start, uint32_t n_centroids, uint32_t topk, uint32_t *d_top_ids, int64_t *d_top_scores,
+                        uint32_t *d_top_len, uint64_t *d_cmps, uint64_t *d_pq_cmps, void *stream);
 /* evaluator brute force (query_disk_index.rs:262-273): exact i64 score of one fp16 query against every row */
 int mse_scores_i64(mse_index *ix, const uint16_t *q_f16, int64_t *scores);
 
@@ -177,6 +201,11 @@ int mse_rabitq_encode(mse_rabitq *r, const uint16_t *x_f16, uint64_t n, uint8_t 
 /* approx_dot (rabitq.py:42-48) of one f32 query against n encoded vectors */
 int mse_rabitq_estimate(mse_rabitq *r, const float *q, const uint8_t *codes, const float *norms, const float *dots, uint64_t n,
                         float *estimates);
+/* query side of approx_dot (rabitq.py:42-46) as byte tables for mse_search_beam_scaled: luts [nq][output_dims/8][256]
+ * (entry v of table b = (1/sqrt(n_dims)) * sum_j (+-) (P q)[8b+j], sign from bit j of v), bias [nq] = <mean, q> */
+int mse_rabitq_preprocess_query(mse_rabitq *r, const float *q, uint32_t nq, float *luts, float *bias);
+/* the same query side kept in HBM: d_qtm [nq][output_dims + 1] = (P q, <mean, q>), asynchronous on `stream` */
+int mse_rabitq_query_dev(mse_rabitq *r, const float *d_q, uint32_t nq, float *d_qtm, void *stream);
 void mse_rabitq_destroy(mse_rabitq *r);
 
 /* =====================================================================================

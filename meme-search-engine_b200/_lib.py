@@ -64,7 +64,13 @@ _SIGS = {
     "mse_index_set_pq_codes": (_i32, [_vp, _vp, _u32]),
     "mse_index_set_descriptors": (_i32, [_vp, _vp, _u32, _vp]),
     "mse_search_graph": (_i32, [_vp, _vp, _u32, _u32, _vp, _u32, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32]),
+    "mse_search_graph_dev": (_i32, [_vp, _vp, _u32, _u32, _vp, _u32, _i32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "mse_search_graph_check": (_i32, [_vp, _u32]),
+    "mse_search_graph_set_mode": (_i32, [_i32]),
     "mse_search_beam": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _u32, _i32, _u32, _vp, _vp, _vp, _u32, _vp, _vp]),
+    "mse_search_beam_scaled": (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _u32, _vp, _vp]),
+    "mse_index_set_code_scales": (_i32, [_vp, _vp]),
+    "mse_search_beam_dev": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _vp, _u32, _u32, _u32, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mse_scores_i64": (_i32, [_vp, _vp, _vp]),
     "mse_robust_prune": (_i32, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
     "mse_index_random_fill_graph": (_i32, [_vp, _u32, _u64]),
@@ -82,6 +88,8 @@ _SIGS = {
     "mse_rabitq_load": (_i32, [_vp, C.c_size_t, _i32, C.POINTER(_vp)]),
     "mse_rabitq_encode": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "mse_rabitq_estimate": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "mse_rabitq_preprocess_query": (_i32, [_vp, _vp, _u32, _vp, _vp]),
+    "mse_rabitq_query_dev": (_i32, [_vp, _vp, _u32, _vp, _vp]),
     "mse_rabitq_destroy": (None, [_vp]),
     "mse_encoder_create": (_i32, [C.c_char_p, _i32, _i32, C.POINTER(_vp)]),
     "mse_encoder_config": (_i32, [_vp, _vp]),

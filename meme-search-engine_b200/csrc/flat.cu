@@ -701,12 +701,18 @@ MSE_API void mse_index_destroy(mse_index *ix) {
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     ix->fw.release();
+    ix->gw_htabs.release();
+    ix->gw_status.release();
+    ix->gw_vis_ids.release();
+    ix->gw_vis_sc.release();
+    ix->gw_vis_len.release();
     for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);
     if (ix->x) cudaFree(ix->x);
     if (ix->max_norm) cudaFree(ix->max_norm);
     if (ix->adj) cudaFree(ix->adj);
     if (ix->deg) cudaFree(ix->deg);
     if (ix->pq_codes) cudaFree(ix->pq_codes);
+    if (ix->code_scale) cudaFree(ix->code_scale);
     if (ix->desc) cudaFree(ix->desc);
     if (ix->has_url) cudaFree(ix->has_url);
     if (ix->stream) cudaStreamDestroy(ix->stream);

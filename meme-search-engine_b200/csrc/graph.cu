@@ -105,21 +105,21 @@ struct GsSmem {
     int *ctl;               // [0] n_pre  [1] pt  [2] scratch
 };
 
-__device__ __forceinline__ GsSmem carve(uint8_t *base, uint32_t L, uint32_t d) {
+__device__ __forceinline__ GsSmem carve(uint8_t *base, uint32_t L, uint32_t d, uint32_t S) {   // S = adjacency stride (max degree)
     GsSmem s;
     size_t o = 0;
     s.nb_scores = (long long *)(base + o); o += (size_t)(L + 1) * 8;
-    s.pre_scores = (long long *)(base + o); o += (size_t)kMaxDeg * 8;
+    s.pre_scores = (long long *)(base + o); o += (size_t)S * 8;
     s.nb_ids = (uint32_t *)(base + o); o += (size_t)(L + 1) * 4;
-    s.pre = (uint32_t *)(base + o); o += (size_t)kMaxDeg * 4;
-    s.raw = (uint32_t *)(base + o); o += (size_t)kMaxDeg * 4;
+    s.pre = (uint32_t *)(base + o); o += (size_t)S * 4;
+    s.raw = (uint32_t *)(base + o); o += (size_t)S * 4;
     s.q = (float *)(base + o); o += (size_t)d * 4;
     s.ctl = (int *)(base + o); o += 16 * 4;
     s.nb_vis = (uint8_t *)(base + o);
     return s;
 }
-__host__ __device__ static size_t gs_smem_bytes(uint32_t L, uint32_t d) {
-    return (size_t)(L + 1) * 8 + kMaxDeg * 8 + (size_t)(L + 1) * 4 + kMaxDeg * 4 + kMaxDeg * 4 + (size_t)d * 4 + 64 + (L + 1) + 64;
+__host__ __device__ static size_t gs_smem_bytes(uint32_t L, uint32_t d, uint32_t S) {
+    return (size_t)(L + 1) * 8 + (size_t)S * 8 + (size_t)(L + 1) * 4 + (size_t)S * 4 + (size_t)S * 4 + (size_t)d * 4 + 64 + (L + 1) + 64;
 }
 
 // exact fast_dot of the shared-memory query against one row; whole warp, bit-identical to vector.rs:192-306
@@ -133,7 +133,7 @@ __device__ __forceinline__ long long score_row(const float *q, const __half *row
 // filter_from: ids >= filter_from are dropped AFTER being marked seen (lib.rs:196-199 base_vectors_only)
 __device__ __forceinline__ int collect_new_neighbours(const GraphArgs &g, GsSmem &s, uint32_t pt, uint32_t *htab, uint32_t hmask,
                                                       uint32_t *hfill, uint32_t filter_from, int n_pre0) {
-    const uint32_t dg = min(g.deg[pt], (uint32_t)kMaxDeg);
+    const uint32_t dg = min(g.deg[pt], g.stride);
     const uint32_t *nbrs = g.adj + (size_t)pt * g.stride;
     for (uint32_t i = threadIdx.x; i < dg; i += blockDim.x) s.raw[i] = nbrs[i];
     __syncthreads();
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kGsThreads) k_greedy_search(GraphArgs g, const
                                                               const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L,
                                                               uint32_t filter_from, uint32_t *htabs, uint32_t hcap, GreedyOut out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    GsSmem s = carve(smem_raw, L, g.d);
+    GsSmem s = carve(smem_raw, L, g.d, g.stride);
     uint32_t *htab = htabs + (size_t)blockIdx.x * hcap;
     const uint32_t hmask = hcap - 1;
     __shared__ uint32_t hfill;
@@ -403,6 +403,10 @@ struct BeamArgs {
     const uint8_t *has_url;   // [n] or NULL: query_disk_index.rs:172 `node.url.len() > 0`
     uint32_t n_desc;
     int disable_pq;
+    const float *code_scale;  // [n] or NULL: candidate score = f32 sum of LUT entries * code_scale[id] + code_bias[q] (RabitQ estimate)
+    const float *code_bias;   // [nq] (used with code_scale)
+    const float *qtm;         // [nq][rq_O + 1] or NULL: RabitQ query side (P q, <mean,q>); the byte tables are built in shared memory
+    uint32_t rq_O, rq_D;
 };
 struct BeamOut {
     uint32_t *ids;            // [nq][cap] expanded-and-recorded nodes in visit order
@@ -410,7 +414,11 @@ struct BeamOut {
     uint32_t *len;            // [nq]
     uint32_t cap;
     unsigned long long *cmps, *pq_cmps;  // [nq]
-    uint32_t *status;
+    uint32_t *status;         // [nq] bit 0: visited-set overflow, bit 1: more than cap expanded nodes
+    uint32_t topk;            // > 0: also emit the best topk expanded nodes, (score desc, visit order asc) = the stable sort of :303
+    uint32_t *top_ids;        // [nq][topk], kEmpty past top_len
+    long long *top_scores;
+    uint32_t *top_len;        // [nq]
 };
 
 // descriptor_product (query_disk_index.rs:135-142): sum_j trunc(scale_j * code_j * 2^32)
@@ -425,8 +433,8 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
                                                             uint32_t nq, const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L,
                                                             uint32_t W, uint32_t *htabs, uint32_t hcap, BeamOut out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    GsSmem s = carve(smem_raw, L, g.d);
-    float *lut = (float *)(smem_raw + ((gs_smem_bytes(L, g.d) + 15) & ~(size_t)15));
+    GsSmem s = carve(smem_raw, L, g.d, g.stride);
+    float *lut = (float *)(smem_raw + ((gs_smem_bytes(L, g.d, g.stride) + 15) & ~(size_t)15));
     // two exact sets like the reference: visited_adjacent (seen as a neighbour) and visited (expanded)
     uint32_t *hadj = htabs + (size_t)blockIdx.x * 2 * hcap, *hvis = hadj + hcap;
     const uint32_t hmask = hcap - 1;
@@ -438,11 +446,24 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
     for (uint32_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
         for (uint32_t i = threadIdx.x; i < 2 * hcap; i += blockDim.x) hadj[i] = kEmpty;
         for (uint32_t i = threadIdx.x; i < g.d; i += blockDim.x) s.q[i] = __half2float(queries[(size_t)qi * g.d + i]);
-        if (!ba.disable_pq)
-            for (uint32_t i = threadIdx.x; i < lut_n; i += blockDim.x) lut[i] = luts[(size_t)qi * lut_n + i];
+        if (!ba.disable_pq) {
+            if (ba.qtm) {                                                            // same expression as pq.cu k_rabitq_lut
+                const float *qt = ba.qtm + (size_t)qi * (ba.rq_O + 1);
+                const float rscale = rsqrtf((float)ba.rq_D);
+                for (uint32_t i = threadIdx.x; i < lut_n; i += blockDim.x) {
+                    const uint32_t b = i >> 8, val = i & 255;
+                    float t = 0.f;
+                    for (int j = 0; j < 8; j++) t += ((val >> j) & 1) ? qt[b * 8 + j] : -qt[b * 8 + j];
+                    lut[i] = rscale * t;
+                }
+            } else {
+                for (uint32_t i = threadIdx.x; i < lut_n; i += blockDim.x) lut[i] = luts[(size_t)qi * lut_n + i];
+            }
+        }
         if (threadIdx.x == 0) { fill_adj = 0; fill_vis = 0; }
         __syncthreads();
         const float *scales = desc_scales ? desc_scales + (size_t)qi * ba.n_desc : nullptr;
+        const float code_bias_q = !ba.code_scale ? 0.f : ba.qtm ? ba.qtm[(size_t)qi * (ba.rq_O + 1) + ba.rq_O] : ba.code_bias[qi];
         NbView nb{s.nb_ids, s.nb_scores, s.nb_vis, 0, (int)L, -1};
         const uint32_t start = starts ? starts[qi] : start_all;
         unsigned long long cmps = 0, pq_cmps = 0;
@@ -494,9 +515,21 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
                     }
                 } else {
                     for (int i = threadIdx.x; i < n_pre; i += blockDim.x) {        // asymmetric_dot_product vector.rs:387-405
-                        const uint8_t *code = ba.codes + (size_t)s.pre[i] * ba.M;
+                        const uint32_t id = s.pre[i];
+                        const uint8_t *code = ba.codes + (size_t)id * ba.M;
                         float acc = 0.f;
-                        for (uint32_t m = 0; m < ba.M; m++) acc += lut[m * ba.C + code[m]];  // f32, chunk order
+                        if ((ba.M & 15) == 0) {                                      // 16 codes per 128-bit load; f32 adds stay in chunk order
+                            const uint4 *c4 = (const uint4 *)code;
+                            for (uint32_t m = 0; m < ba.M; m += 16) {
+                                const uint4 v = c4[m >> 4];
+                                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                                for (int j = 0; j < 16; j++) acc += lut[(m + j) * ba.C + ((w[j >> 2] >> (8 * (j & 3))) & 255u)];
+                            }
+                        } else {
+                            for (uint32_t m = 0; m < ba.M; m++) acc += lut[m * ba.C + code[m]];
+                        }
+                        if (ba.code_scale) acc = fmaf(acc, ba.code_scale[id], code_bias_q);   // RabitQ: |o| <o_bar,o> <o_bar,Pq> + <mean,q>
                         s.pre_scores[i] = fast_dot_fix(acc);
                     }
                 }
@@ -521,9 +554,24 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
             out.len[qi] = n_out;
             out.cmps[qi] = cmps;
             out.pq_cmps[qi] = pq_cmps;
-            out.status[qi] = (fill_adj * 4 > hcap * 3) ? 1u : 0u;
+            out.status[qi] = ((fill_adj * 4 > hcap * 3) ? 1u : 0u) | (n_out > out.cap ? 2u : 0u);
+            s.ctl[2] = (int)min(n_out, out.cap);
         }
         __syncthreads();
+        if (out.topk) {                                                              // rank by counting: lists are ~L long
+            const uint32_t m = (uint32_t)s.ctl[2];
+            const uint32_t *vi = out.ids + (size_t)qi * out.cap;
+            const long long *vs = out.scores + (size_t)qi * out.cap;
+            for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                const long long si = vs[i];
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < m; j++) { const long long sj = vs[j]; rank += (sj > si) || (sj == si && j < i); }
+                if (rank < out.topk) { out.top_ids[(size_t)qi * out.topk + rank] = vi[i]; out.top_scores[(size_t)qi * out.topk + rank] = si; }
+            }
+            for (uint32_t i = m + threadIdx.x; i < out.topk; i += blockDim.x) { out.top_ids[(size_t)qi * out.topk + i] = kEmpty; out.top_scores[(size_t)qi * out.topk + i] = 0; }
+            if (threadIdx.x == 0) out.top_len[qi] = min(m, out.topk);
+            __syncthreads();
+        }
     }
 }
 
@@ -548,16 +596,46 @@ uint32_t greedy_hash_capacity(uint32_t L, uint32_t stride) {
     while (p < v && p < (1u << 30)) p <<= 1;
     return p;
 }
-uint32_t greedy_grid(const mse_index *ix, uint32_t nq) { return std::min<uint32_t>(nq, (uint32_t)sm_count(ix->device) * 2); }
+
+// 0 = automatic (warp-per-query for batches that fill the GPU, CTA-per-query below that), 1 = CTA-per-query, 2 = warp-per-query
+static std::atomic<int> g_graph_mode{0};
+static bool use_wq(const mse_index *ix, uint32_t nq) {
+    const int m = g_graph_mode.load(std::memory_order_relaxed);
+    if (m == 1) return false;
+    if (m == 2) return true;
+    return nq >= (uint32_t)sm_count(ix->device) * 4;
+}
+// number of workers (= visited-set tables) a launch for nq queries uses; non-decreasing in nq
+uint32_t greedy_grid(const mse_index *ix, uint32_t nq) {
+    const uint32_t sms = (uint32_t)sm_count(ix->device);
+    if (use_wq(ix, nq)) return std::min<uint32_t>((nq + kWqWarps - 1) / kWqWarps, sms * 4) * kWqWarps;
+    return std::min<uint32_t>(nq, sms * 2);
+}
 
 int greedy_search_launch(mse_index *ix, const __half *d_queries, const uint32_t *d_q_rows, uint32_t nq, const uint32_t *d_starts,
-                         uint32_t start, uint32_t L, uint32_t filter_from, uint32_t *d_htabs, uint32_t hcap, uint32_t grid, GreedyOut o,
+                         uint32_t start, uint32_t L, uint32_t filter_from, uint32_t *d_htabs, uint32_t hcap, uint32_t workers, GreedyOut o,
                          cudaStream_t st) {
-    const size_t smem = gs_smem_bytes(L, ix->d);
+    GraphArgs g{ix->x, ix->adj, ix->deg, ix->graph_stride, ix->d, ix->n};
+    if (use_wq(ix, nq) && workers >= (uint32_t)kWqWarps) {
+        const bool fixed = ix->d == 1152;
+        const size_t smem = wq_warp_bytes(L, ix->graph_stride, ix->d, !fixed) * kWqWarps;
+        if (smem <= 200 * 1024) {
+            const uint32_t grid = std::min<uint32_t>(workers / kWqWarps, (nq + kWqWarps - 1) / kWqWarps);
+            if (fixed) {
+                MSE_CUDA(cudaFuncSetAttribute(k_greedy_search_wq<36>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_greedy_search_wq<36><<<grid, kWqWarps * 32, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, d_htabs, hcap, o);
+            } else {
+                MSE_CUDA(cudaFuncSetAttribute(k_greedy_search_wq<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_greedy_search_wq<0><<<grid, kWqWarps * 32, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, d_htabs, hcap, o);
+            }
+            MSE_LAUNCH_OK();
+            return MSE_OK;
+        }
+    }
+    const size_t smem = gs_smem_bytes(L, ix->d, ix->graph_stride);
     MSE_REQUIRE(smem <= 200 * 1024, MSE_ERR_UNSUPPORTED, "greedy_search: L=%u does not fit shared memory", L);
     MSE_CUDA(cudaFuncSetAttribute(k_greedy_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GraphArgs g{ix->x, ix->adj, ix->deg, ix->graph_stride, ix->d, ix->n};
-    k_greedy_search<<<grid, kGsThreads, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, d_htabs, hcap, o);
+    k_greedy_search<<<std::min(workers, nq), kGsThreads, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, d_htabs, hcap, o);
     MSE_LAUNCH_OK();
     return MSE_OK;
 }
@@ -689,13 +767,55 @@ MSE_API int mse_search_graph(mse_index *ix, const uint16_t *q_f16, uint32_t nq, 
     return rc;
 }
 
+MSE_API int mse_search_graph_set_mode(int mode) {
+    MSE_REQUIRE(mode >= 0 && mode <= 2, MSE_ERR_INVALID, "search_graph_set_mode: mode %d (0 auto, 1 CTA per query, 2 warp per query)", mode);
+    g_graph_mode.store(mode, std::memory_order_relaxed);
+    return MSE_OK;
+}
+
+// greedy_search with every buffer already in HBM, asynchronous on `stream` (no allocation in steady state, no sync).
+// The per-query overflow status stays on the device; mse_search_graph_check reads it back.
+MSE_API int mse_search_graph_dev(mse_index *ix, const uint16_t *d_q_f16, uint32_t nq, uint32_t L, const uint32_t *d_starts, uint32_t start,
+                                 int base_vectors_only, uint32_t query_breakpoint, uint32_t *d_ids, int64_t *d_scores, uint32_t *d_len,
+                                 uint64_t *d_distances, void *stream) {
+    MSE_CHECK(require_graph(ix, "search_graph_dev"));
+    MSE_REQUIRE(d_q_f16 && d_ids && d_scores && d_len && d_distances, MSE_ERR_INVALID, "search_graph_dev: NULL buffer");
+    MSE_REQUIRE(L >= 1 && L <= 4096, MSE_ERR_UNSUPPORTED, "search_graph_dev: L=%u out of range [1,4096]", L);
+    if (nq == 0) return MSE_OK;
+    MSE_CHECK(use_device(ix->device));
+    const uint32_t workers = greedy_grid(ix, nq);
+    const uint32_t hcap = greedy_hash_capacity(L, ix->graph_stride);
+    MSE_CHECK(ix->gw_htabs.ensure((size_t)workers * hcap * 4));
+    MSE_CHECK(ix->gw_status.ensure((size_t)nq * 4));
+    GreedyOut o{d_ids, (long long *)d_scores, d_len, (unsigned long long *)d_distances, nullptr, nullptr, nullptr, 0, ix->gw_status.as<uint32_t>()};
+    return greedy_search_launch(ix, (const __half *)d_q_f16, nullptr, nq, d_starts, start, L, base_vectors_only ? query_breakpoint : 0xFFFFFFFFu,
+                                ix->gw_htabs.as<uint32_t>(), hcap, workers, o, (cudaStream_t)stream);
+}
+
+// synchronises the device and reports a visited-set overflow of the last mse_search_graph_dev call on this handle
+MSE_API int mse_search_graph_check(mse_index *ix, uint32_t nq) {
+    MSE_REQUIRE(ix != nullptr, MSE_ERR_INVALID, "search_graph_check: NULL handle");
+    MSE_CHECK(use_device(ix->device));
+    MSE_CUDA(cudaDeviceSynchronize());
+    if (nq == 0 || !ix->gw_status.p) return MSE_OK;
+    MSE_REQUIRE((size_t)nq * 4 <= ix->gw_status.cap, MSE_ERR_INVALID, "search_graph_check: nq=%u exceeds the last search", nq);
+    std::vector<uint32_t> status(nq);
+    MSE_CUDA(cudaMemcpy(status.data(), ix->gw_status.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < nq; i++) {
+        MSE_REQUIRE(!(status[i] & 1u), MSE_ERR_UNSUPPORTED, "search_graph: visited-set table overflowed for query %u", i);
+        MSE_REQUIRE(!(status[i] & 2u), MSE_ERR_UNSUPPORTED, "search_beam_dev: query %u expanded more nodes than the visit list holds", i);
+    }
+    return MSE_OK;
+}
+
 // Beam search over the packed index (query_disk_index.rs:144-212).  luts: [nq][M*C] f32 from mse_pq_preprocess_query;
 // desc_scales: [nq][n_desc] or NULL.  out_ids/out_scores: [nq][out_cap] expanded nodes in visit order (the caller sorts by
 // score as :529 does); out_len/cmps/pq_cmps: [nq].
-MSE_API int mse_search_beam(mse_index *ix, const uint16_t *q_f16, const float *luts, const float *desc_scales, uint32_t nq, uint32_t L,
+static int search_beam_impl(mse_index *ix, const uint16_t *q_f16, const float *luts, const float *desc_scales, uint32_t nq, uint32_t L,
                             uint32_t W, const uint32_t *starts, uint32_t start, int disable_pq, uint32_t n_centroids, uint32_t *out_ids,
-                            int64_t *out_scores, uint32_t *out_len, uint32_t out_cap, uint64_t *cmps, uint64_t *pq_cmps) {
+                            int64_t *out_scores, uint32_t *out_len, uint32_t out_cap, uint64_t *cmps, uint64_t *pq_cmps, const float *code_bias) {
     MSE_CHECK(require_graph(ix, "search_beam"));
+    MSE_REQUIRE(!code_bias || (ix->code_scale && !disable_pq), MSE_ERR_STATE, "search_beam_scaled: per-vector code scales missing (mse_index_set_code_scales)");
     MSE_REQUIRE(q_f16 && out_ids && out_scores && out_len && cmps && pq_cmps && out_cap >= 1, MSE_ERR_INVALID, "search_beam: NULL buffer");
     MSE_REQUIRE(disable_pq || (ix->pq_codes && luts && n_centroids), MSE_ERR_STATE, "search_beam: PQ codes / LUTs missing (mse_index_set_pq_codes)");
     MSE_REQUIRE(L >= 1 && L <= 4096 && W >= 1 && W <= 64, MSE_ERR_UNSUPPORTED, "search_beam: L=%u W=%u out of range", L, W);
@@ -704,15 +824,17 @@ MSE_API int mse_search_beam(mse_index *ix, const uint16_t *q_f16, const float *l
     MSE_CHECK(use_device(ix->device));
     const uint32_t M = ix->code_size, C = n_centroids;
     const size_t lut_bytes = disable_pq ? 16 : (size_t)M * C * 4;
-    const size_t smem = ((gs_smem_bytes(L, ix->d) + 15) & ~(size_t)15) + lut_bytes;
+    const size_t smem = ((gs_smem_bytes(L, ix->d, ix->graph_stride) + 15) & ~(size_t)15) + lut_bytes;
     MSE_REQUIRE(smem <= 220 * 1024, MSE_ERR_UNSUPPORTED, "search_beam: L=%u with a %zu-byte LUT does not fit shared memory", L, lut_bytes);
     MSE_CUDA(cudaFuncSetAttribute(k_beam_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t grid = std::min<uint32_t>(nq, (uint32_t)sm_count(ix->device) * 2);
     const uint32_t hcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * ix->graph_stride * 8);
-    DevBuf b_q, b_lut, b_ds, b_ids, b_sc, b_len, b_c, b_p, b_st, b_h, b_starts;
+    DevBuf b_q, b_lut, b_ds, b_ids, b_sc, b_len, b_c, b_p, b_st, b_h, b_starts, b_cb;
     int rc = MSE_OK;
     std::vector<uint32_t> status(nq);
     do {
+        if (code_bias && (rc = b_cb.ensure((size_t)nq * 4))) break;
+        if (code_bias) cudaMemcpy(b_cb.p, code_bias, (size_t)nq * 4, cudaMemcpyHostToDevice);
         if ((rc = b_q.ensure((size_t)nq * ix->d * 2)) || (rc = b_lut.ensure(std::max<size_t>((size_t)nq * M * C * 4, 16))) ||
             (rc = b_ids.ensure((size_t)nq * out_cap * 4)) || (rc = b_sc.ensure((size_t)nq * out_cap * 8)) || (rc = b_len.ensure((size_t)nq * 4)) ||
             (rc = b_c.ensure((size_t)nq * 8)) || (rc = b_p.ensure((size_t)nq * 8)) || (rc = b_st.ensure((size_t)nq * 4)) ||
@@ -725,9 +847,9 @@ MSE_API int mse_search_beam(mse_index *ix, const uint16_t *q_f16, const float *l
         if (starts) cudaMemcpy(b_starts.p, starts, (size_t)nq * 4, cudaMemcpyHostToDevice);
         if (ix->n_desc) cudaMemcpy(b_ds.p, desc_scales, (size_t)nq * ix->n_desc * 4, cudaMemcpyHostToDevice);
         GraphArgs g{ix->x, ix->adj, ix->deg, ix->graph_stride, ix->d, ix->n};
-        BeamArgs ba{ix->pq_codes, M, C, ix->desc, ix->has_url, ix->n_desc, disable_pq};
+        BeamArgs ba{ix->pq_codes, M, C, ix->desc, ix->has_url, ix->n_desc, disable_pq, code_bias ? ix->code_scale : nullptr, b_cb.as<float>(), nullptr, 0, 0};
         BeamOut o{b_ids.as<uint32_t>(), b_sc.as<long long>(), b_len.as<uint32_t>(), out_cap, b_c.as<unsigned long long>(),
-                  b_p.as<unsigned long long>(), b_st.as<uint32_t>()};
+                  b_p.as<unsigned long long>(), b_st.as<uint32_t>(), 0, nullptr, nullptr, nullptr};
         k_beam_search<<<grid, kGsThreads, smem>>>(g, ba, b_q.as<__half>(), b_lut.as<float>(), ix->n_desc ? b_ds.as<float>() : nullptr, nq,
                                                  starts ? b_starts.as<uint32_t>() : nullptr, start, L, W, b_h.as<uint32_t>(), hcap, o);
         count_launch();
@@ -740,11 +862,80 @@ MSE_API int mse_search_beam(mse_index *ix, const uint16_t *q_f16, const float *l
         cudaMemcpy(pq_cmps, b_p.p, (size_t)nq * 8, cudaMemcpyDeviceToHost);
         cudaMemcpy(status.data(), b_st.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
         for (uint32_t i = 0; i < nq; i++)
-            if (status[i]) { set_error("search_beam: visited-set table overflowed for query %u", i); rc = MSE_ERR_UNSUPPORTED; break; }
+            if (status[i] & 1u) { set_error("search_beam: visited-set table overflowed for query %u", i); rc = MSE_ERR_UNSUPPORTED; break; }
     } while (0);
     b_q.release(); b_lut.release(); b_ds.release(); b_ids.release(); b_sc.release(); b_len.release(); b_c.release(); b_p.release();
-    b_st.release(); b_h.release(); b_starts.release();
+    b_st.release(); b_h.release(); b_starts.release(); b_cb.release();
     return rc;
+}
+
+MSE_API int mse_search_beam(mse_index *ix, const uint16_t *q_f16, const float *luts, const float *desc_scales, uint32_t nq, uint32_t L,
+                            uint32_t W, const uint32_t *starts, uint32_t start, int disable_pq, uint32_t n_centroids, uint32_t *out_ids,
+                            int64_t *out_scores, uint32_t *out_len, uint32_t out_cap, uint64_t *cmps, uint64_t *pq_cmps) {
+    return search_beam_impl(ix, q_f16, luts, desc_scales, nq, L, W, starts, start, disable_pq, n_centroids, out_ids, out_scores, out_len, out_cap,
+                            cmps, pq_cmps, nullptr);
+}
+
+// The same traversal with candidates ranked by  f32(sum of LUT entries) * code_scale[id] + code_bias[q]  -- the RabitQ
+// estimator of diskann/rabitq.py:42-48 when luts / code_bias come from mse_rabitq_preprocess_query, the codes from
+// mse_rabitq_encode and code_scale[id] = norms[id] * dots[id] (mse_index_set_code_scales).  Expanded nodes are still scored
+// exactly, as query_disk_index.rs:169-170 does.
+MSE_API int mse_search_beam_scaled(mse_index *ix, const uint16_t *q_f16, const float *luts, const float *code_bias, const float *desc_scales,
+                                   uint32_t nq, uint32_t L, uint32_t W, const uint32_t *starts, uint32_t start, uint32_t n_centroids,
+                                   uint32_t *out_ids, int64_t *out_scores, uint32_t *out_len, uint32_t out_cap, uint64_t *cmps, uint64_t *pq_cmps) {
+    MSE_REQUIRE(code_bias != nullptr, MSE_ERR_INVALID, "search_beam_scaled: code_bias is NULL");
+    return search_beam_impl(ix, q_f16, luts, desc_scales, nq, L, W, starts, start, 0, n_centroids, out_ids, out_scores, out_len, out_cap, cmps,
+                            pq_cmps, code_bias);
+}
+
+// Beam search with every buffer in HBM, asynchronous on `stream`, top-k selected on the device.  Candidate scores come from
+// d_luts ([nq][M * n_centroids], PQ ADC), or -- when d_qtm is given -- from RabitQ byte tables the kernel builds in shared
+// memory out of d_qtm ([nq][output_dims + 1] from mse_rabitq_query_dev) with the per-vector scales of mse_index_set_code_scales.
+MSE_API int mse_search_beam_dev(mse_index *ix, const uint16_t *d_q_f16, const float *d_luts, const float *d_qtm, uint32_t rabitq_output_dims,
+                                uint32_t rabitq_n_dims, const float *d_desc_scales, uint32_t nq, uint32_t L, uint32_t W, const uint32_t *d_starts,
+                                uint32_t start, uint32_t n_centroids, uint32_t topk, uint32_t *d_top_ids, int64_t *d_top_scores,
+                                uint32_t *d_top_len, uint64_t *d_cmps, uint64_t *d_pq_cmps, void *stream) {
+    MSE_CHECK(require_graph(ix, "search_beam_dev"));
+    MSE_REQUIRE(d_q_f16 && d_top_ids && d_top_scores && d_top_len && d_cmps && d_pq_cmps && topk >= 1, MSE_ERR_INVALID, "search_beam_dev: NULL buffer");
+    MSE_REQUIRE(ix->pq_codes && (d_luts || d_qtm), MSE_ERR_STATE, "search_beam_dev: codes (mse_index_set_pq_codes) and d_luts or d_qtm are required");
+    MSE_REQUIRE(!d_qtm || (ix->code_scale && rabitq_output_dims == ix->code_size * 8 && rabitq_n_dims), MSE_ERR_STATE,
+                "search_beam_dev: RabitQ mode needs mse_index_set_code_scales and output_dims == 8 * code size");
+    MSE_REQUIRE(L >= 1 && L <= 4096 && W >= 1 && W <= 64, MSE_ERR_UNSUPPORTED, "search_beam_dev: L=%u W=%u out of range", L, W);
+    MSE_REQUIRE(!ix->n_desc || d_desc_scales, MSE_ERR_INVALID, "search_beam_dev: the index has descriptors but d_desc_scales is NULL");
+    if (nq == 0) return MSE_OK;
+    MSE_CHECK(use_device(ix->device));
+    const uint32_t M = ix->code_size, C = d_qtm ? 256u : n_centroids;
+    MSE_REQUIRE(C >= 1, MSE_ERR_INVALID, "search_beam_dev: n_centroids is 0");
+    const size_t smem = ((gs_smem_bytes(L, ix->d, ix->graph_stride) + 15) & ~(size_t)15) + (size_t)M * C * 4;
+    MSE_REQUIRE(smem <= 220 * 1024, MSE_ERR_UNSUPPORTED, "search_beam_dev: L=%u with a %zu-byte LUT does not fit shared memory", L, (size_t)M * C * 4);
+    MSE_CUDA(cudaFuncSetAttribute(k_beam_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(3, (size_t)(224 * 1024) / (smem + 1024)));
+    const uint32_t grid = std::min<uint32_t>(nq, (uint32_t)sm_count(ix->device) * per_sm);
+    const uint32_t hcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * ix->graph_stride * 8);
+    const uint32_t cap = std::max<uint32_t>(8 * L + 64, topk);
+    MSE_CHECK(ix->gw_htabs.ensure((size_t)grid * 2 * hcap * 4));
+    MSE_CHECK(ix->gw_status.ensure((size_t)nq * 4));
+    MSE_CHECK(ix->gw_vis_ids.ensure((size_t)nq * cap * 4));
+    MSE_CHECK(ix->gw_vis_sc.ensure((size_t)nq * cap * 8));
+    MSE_CHECK(ix->gw_vis_len.ensure((size_t)nq * 4));
+    GraphArgs g{ix->x, ix->adj, ix->deg, ix->graph_stride, ix->d, ix->n};
+    BeamArgs ba{ix->pq_codes, M, C, ix->desc, ix->has_url, ix->n_desc, 0, d_qtm ? ix->code_scale : nullptr, nullptr, d_qtm, rabitq_output_dims, rabitq_n_dims};
+    BeamOut o{ix->gw_vis_ids.as<uint32_t>(), ix->gw_vis_sc.as<long long>(), ix->gw_vis_len.as<uint32_t>(), cap, (unsigned long long *)d_cmps,
+              (unsigned long long *)d_pq_cmps, ix->gw_status.as<uint32_t>(), topk, d_top_ids, (long long *)d_top_scores, d_top_len};
+    k_beam_search<<<grid, kGsThreads, smem, (cudaStream_t)stream>>>(g, ba, (const __half *)d_q_f16, d_luts, ix->n_desc ? d_desc_scales : nullptr, nq,
+                                                                    d_starts, start, L, W, ix->gw_htabs.as<uint32_t>(), hcap, o);
+    MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
+MSE_API int mse_index_set_code_scales(mse_index *ix, const float *scales) {
+    MSE_REQUIRE(ix != nullptr && scales != nullptr, MSE_ERR_INVALID, "index_set_code_scales: bad argument");
+    MSE_CHECK(use_device(ix->device));
+    if (ix->code_scale) cudaFree(ix->code_scale);
+    ix->code_scale = nullptr;
+    MSE_CUDA(cudaMalloc(&ix->code_scale, std::max<size_t>(ix->n * 4, 16)));
+    MSE_CUDA(cudaMemcpy(ix->code_scale, scales, ix->n * 4, cudaMemcpyHostToDevice));
+    return MSE_OK;
 }
 
 // exact i64 scores of one fp16 query against every row of the index (query_disk_index.rs:262-273 without the sort)

@@ -41,6 +41,7 @@ struct mse_index {
     uint32_t graph_stride = 0;
     uint8_t *pq_codes = nullptr;               // [n][code_size]
     uint32_t code_size = 0;
+    float *code_scale = nullptr;               // [n] per-vector factor of scaled codes (RabitQ: |o| * <o_bar, o>)
     uint8_t *desc = nullptr, *has_url = nullptr;  // [n][n_desc], [n]
     uint32_t n_desc = 0;
     int flat_mode = 0;
@@ -49,6 +50,7 @@ struct mse_index {
     size_t prof_used = 0;
     uint64_t stats[8] = {0};
     mse::FlatWork fw;
+    mse::DevBuf gw_htabs, gw_status, gw_vis_ids, gw_vis_sc, gw_vis_len;  // graph search workspace of the device-pointer API (visited-set tables, per-query status)
     cudaStream_t stream = nullptr;  // handle-owned stream for the host-pointer API
     // tensor-map cache for the tensor path (encoded lazily, invalidated on growth)
     bool tmap_valid = false;

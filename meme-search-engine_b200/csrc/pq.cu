@@ -191,6 +191,22 @@ __global__ void __launch_bounds__(256) k_rabitq_estimate(const float *__restrict
     }
 }
 
+// per-query byte tables of the RabitQ estimator for the graph traversal (graph.cu k_beam_search): lut[b][v] =
+// (1/sqrt(D)) * sum_{j<8} (+-) qt[8b+j], bias = <mean, q>.  One CTA per query.  qtm: [nq][O + 1] from k_rabitq_query.
+__global__ void __launch_bounds__(256) k_rabitq_lut(const float *__restrict__ qtm, uint32_t O, uint32_t D, float *__restrict__ lut,
+                                                    float *__restrict__ bias) {
+    const uint32_t nb = O / 8, v = blockIdx.x;
+    const float *qt = qtm + (size_t)v * (O + 1);
+    const float scale = rsqrtf((float)D);
+    for (uint32_t i = threadIdx.x; i < nb * 256; i += blockDim.x) {
+        const uint32_t b = i >> 8, val = i & 255;
+        float s = 0.f;
+        for (int j = 0; j < 8; j++) s += ((val >> j) & 1) ? qt[b * 8 + j] : -qt[b * 8 + j];
+        lut[(size_t)v * nb * 256 + i] = scale * s;
+    }
+    if (threadIdx.x == 0) bias[v] = qt[O];
+}
+
 // ---- minimal msgpack reader for opq.msgpack / rabitq.msgpack (maps of str -> int | float array)
 struct MpReader {
     const uint8_t *p, *end;
@@ -492,4 +508,40 @@ MSE_API int mse_rabitq_estimate(mse_rabitq *r, const float *q, const uint8_t *co
     } while (0);
     bq.release(); bt.release(); bc.release(); bn.release(); bd.release(); bo.release();
     return rc;
+}
+
+// query side of the estimator as byte tables (for mse_search_beam_scaled): luts [nq][output_dims/8][256], bias [nq]
+MSE_API int mse_rabitq_preprocess_query(mse_rabitq *r, const float *q, uint32_t nq, float *luts, float *bias) {
+    MSE_REQUIRE(r && q && luts && bias, MSE_ERR_INVALID, "rabitq_preprocess_query: NULL argument");
+    if (nq == 0) return MSE_OK;
+    MSE_CHECK(use_device(r->device));
+    const size_t per = (size_t)(r->O / 8) * 256;
+    DevBuf bq, bt, bl, bb;
+    int rc = MSE_OK;
+    do {
+        if ((rc = bq.ensure((size_t)nq * r->D * 4)) || (rc = bt.ensure((size_t)nq * (r->O + 1) * 4)) || (rc = bl.ensure((size_t)nq * per * 4)) ||
+            (rc = bb.ensure((size_t)nq * 4)))
+            break;
+        cudaMemcpy(bq.p, q, (size_t)nq * r->D * 4, cudaMemcpyHostToDevice);
+        k_rabitq_query<<<nq, 256, r->D * 4>>>(r->mean, r->Pt, bq.as<float>(), r->D, r->O, bt.as<float>());
+        count_launch();
+        k_rabitq_lut<<<nq, 256>>>(bt.as<float>(), r->O, r->D, bl.as<float>(), bb.as<float>());
+        count_launch();
+        cudaMemcpy(luts, bl.p, (size_t)nq * per * 4, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaMemcpy(bias, bb.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("rabitq_preprocess_query: %s", cudaGetErrorString(e)); rc = MSE_ERR_CUDA; }
+    } while (0);
+    bq.release(); bt.release(); bl.release(); bb.release();
+    return rc;
+}
+
+// query side of the estimator in HBM, asynchronous: d_qtm [nq][output_dims + 1] = (P q, <mean, q>) -- what
+// mse_search_beam_dev turns into byte tables in shared memory.  d_q: [nq][n_dims] f32.
+MSE_API int mse_rabitq_query_dev(mse_rabitq *r, const float *d_q, uint32_t nq, float *d_qtm, void *stream) {
+    MSE_REQUIRE(r && d_q && d_qtm, MSE_ERR_INVALID, "rabitq_query_dev: NULL argument");
+    if (nq == 0) return MSE_OK;
+    MSE_CHECK(use_device(r->device));
+    k_rabitq_query<<<nq, 256, r->D * 4, (cudaStream_t)stream>>>(r->mean, r->Pt, d_q, r->D, r->O, d_qtm);
+    MSE_LAUNCH_OK();
+    return MSE_OK;
 }

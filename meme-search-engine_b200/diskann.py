@@ -76,6 +76,12 @@ class VectorList(FlatIndex):
         hu = np.ascontiguousarray(has_url, np.uint8) if has_url is not None else None
         check(lib().mse_index_set_descriptors(self._h, _p(desc), desc.shape[1] if desc is not None else 0, _p(hu)), "mse_index_set_descriptors")
 
+    def set_code_scales(self, scales: np.ndarray):
+        """Per-vector factor of scaled codes; RabitQ (rabitq.py:47-48): norms * dots."""
+        scales = np.ascontiguousarray(scales, np.float32)
+        assert scales.size == self.ntotal
+        check(lib().mse_index_set_code_scales(self._h, _p(scales)), "mse_index_set_code_scales")
+
     def scores_i64(self, q16: np.ndarray) -> np.ndarray:
         """fast_dot_noprefetch of one query against every row (query_disk_index.rs:262-273)."""
         q16 = np.ascontiguousarray(q16)
@@ -139,6 +145,26 @@ def greedy_search(vecs: VectorList, queries16: np.ndarray, start, config: IndexB
     return SearchResult(ids, sc, ln, dist, visited)
 
 
+GRAPH_MODE_AUTO, GRAPH_MODE_CTA, GRAPH_MODE_WARP = 0, 1, 2
+
+
+def set_graph_mode(mode: int):
+    """Schedule of greedy_search on the GPU (one CTA or one warp per query); results are identical in every mode."""
+    check(lib().mse_search_graph_set_mode(int(mode)), "mse_search_graph_set_mode")
+
+
+def greedy_search_dev(vecs: VectorList, d_queries16: int, nq: int, L: int, start: int, d_ids: int, d_scores: int, d_len: int,
+                      d_distances: int, stream: int = 0, d_starts: int = 0, base_vectors_only: bool = False,
+                      query_breakpoint: int = 0xFFFFFFFF):
+    """greedy_search with device pointers (ints), asynchronous on `stream`; call greedy_search_check afterwards."""
+    check(lib().mse_search_graph_dev(vecs._h, d_queries16, nq, L, d_starts or None, start, int(base_vectors_only), query_breakpoint,
+                                     d_ids, d_scores, d_len, d_distances, stream or None), "mse_search_graph_dev")
+
+
+def greedy_search_check(vecs: VectorList, nq: int):
+    check(lib().mse_search_graph_check(vecs._h, nq), "mse_search_graph_check")
+
+
 class ProductQuantizer:
     """diskann/src/vector.rs:308-406."""
 
@@ -199,8 +225,10 @@ class ProductQuantizer:
 
 
 def beam_search(vecs: VectorList, queries16, luts, start, L: int, beamwidth: int, desc_scales=None, disable_pq=False, n_centroids=256,
-                out_cap: int = 4096):
-    """src/query_disk_index.rs:144-212, batched. -> per query (ids, exact scores) of expanded nodes in visit order, cmps, pq_cmps."""
+                out_cap: int = 4096, code_bias=None):
+    """src/query_disk_index.rs:144-212, batched. -> per query (ids, exact scores) of expanded nodes in visit order, cmps, pq_cmps.
+    With code_bias (one f32 per query) candidates are ranked by lut_sum * code_scale[id] + code_bias[q] (RabitQ codes:
+    RabitQ.preprocess_query + VectorList.set_code_scales)."""
     q = np.ascontiguousarray(queries16).reshape(-1, vecs.d)
     nq = q.shape[0]
     luts = np.ascontiguousarray(luts, np.float32) if luts is not None else None
@@ -210,10 +238,25 @@ def beam_search(vecs: VectorList, queries16, luts, start, L: int, beamwidth: int
     sc = np.empty((nq, out_cap), np.int64)
     ln = np.empty(nq, np.uint32)
     cmps, pq = np.empty(nq, np.uint64), np.empty(nq, np.uint64)
-    check(lib().mse_search_beam(vecs._h, _p(q), _p(luts), _p(ds), nq, L, beamwidth, _p(starts), int(start) if starts is None else 0,
-                                int(disable_pq), n_centroids, _p(ids), _p(sc), _p(ln), out_cap, _p(cmps), _p(pq)), "mse_search_beam")
+    if code_bias is not None:
+        cb = np.ascontiguousarray(code_bias, np.float32)
+        check(lib().mse_search_beam_scaled(vecs._h, _p(q), _p(luts), _p(cb), _p(ds), nq, L, beamwidth, _p(starts),
+                                           int(start) if starts is None else 0, n_centroids, _p(ids), _p(sc), _p(ln), out_cap, _p(cmps), _p(pq)),
+              "mse_search_beam_scaled")
+    else:
+        check(lib().mse_search_beam(vecs._h, _p(q), _p(luts), _p(ds), nq, L, beamwidth, _p(starts), int(start) if starts is None else 0,
+                                    int(disable_pq), n_centroids, _p(ids), _p(sc), _p(ln), out_cap, _p(cmps), _p(pq)), "mse_search_beam")
     res = [(ids[i, : min(ln[i], out_cap)].copy(), sc[i, : min(ln[i], out_cap)].copy()) for i in range(nq)]
     return res, cmps, pq
+
+
+def beam_search_dev(vecs: VectorList, d_queries16: int, nq: int, L: int, beamwidth: int, start: int, topk: int, d_top_ids: int,
+                    d_top_scores: int, d_top_len: int, d_cmps: int, d_pq_cmps: int, stream: int = 0, d_luts: int = 0, n_centroids: int = 256,
+                    d_qtm: int = 0, rabitq: "RabitQ | None" = None, d_desc_scales: int = 0, d_starts: int = 0):
+    """Beam search with device pointers (ints), top-k on the device; PQ tables (d_luts) or RabitQ (d_qtm + rabitq codec)."""
+    check(lib().mse_search_beam_dev(vecs._h, d_queries16, d_luts or None, d_qtm or None, rabitq.output_dims if rabitq else 0,
+                                    rabitq.n_dims if rabitq else 0, d_desc_scales or None, nq, L, beamwidth, d_starts or None, start, n_centroids,
+                                    topk, d_top_ids, d_top_scores, d_top_len, d_cmps, d_pq_cmps, stream or None), "mse_search_beam_dev")
 
 
 class RabitQ:
@@ -254,6 +297,18 @@ class RabitQ:
         norms, dots = np.empty(n, np.float32), np.empty(n, np.float32)
         check(lib().mse_rabitq_encode(self._h, _p(x16), n, _p(codes), _p(norms), _p(dots)), "mse_rabitq_encode")
         return codes, norms, dots
+
+    def preprocess_query(self, q):
+        """Query side of approx_dot as byte tables: (luts [nq, output_dims/8 * 256], bias [nq]) for beam_search(code_bias=...)."""
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, self.n_dims)
+        luts = np.empty((q.shape[0], self.output_dims // 8 * 256), np.float32)
+        bias = np.empty(q.shape[0], np.float32)
+        check(lib().mse_rabitq_preprocess_query(self._h, _p(q), q.shape[0], _p(luts), _p(bias)), "mse_rabitq_preprocess_query")
+        return luts, bias
+
+    def query_dev(self, d_q_f32: int, nq: int, d_qtm: int, stream: int = 0):
+        """(P q, <mean, q>) rows [nq][output_dims + 1] in HBM for beam_search_dev(d_qtm=...)."""
+        check(lib().mse_rabitq_query_dev(self._h, d_q_f32, nq, d_qtm, stream or None), "mse_rabitq_query_dev")
 
     def approx_dot(self, codes, norms, dots, q) -> np.ndarray:
         q = np.ascontiguousarray(q, np.float32)

@@ -901,9 +901,10 @@ static int64_t descriptor_product(const orc_disk_index *ix, const float *scales,
  * faithful_prebuffer != 0 reproduces :157 (the pre-buffer is cleared once per beam iteration, so later nodes
  * of a beam re-score earlier nodes' neighbours); 0 clears it per expanded node.
  */
-ORC_API size_t orc_beam_search(const orc_disk_index *ix, uint32_t start, const uint16_t *query, const float *lut,
+static size_t beam_search_impl(const orc_disk_index *ix, uint32_t start, const uint16_t *query, const float *lut,
                                const float *desc_scales, size_t L, size_t beamwidth, int disable_pq, int faithful_prebuffer,
-                               uint32_t *out_ids, int64_t *out_scores, size_t out_cap, uint64_t *counts) {
+                               uint32_t *out_ids, int64_t *out_scores, size_t out_cap, uint64_t *counts,
+                               const float *code_scale, float code_bias) {
     size_t n = ix->n, d = ix->d;
     uint8_t *vadj = (uint8_t *)calloc(n + 1, 1), *vis = (uint8_t *)calloc(n + 1, 1);
     orc_nb *nb = orc_nb_new(L);
@@ -957,6 +958,7 @@ ORC_API size_t orc_beam_search(const orc_disk_index *ix, uint32_t start, const u
                     float s = 0.0f;
                     const uint8_t *code = ix->pq_codes + (size_t)t * M;
                     for (size_t m = 0; m < M; m++) s += lut[m * ix->n_centroids + code[m]];
+                    if (code_scale) s = fmaf(s, code_scale[t], code_bias); /* RabitQ estimate, rabitq.py:47-48 */
                     sc = sat_trunc_f32(s * 4294967296.0f);
                     pq_cmps++;
                 }
@@ -968,4 +970,19 @@ ORC_API size_t orc_beam_search(const orc_disk_index *ix, uint32_t start, const u
     if (counts) { counts[0] = cmps; counts[1] = pq_cmps; }
     free(vadj); free(vis); orc_nb_free(nb); free(pre); free(pts); free(approx);
     return nout;
+}
+
+ORC_API size_t orc_beam_search(const orc_disk_index *ix, uint32_t start, const uint16_t *query, const float *lut,
+                               const float *desc_scales, size_t L, size_t beamwidth, int disable_pq, int faithful_prebuffer,
+                               uint32_t *out_ids, int64_t *out_scores, size_t out_cap, uint64_t *counts) {
+    return beam_search_impl(ix, start, query, lut, desc_scales, L, beamwidth, disable_pq, faithful_prebuffer, out_ids, out_scores, out_cap,
+                            counts, NULL, 0.0f);
+}
+
+/* candidates ranked by (sum of LUT entries) * code_scale[id] + code_bias: the traversal over RabitQ codes (diskann/rabitq.py:42-48
+ * as byte tables); everything else as orc_beam_search */
+ORC_API size_t orc_beam_search_scaled(const orc_disk_index *ix, uint32_t start, const uint16_t *query, const float *lut,
+                                      const float *code_scale, float code_bias, const float *desc_scales, size_t L, size_t beamwidth,
+                                      uint32_t *out_ids, int64_t *out_scores, size_t out_cap, uint64_t *counts) {
+    return beam_search_impl(ix, start, query, lut, desc_scales, L, beamwidth, 0, 0, out_ids, out_scores, out_cap, counts, code_scale, code_bias);
 }

@@ -90,6 +90,7 @@ def _bind(l):
         "orc_pq_apply_transform": (None, [vp, vp, sz, vp]), "orc_pq_quantize_batch": (None, [vp, vp, sz, vp]),
         "orc_pq_preprocess_query": (None, [vp, vp, vp]), "orc_pq_adc": (None, [vp, sz, sz, vp, sz, vp]),
         "orc_beam_search": (sz, [vp, u32, vp, vp, vp, sz, sz, C.c_int, C.c_int, vp, vp, sz, vp]),
+        "orc_beam_search_scaled": (sz, [vp, u32, vp, vp, vp, C.c_float, vp, sz, sz, vp, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(l, name)
@@ -354,7 +355,7 @@ class ProductQuantizer:
 # ---------------------------------------------------------------- packed-index beam search
 
 def beam_search(vectors, adj, offsets, pq_codes, lut, start, query, L, beamwidth, descriptors=None, desc_scales=None,
-                has_url=None, disable_pq=False, faithful_prebuffer=False, n_centroids=256):
+                has_url=None, disable_pq=False, faithful_prebuffer=False, n_centroids=256, code_scale=None, code_bias=0.0):
     """src/query_disk_index.rs:144-212 over in-memory node records.
     -> (ids, scores) of expanded nodes in visit order, (cmps, pq_cmps)."""
     v16 = as_u16(vectors)
@@ -373,6 +374,11 @@ def beam_search(vectors, adj, offsets, pq_codes, lut, start, query, L, beamwidth
     cap = n
     ids, sc = np.empty(cap, np.uint32), np.empty(cap, np.int64)
     counts = np.zeros(2, np.uint64)
-    m = lib().orc_beam_search(C.byref(ix), start, _p(q16), _p(lut), _p(scales), L, beamwidth, int(disable_pq),
-                              int(faithful_prebuffer), _p(ids), _p(sc), cap, _p(counts))
+    if code_scale is not None:
+        cs = _c(code_scale, np.float32)
+        m = lib().orc_beam_search_scaled(C.byref(ix), start, _p(q16), _p(lut), _p(cs), C.c_float(code_bias), _p(scales), L, beamwidth,
+                                         _p(ids), _p(sc), cap, _p(counts))
+    else:
+        m = lib().orc_beam_search(C.byref(ix), start, _p(q16), _p(lut), _p(scales), L, beamwidth, int(disable_pq),
+                                  int(faithful_prebuffer), _p(ids), _p(sc), cap, _p(counts))
     return ids[:m].copy(), sc[:m].copy(), (int(counts[0]), int(counts[1]))

@@ -23,7 +23,14 @@ def world(mse, oracle):
     return dict(n=n, R=R, L=L, x=x, g=g, med=med, vl=vl, cfg=cfg)
 
 
-def test_greedy_search_bit_exact(mse, oracle, world):
+@pytest.fixture(params=[1, 2], ids=["cta_per_query", "warp_per_query"])
+def graph_mode(mse, request):
+    mse.diskann.set_graph_mode(request.param)
+    yield request.param
+    mse.diskann.set_graph_mode(0)
+
+
+def test_greedy_search_bit_exact(mse, oracle, world, graph_mode):
     w = world
     q = np.concatenate([w["x"][:60], clustered_f16(62, 60, n_clusters=24), unit_rows(63, 8).astype(np.float16)])
     for L in (w["L"], 7, 130):
@@ -43,7 +50,7 @@ def test_greedy_search_bit_exact(mse, oracle, world):
             assert np.array_equal(res.visited[i][0], vi) and np.array_equal(res.visited[i][1], vs)
 
 
-def test_greedy_search_raw_random_graph_and_filter(mse, oracle):
+def test_greedy_search_raw_random_graph_and_filter(mse, oracle, graph_mode):
     """An un-pruned random graph has self loops; duplicate ids inside a list are injected by hand (robust_prune's skip-one
     quirk produces them in real graphs).  Also exercises base_vectors_only (lib.rs:196-199) and per-query starts."""
     n, R, L = 1500, 16, 32
@@ -70,6 +77,57 @@ def test_greedy_search_raw_random_graph_and_filter(mse, oracle):
             assert int(res.distances[i]) == d
             if bvo:
                 assert (res.ids[i, :m][1:] < qb).all() or res.ids[i, 0] >= qb
+
+
+@pytest.mark.parametrize("d", [64, 256])
+def test_greedy_search_other_dims(mse, oracle, graph_mode, d):
+    """d != 1152 takes the generic (query in shared memory) instantiation of the warp-per-query kernel."""
+    n, R, L = 800, 12, 20
+    x = clustered_f16(81, n, n_clusters=8, d=d)
+    g = oracle.IndexGraph(n, R)
+    oracle.random_fill_graph(g, R, seed=2)
+    vl = mse.diskann.VectorList.from_f16s(x)
+    vl.set_graph(g.adj.copy(), g.deg.copy())
+    cfg_o = oracle.make_config(r=R, l=L, maxc=100)
+    cfg_g = mse.diskann.IndexBuildConfig(r=R, l=L, maxc=100)
+    q = clustered_f16(82, 33, n_clusters=8, d=d)
+    res = mse.diskann.greedy_search(vl, q, 5, cfg_g, visited_cap=2048)
+    s = oracle.Scratch(n, cfg_o)
+    for i in range(q.shape[0]):
+        dist = oracle.greedy_search(s, 5, False, q[i], x, g, cfg_o)
+        m = int(res.len[i])
+        assert np.array_equal(res.ids[i, :m], s.neighbour_ids) and np.array_equal(res.scores[i, :m], s.neighbour_scores)
+        assert int(res.distances[i]) == dist
+        vi, vs = s.visited_list()
+        assert np.array_equal(res.visited[i][0], vi) and np.array_equal(res.visited[i][1], vs)
+
+
+def test_greedy_search_dev_matches_host_api(mse, world):
+    """Device-pointer entry (what bench.py times): same ids / scores / counters as the host-pointer call, in both schedules
+    and in the automatic one at a batch large enough to switch to warp-per-query."""
+    import torch
+    w = world
+    q = np.concatenate([clustered_f16(64, 700, n_clusters=24), w["x"][:68]])
+    nq, L = q.shape[0], 40
+    cfg_g = mse.diskann.IndexBuildConfig(r=w["R"], l=L, maxc=200)
+    mse.diskann.set_graph_mode(1)
+    ref = mse.diskann.greedy_search(w["vl"], q, w["med"], cfg_g)
+    dev = torch.device("cuda:0")
+    dq = torch.from_numpy(q.view(np.int16)).to(dev)
+    for mode in (0, 1, 2):
+        mse.diskann.set_graph_mode(mode)
+        ids = torch.zeros((nq, L), dtype=torch.int32, device=dev)
+        sc = torch.zeros((nq, L), dtype=torch.int64, device=dev)
+        ln = torch.zeros(nq, dtype=torch.int32, device=dev)
+        dist = torch.zeros(nq, dtype=torch.int64, device=dev)
+        mse.diskann.greedy_search_dev(w["vl"], dq.data_ptr(), nq, L, w["med"], ids.data_ptr(), sc.data_ptr(), ln.data_ptr(), dist.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream)
+        mse.diskann.greedy_search_check(w["vl"], nq)
+        assert np.array_equal(ids.cpu().numpy().view(np.uint32), ref.ids), mode
+        assert np.array_equal(sc.cpu().numpy(), ref.scores)
+        assert np.array_equal(ln.cpu().numpy().view(np.uint32), ref.len)
+        assert np.array_equal(dist.cpu().numpy().view(np.uint64), ref.distances)
+    mse.diskann.set_graph_mode(0)
 
 
 def test_scores_i64_and_medioid(mse, oracle, world):
@@ -211,3 +269,102 @@ def test_rabitq_vs_numpy(mse):
     g2 = mse.diskann.RabitQ.from_msgpack(ref.to_msgpack())
     c2, n2, d2 = g2.quantize(x[:50])
     assert np.array_equal(c2, codes[:50])
+
+
+def test_beam_search_over_rabitq_codes(mse, oracle, world):
+    """C4's traversal: candidates ranked by the RabitQ estimate (byte tables + per-vector scale + per-query bias), expanded nodes
+    scored exactly.  The tables are floating point (checked against the numpy restatement, tolerance 2e-5); given the tables,
+    the traversal is integer work and must match the C oracle bit for bit."""
+    from oracle.rabitq_np import RabitQ as NpRabitQ
+    w = world
+    x = w["x"]
+    ref = NpRabitQ.train(x[:1000].astype(np.float32), output_dims=512, seed=4)
+    g = mse.diskann.RabitQ(ref.mean, ref.p)
+    codes, norms, dots = g.quantize(x)
+    q = np.concatenate([x[200:220], clustered_f16(65, 20, n_clusters=24)])
+    luts, bias = g.preprocess_query(q.astype(np.float32))
+    # tables vs numpy: lut[b][v] = scale * sum_j (+-) (P q)[8b + j]
+    qt = (ref.p.astype(np.float64) @ q.astype(np.float64).T).T
+    signs = 2.0 * ((np.arange(256)[:, None] >> np.arange(8)[None, :]) & 1) - 1.0            # [256][8]
+    want = ref.scale * np.einsum("vj,qbj->qbv", signs, qt.reshape(q.shape[0], 64, 8))
+    assert np.abs(luts.reshape(q.shape[0], 64, 256) - want).max() < 2e-5
+    assert np.abs(bias - q.astype(np.float64) @ ref.mean.astype(np.float64)).max() < 2e-5
+    # the estimate through the tables equals approx_dot (rabitq.py:42-48)
+    est = (luts[0].reshape(64, 256)[np.arange(64)[None, :], codes[:300]].sum(axis=1) * (norms * dots)[:300] + bias[0])
+    assert np.abs(est - g.approx_dot(codes[:300], norms[:300], dots[:300], q[0].astype(np.float32))).max() < 2e-4
+    vl = w["vl"]
+    vl.set_descriptors(None, None)
+    vl.set_pq_codes(codes)
+    scale = (norms * dots).astype(np.float32)
+    vl.set_code_scales(scale)
+    adj, off = w["g"].to_csr()
+    for W, L in [(1, 32), (4, 64)]:
+        res, cmps, pqc = mse.diskann.beam_search(vl, q, luts, w["med"], L, W, code_bias=bias)
+        for i in range(q.shape[0]):
+            ids, sc, (c, pc) = oracle.beam_search(x, adj, off, codes, luts[i], w["med"], q[i], L, W, code_scale=scale, code_bias=float(bias[i]))
+            assert np.array_equal(res[i][0], ids), (W, i)
+            assert np.array_equal(res[i][1], sc)
+            assert int(cmps[i]) == c and int(pqc[i]) == pc
+
+
+def test_beam_search_dev_topk(mse, oracle, world):
+    """Device-pointer beam search (what bench.py times): RabitQ tables built in shared memory from (P q, <mean,q>) and PQ tables
+    from HBM; the on-device top-k must equal the stable sort (score desc, visit order) of the host-API visit list."""
+    import torch
+    from oracle.rabitq_np import RabitQ as NpRabitQ
+    w = world
+    x, vl = w["x"], w["vl"]
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    q = np.concatenate([x[300:330], clustered_f16(66, 34, n_clusters=24)])
+    nq, L, W, k = q.shape[0], 48, 3, 10
+    dq16 = torch.from_numpy(q.view(np.int16)).to(dev)
+    top_ids = torch.zeros((nq, k), dtype=torch.int32, device=dev)
+    top_sc = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+    top_len = torch.zeros(nq, dtype=torch.int32, device=dev)
+    cm = torch.zeros(nq, dtype=torch.int64, device=dev)
+    pc = torch.zeros(nq, dtype=torch.int64, device=dev)
+    vl.set_descriptors(None, None)
+
+    def expect(res):
+        out = []
+        for ids, sc in res:
+            o = np.argsort(-sc, kind="stable")[:k]
+            out.append((ids[o], sc[o]))
+        return out
+
+    def compare(res, cmps, pqc):
+        ti, ts, tl = top_ids.cpu().numpy().view(np.uint32), top_sc.cpu().numpy(), top_len.cpu().numpy()
+        for i, (ids, sc) in enumerate(expect(res)):
+            m = int(tl[i])
+            assert m == len(ids) and np.array_equal(ti[i, :m], ids) and np.array_equal(ts[i, :m], sc), i
+            assert (ti[i, m:] == 0xFFFFFFFF).all()
+        assert np.array_equal(cm.cpu().numpy().view(np.uint64), cmps) and np.array_equal(pc.cpu().numpy().view(np.uint64), pqc)
+
+    # RabitQ codes
+    ref = NpRabitQ.train(x[:1000].astype(np.float32), output_dims=512, seed=4)
+    g = mse.diskann.RabitQ(ref.mean, ref.p)
+    codes, norms, dots = g.quantize(x)
+    vl.set_pq_codes(codes)
+    vl.set_code_scales(norms * dots)
+    luts, bias = g.preprocess_query(q.astype(np.float32))
+    res, cmps, pqc = mse.diskann.beam_search(vl, q, luts, w["med"], L, W, code_bias=bias)
+    dq32 = torch.from_numpy(q.astype(np.float32)).to(dev)
+    qtm = torch.empty((nq, 513), dtype=torch.float32, device=dev)
+    g.query_dev(dq32.data_ptr(), nq, qtm.data_ptr(), stream)
+    mse.diskann.beam_search_dev(vl, dq16.data_ptr(), nq, L, W, w["med"], k, top_ids.data_ptr(), top_sc.data_ptr(), top_len.data_ptr(),
+                                cm.data_ptr(), pc.data_ptr(), stream, d_qtm=qtm.data_ptr(), rabitq=g)
+    mse.diskann.greedy_search_check(vl, nq)
+    compare(res, cmps, pqc)
+
+    # PQ codes, tables in HBM
+    po, pg, _, _ = _pq_setup(oracle, mse, x)
+    pcodes = pg.quantize_batch(x.astype(np.float32))
+    vl.set_pq_codes(pcodes)
+    pl = pg.preprocess_query(q.astype(np.float32))
+    res, cmps, pqc = mse.diskann.beam_search(vl, q, pl, w["med"], L, W)
+    dl = torch.from_numpy(pl).to(dev)
+    mse.diskann.beam_search_dev(vl, dq16.data_ptr(), nq, L, W, w["med"], k, top_ids.data_ptr(), top_sc.data_ptr(), top_len.data_ptr(),
+                                cm.data_ptr(), pc.data_ptr(), stream, d_luts=dl.data_ptr(), n_centroids=256)
+    mse.diskann.greedy_search_check(vl, nq)
+    compare(res, cmps, pqc)
