@@ -582,6 +582,54 @@ ORC_API uint64_t orc_greedy_search(orc_scratch *s, uint32_t start, int base_vect
     return distances;
 }
 
+/* greedy_search over a batch of queries, OpenMP over queries with one Scratch per thread (the way diskann/src/main.rs:117-125
+ * drives it through rayon); prefetches the next neighbour's row like lib.rs:202-203.  Used by bench.py's cpu_baseline leg. */
+ORC_API void orc_greedy_search_batch(const uint16_t *x, size_t n, size_t d, const orc_graph *g, const orc_build_config *cfg, uint32_t start,
+                                     const uint16_t *queries, size_t nq, uint32_t *out_ids, int64_t *out_scores, uint32_t *out_len,
+                                     uint64_t *out_distances) {
+    size_t L = cfg->l;
+#pragma omp parallel
+    {
+        orc_scratch *s = orc_scratch_new(n, cfg->l, cfg->r);
+#pragma omp for schedule(dynamic, 4)
+        for (long qi = 0; qi < (long)nq; qi++) {
+            const uint16_t *query = queries + (size_t)qi * d;
+            visit_clear(s);
+            orc_nb_clear(s->nb);
+            s->vlen = 0;
+            orc_nb_insert(s->nb, start, fast_dot(query, x + (size_t)start * d, d));
+            visit_insert(s, start);
+            uint64_t distances = 0;
+            uint32_t pt;
+            while (orc_nb_next_unvisited(s->nb, &pt)) {
+                size_t npre = 0;
+                const uint32_t *nbrs = g->adj + (size_t)pt * g->stride;
+                uint32_t dg = g->deg[pt];
+                if (dg > s->pre_cap) { s->pre_cap = dg; s->pre = (uint32_t *)realloc(s->pre, sizeof(uint32_t) * dg); }
+                for (uint32_t j = 0; j < dg; j++)
+                    if (visit_insert(s, nbrs[j])) s->pre[npre++] = nbrs[j];
+                for (size_t j = 0; j < npre; j++) {
+                    if (j + 1 < npre) {
+                        const char *nx = (const char *)(x + (size_t)s->pre[j + 1] * d);
+                        for (size_t b = 0; b < d * 2; b += 64) __builtin_prefetch(nx + b, 0, 3);
+                    }
+                    int64_t sc = fast_dot(query, x + (size_t)s->pre[j] * d, d);
+                    distances++;
+                    orc_nb_insert(s->nb, s->pre[j], sc);
+                }
+            }
+            size_t len = orc_nb_len(s->nb);
+            for (size_t i = 0; i < L; i++) {
+                out_ids[(size_t)qi * L + i] = i < len ? s->nb->ids[i] : 0xFFFFFFFFu;
+                out_scores[(size_t)qi * L + i] = i < len ? s->nb->scores[i] : 0;
+            }
+            out_len[qi] = (uint32_t)len;
+            out_distances[qi] = distances;
+        }
+        orc_scratch_free(s);
+    }
+}
+
 /* ------------------------------------------------------------------ robust_prune (lib.rs:215-285) */
 
 static void merge_existing(orc_scratch *s, uint32_t point, const uint32_t *neigh, size_t n_neigh, const uint16_t *x, size_t d) {

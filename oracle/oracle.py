@@ -84,6 +84,7 @@ def _bind(l):
         "orc_scratch_new": (vp, [sz, sz, sz]), "orc_scratch_free": (None, [vp]), "orc_scratch_nb": (vp, [vp]),
         "orc_scratch_visited_len": (sz, [vp]), "orc_scratch_visited_copy": (None, [vp, vp, vp]),
         "orc_greedy_search": (u64, [vp, u32, C.c_int, vp, vp, sz, vp, vp]),
+        "orc_greedy_search_batch": (None, [vp, sz, sz, vp, vp, u32, vp, sz, vp, vp, vp, vp]),
         "orc_robust_prune": (sz, [u32, vp, vp, sz, vp, sz, sz, vp, vp]),
         "orc_build_graph": (None, [vp, u32, vp, sz, vp, u64, C.c_int]),
         "orc_robust_stitch": (None, [vp, vp, sz, vp, u64]),
@@ -292,6 +293,19 @@ def greedy_search(scratch: Scratch, start: int, base_vectors_only: bool, query, 
     q16, x16 = as_u16(query), as_u16(x)
     return int(lib().orc_greedy_search(scratch._h, start, int(base_vectors_only), _p(q16), _p(x16), x16.shape[1],
                                        graph._h, C.byref(config)))
+
+
+def greedy_search_batch(start: int, queries, x, graph: IndexGraph, config: BuildConfig):
+    """greedy_search for a batch of queries on all host cores (OpenMP over queries, one Scratch per thread).
+    -> ids [nq, L] (0xFFFFFFFF past len), scores [nq, L], len [nq], distances [nq]."""
+    q16, x16 = as_u16(queries), as_u16(x)
+    q16 = q16.reshape(-1, x16.shape[1])
+    nq, L = q16.shape[0], int(config.l)
+    ids, sc = np.empty((nq, L), np.uint32), np.empty((nq, L), np.int64)
+    ln, dist = np.empty(nq, np.uint32), np.empty(nq, np.uint64)
+    lib().orc_greedy_search_batch(_p(x16), x16.shape[0], x16.shape[1], graph._h, C.byref(config), start, _p(q16), nq, _p(ids), _p(sc), _p(ln),
+                                  _p(dist))
+    return ids, sc, ln, dist
 
 
 def robust_prune(p: int, cand_ids, cand_scores, x, config: BuildConfig) -> np.ndarray:

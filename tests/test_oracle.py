@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import PyNeighbourBuffer, index_f16, np_fast_dot, np_flat_topk, unit_rows
+from helpers import PyNeighbourBuffer, clustered_f16, index_f16, np_fast_dot, np_flat_topk, unit_rows
 
 G = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -265,3 +265,22 @@ def test_beam_search_faithful_equals_clean(oracle):
         assert a[2][0] == b[2][0] and a[2][1] >= b[2][1]
         best = a[0][np.argmax(a[1])]
         assert best == qi
+
+
+def test_greedy_search_batch_equals_single(oracle):
+    """The OpenMP batch entry bench.py's cpu_baseline times returns what the per-query entry returns."""
+    n, R, L = 1200, 12, 24
+    x = clustered_f16(21, n, n_clusters=8)
+    g = oracle.IndexGraph(n, R)
+    oracle.random_fill_graph(g, R, seed=1)
+    cfg = oracle.make_config(r=R, l=L, maxc=100)
+    oracle.build_graph(g, oracle.medioid(x), x, cfg, seed=2)
+    q = clustered_f16(22, 37, n_clusters=8)
+    ids, sc, ln, dist = oracle.greedy_search_batch(3, q, x, g, cfg)
+    s = oracle.Scratch(n, cfg)
+    for i in range(q.shape[0]):
+        d = oracle.greedy_search(s, 3, False, q[i], x, g, cfg)
+        m = int(ln[i])
+        assert m == len(s.neighbour_ids) and d == int(dist[i])
+        assert np.array_equal(ids[i, :m], s.neighbour_ids) and np.array_equal(sc[i, :m], s.neighbour_scores)
+        assert (ids[i, m:] == 0xFFFFFFFF).all()
