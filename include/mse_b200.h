@@ -173,6 +173,10 @@ int mse_robust_prune(mse_index *ix, uint32_t p, const uint32_t *cand_ids, const 
 int mse_index_random_fill_graph(mse_index *ix, uint32_t r, uint64_t seed);
 /* medioid (lib.rs:54-68) */
 int mse_index_medioid(mse_index *ix, uint32_t *out);
+/* robust_stitch (lib.rs:326-374): nodes >= cfg->query_breakpoint are query nodes; base -> query edges are dropped and each
+ * base node that had one receives the query's best out-neighbours (<= max_add_per_stitch_iter per query, up to r).
+ * query_order: the query node ids in the order of the reference's shuffled loop (:333-334), or NULL for a seeded shuffle. */
+int mse_index_robust_stitch(mse_index *ix, const mse_build_config *cfg, const uint32_t *query_order, uint64_t seed);
 /* build_graph (lib.rs:287-324), batch-synchronous (see csrc/build.cu).  max_batch 0 = default.
  * stats (optional, 4 values): batches, point searches, back-edge merges, distance evaluations of the searches */
 int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_build_config *cfg, uint64_t seed, uint32_t max_batch,

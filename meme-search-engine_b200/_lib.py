@@ -75,6 +75,7 @@ _SIGS = {
     "mse_robust_prune": (_i32, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
     "mse_index_random_fill_graph": (_i32, [_vp, _u32, _u64]),
     "mse_index_medioid": (_i32, [_vp, _vp]),
+    "mse_index_robust_stitch": (_i32, [_vp, _vp, _vp, _u64]),
     "mse_index_build_vamana": (_i32, [_vp, _u32, _vp, _u64, _u32, _vp]),
     "mse_pq_create": (_i32, [_vp, _vp, _u32, _u32, _u32, _i32, C.POINTER(_vp)]),
     "mse_pq_load": (_i32, [_vp, C.c_size_t, _i32, C.POINTER(_vp)]),

@@ -326,6 +326,100 @@ __global__ void k_argmax_last(const long long *scores, uint64_t n, unsigned long
     if (threadIdx.x == 0) { best[2 * blockIdx.x] = s_hi[0]; best[2 * blockIdx.x + 1] = s_lo[0]; }
 }
 
+// ------------------------------------------------------------------ robust_stitch (lib.rs:326-374)
+//
+// The reference drops every base -> query edge, then walks the query nodes in a shuffled order and, for each base node that
+// pointed at the query, appends the query's best out-neighbours (by fast_dot to the base node) to the base node's list.
+// Only base nodes' lists are written and query nodes' lists are only read, so the work factors per BASE node: its incident
+// queries, in shuffled order, are applied one after the other.  One warp per base node; `rank[q - qb]` is the position of
+// query q in the shuffled order.  Same result as the sequential loop for the same order.
+static constexpr int kStitchWarps = 4;
+
+__global__ void __launch_bounds__(kStitchWarps * 32) k_robust_stitch(const __half *__restrict__ x, uint32_t d, uint32_t *adj, uint32_t *deg, uint32_t stride,
+                                                                     uint32_t qb, const uint32_t *__restrict__ rank, uint32_t r, uint32_t max_add) {
+    extern __shared__ __align__(16) uint8_t stitch_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per warp: qs[stride] (query targets), cs[stride] scores, cid[stride] ids
+    uint8_t *base = stitch_smem + (size_t)warp * ((size_t)stride * 16);
+    long long *cs = (long long *)base;
+    uint32_t *cid = (uint32_t *)(cs + stride);
+    uint32_t *qs = cid + stride;
+    const uint32_t b = blockIdx.x * kStitchWarps + warp;
+    if (b >= qb) return;
+    uint32_t *out = adj + (size_t)b * stride;
+    const uint32_t dg = min(deg[b], stride);
+    // partition the list: non-query targets stay (order kept), query targets go to qs (order kept)   :339-347
+    uint32_t nkeep = 0, nqs = 0;
+    for (uint32_t b0 = 0; b0 < dg; b0 += 32) {
+        const uint32_t i = b0 + lane;
+        const bool have = i < dg;
+        const uint32_t t = have ? out[i] : 0;
+        const bool isq = have && t >= qb;
+        const unsigned mq = __ballot_sync(0xffffffffu, isq), mk = __ballot_sync(0xffffffffu, have && !isq);
+        __syncwarp();
+        if (isq) qs[nqs + __popc(mq & ((1u << lane) - 1))] = t;
+        if (have && !isq) out[nkeep + __popc(mk & ((1u << lane) - 1))] = t;   // nkeep + rank <= i: never overtakes an unread entry of a later chunk
+        nqs += __popc(mq);
+        nkeep += __popc(mk);
+        __syncwarp();
+    }
+    uint32_t cur = nkeep;
+    if (nqs == 0) { if (lane == 0) deg[b] = cur; return; }
+    // queries in shuffled order (stable for duplicates): insertion sort by lane 0, lists are <= R long
+    if (lane == 0) {
+        for (uint32_t i = 1; i < nqs; i++) {
+            const uint32_t q = qs[i], rq = rank[q - qb];
+            uint32_t j = i;
+            while (j > 0 && rank[qs[j - 1] - qb] > rq) { qs[j] = qs[j - 1]; j--; }
+            qs[j] = q;
+        }
+    }
+    __syncwarp();
+    const __half *xb = x + (size_t)b * d;
+    for (uint32_t qi = 0; qi < nqs && cur < r; qi++) {
+        const uint32_t q = qs[qi];
+        const uint32_t qd = min(deg[q], stride);
+        const uint32_t *qn = adj + (size_t)q * stride;
+        for (uint32_t j = 0; j < qd; j++) {                                           // :355-358
+            const uint32_t nid = qn[j];
+            const float f = fast_dot_warp(xb, x + (size_t)nid * d, d, lane);
+            if (lane == 0) { cs[j] = fast_dot_fix(f); cid[j] = nid; }
+        }
+        __syncwarp();
+        // candidates by (score desc, position asc); walk them in that order (:359-371)
+        uint32_t added = 0;
+        for (uint32_t taken = 0; taken < qd; taken++) {
+            if (added >= max_add || cur >= r) break;
+            // next best not yet taken: tombstone taken entries with position marker in cid (kept) and score = kDead - 1? use a separate pass
+            long long best = 0; uint32_t bj = 0xFFFFFFFFu;
+            for (uint32_t j = lane; j < qd; j += 32) {
+                const long long sj = cs[j];
+                if (sj == kDead) continue;
+                if (bj == 0xFFFFFFFFu || sj > best) { best = sj; bj = j; }     // ascending j per lane: first max wins
+            }
+            for (int o = 16; o; o >>= 1) {
+                const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (oj != 0xFFFFFFFFu && (bj == 0xFFFFFFFFu || ob > best || (ob == best && oj < bj))) { best = ob; bj = oj; }
+            }
+            if (bj == 0xFFFFFFFFu) break;
+            const uint32_t nid = cid[bj];
+            __syncwarp();
+            if (lane == 0) cs[bj] = kDead;
+            bool present = false;
+            for (uint32_t t = lane; t < cur; t += 32) present |= out[t] == nid;
+            present = __any_sync(0xffffffffu, present);
+            if (!present) {
+                if (lane == 0) out[cur] = nid;
+                cur++;
+                added++;
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) deg[b] = cur;
+}
+
 static PruneCfg to_prune_cfg(const mse_build_config &c) {
     PruneCfg p;
     p.r = (uint32_t)c.r; p.maxc = (uint32_t)c.maxc; p.alpha = c.alpha; p.query_alpha = c.query_alpha;
@@ -507,5 +601,53 @@ MSE_API int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_bu
     b_sigma.release(); b_ids.release(); b_sc.release(); b_len.release(); b_dist.release(); b_st.release(); b_h.release(); b_vi.release();
     b_vs.release(); b_vl.release(); b_na.release(); b_nd.release(); b_in.release(); b_ic.release(); b_t.release(); b_nt.release();
     if (stats) { stats[0] = st_batches; stats[1] = st_search; stats[2] = st_merge; stats[3] = st_dist; }
+    return rc;
+}
+
+// robust_stitch (lib.rs:326-374).  query_order: the n - query_breakpoint query node ids in the order the reference's shuffled
+// loop would visit them (NULL: a seeded shuffle is drawn here).  Nodes >= cfg->query_breakpoint are query nodes.
+MSE_API int mse_index_robust_stitch(mse_index *ix, const mse_build_config *cfg, const uint32_t *query_order, uint64_t seed) {
+    MSE_REQUIRE(ix != nullptr && cfg != nullptr, MSE_ERR_INVALID, "robust_stitch: NULL argument");
+    MSE_REQUIRE(ix->adj && ix->deg, MSE_ERR_STATE, "robust_stitch: the index has no graph");
+    MSE_REQUIRE(ix->d % 64 == 0, MSE_ERR_UNSUPPORTED, "robust_stitch: fast_dot needs d %% 64 == 0");
+    MSE_REQUIRE(cfg->r >= 1 && cfg->r <= ix->graph_stride, MSE_ERR_INVALID, "robust_stitch: r=%llu exceeds the adjacency stride %u",
+                (unsigned long long)cfg->r, ix->graph_stride);
+    const uint64_t n = ix->n;
+    const uint32_t qb = cfg->query_breakpoint;
+    if (qb >= n) return MSE_OK;                                  // no query nodes: nothing to stitch (generate_index_shard.rs:129)
+    MSE_CHECK(use_device(ix->device));
+    const uint32_t nq = (uint32_t)(n - qb);
+    std::vector<uint32_t> order(nq), rank(nq);
+    if (query_order) {
+        std::vector<uint8_t> seen(nq, 0);
+        for (uint32_t i = 0; i < nq; i++) {
+            MSE_REQUIRE(query_order[i] >= qb && query_order[i] < n && !seen[query_order[i] - qb], MSE_ERR_INVALID,
+                        "robust_stitch: query_order is not a permutation of [query_breakpoint, n)");
+            seen[query_order[i] - qb] = 1;
+            order[i] = query_order[i];
+        }
+    } else {
+        for (uint32_t i = 0; i < nq; i++) order[i] = qb + i;
+        uint64_t s = seed ? seed : 0x9e3779b97f4a7c15ull;
+        auto next = [&]() { uint64_t z = (s += 0x9e3779b97f4a7c15ull); z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31); };
+        for (uint32_t i = nq; i > 1; i--) std::swap(order[i - 1], order[next() % i]);
+    }
+    for (uint32_t i = 0; i < nq; i++) rank[order[i] - qb] = i;
+    DevBuf b_rank;
+    int rc = MSE_OK;
+    do {
+        if ((rc = b_rank.ensure((size_t)nq * 4))) break;
+        cudaMemcpy(b_rank.p, rank.data(), (size_t)nq * 4, cudaMemcpyHostToDevice);
+        if (qb > 0) {
+            const size_t smem = (size_t)kStitchWarps * ix->graph_stride * 16;
+            k_robust_stitch<<<(qb + kStitchWarps - 1) / kStitchWarps, kStitchWarps * 32, smem>>>(ix->x, ix->d, ix->adj, ix->deg, ix->graph_stride, qb,
+                                                                                             b_rank.as<uint32_t>(), (uint32_t)cfg->r,
+                                                                                             (uint32_t)cfg->max_add_per_stitch_iter);
+            count_launch();
+        }
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { set_error("robust_stitch: %s", cudaGetErrorString(e)); rc = MSE_ERR_CUDA; }
+    } while (0);
+    b_rank.release();
     return rc;
 }

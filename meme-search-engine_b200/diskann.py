@@ -5,6 +5,7 @@
     IndexGraph::empty + random_fill_graph              random_fill_graph(vecs, r, seed)
     medioid(&vecs)                                     medioid(vecs)
     build_graph(rng, graph, medioid, vecs, config)     build_graph(vecs, medioid, config, seed)
+    robust_stitch(rng, graph, vecs, config)            robust_stitch(vecs, config, seed, order)
     greedy_search(scratch, start, ..., query, ...)     greedy_search(vecs, queries, start, config) -> SearchResult (batched)
     ProductQuantizer::{quantize_batch, preprocess_query, asymmetric_dot_product}   ProductQuantizer
     query_disk_index.rs greedy_search (beam, PQ)       beam_search(vecs, ...)
@@ -104,6 +105,12 @@ def build_graph(vecs: VectorList, medioid_: int, config: IndexBuildConfig, seed:
     stats = (C.c_uint64 * 4)()
     check(lib().mse_index_build_vamana(vecs._h, medioid_, C.byref(config), seed, max_batch, stats), "mse_index_build_vamana")
     return {"batches": int(stats[0]), "searches": int(stats[1]), "backedge_merges": int(stats[2]), "distances": int(stats[3])}
+
+
+def robust_stitch(vecs: VectorList, config: IndexBuildConfig, seed: int = 0, order=None):
+    """diskann/src/lib.rs:326-374 on the graph attached to `vecs`; `order` fixes the shuffled visiting order of the query nodes."""
+    o = np.ascontiguousarray(order, np.uint32) if order is not None else None
+    check(lib().mse_index_robust_stitch(vecs._h, C.byref(config), _p(o), seed), "mse_index_robust_stitch")
 
 
 def robust_prune(vecs: VectorList, p: int, cand_ids, cand_scores, config: IndexBuildConfig) -> np.ndarray:

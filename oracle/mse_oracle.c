@@ -803,7 +803,7 @@ static int cand_desc_cmp(const void *a, const void *b) {
     if (x->c.score != y->c.score) return x->c.score > y->c.score ? -1 : 1;
     return x->ord < y->ord ? -1 : (x->ord > y->ord ? 1 : 0);
 }
-ORC_API void orc_robust_stitch(orc_graph *g, const uint16_t *x, size_t d, const orc_build_config *cfg, uint64_t seed) {
+static void robust_stitch_impl(orc_graph *g, const uint16_t *x, size_t d, const orc_build_config *cfg, uint64_t seed, const uint32_t *given_order) {
     uint32_t qb = cfg->query_breakpoint;
     size_t n = g->n;
     if (qb >= n) return;
@@ -825,8 +825,11 @@ ORC_API void orc_robust_stitch(orc_graph *g, const uint16_t *x, size_t d, const 
         g->deg[b] = w;
     }
     uint32_t *order = (uint32_t *)malloc(sizeof(uint32_t) * nq);
-    for (size_t i = 0; i < nq; i++) order[i] = qb + (uint32_t)i;
-    shuffle_u32(order, nq, &seed);
+    if (given_order) memcpy(order, given_order, sizeof(uint32_t) * nq);
+    else {
+        for (size_t i = 0; i < nq; i++) order[i] = qb + (uint32_t)i;
+        shuffle_u32(order, nq, &seed);
+    }
     scand_t *cs = (scand_t *)malloc(sizeof(scand_t) * (g->stride + 1));
     for (size_t oi = 0; oi < nq; oi++) {
         uint32_t q = order[oi];
@@ -855,6 +858,14 @@ ORC_API void orc_robust_stitch(orc_graph *g, const uint16_t *x, size_t d, const 
     free(cs); free(order);
     for (size_t i = 0; i < nq; i++) free(in[i]);
     free(in); free(in_n); free(in_c);
+}
+
+ORC_API void orc_robust_stitch(orc_graph *g, const uint16_t *x, size_t d, const orc_build_config *cfg, uint64_t seed) {
+    robust_stitch_impl(g, x, d, cfg, seed, NULL);
+}
+/* the same with the shuffled visiting order of the query nodes (lib.rs:333-334) given by the caller */
+ORC_API void orc_robust_stitch_order(orc_graph *g, const uint16_t *x, size_t d, const orc_build_config *cfg, const uint32_t *order) {
+    robust_stitch_impl(g, x, d, cfg, 0, order);
 }
 
 /* ------------------------------------------------------------------ ProductQuantizer (vector.rs:308-406) */

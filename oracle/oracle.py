@@ -88,6 +88,7 @@ def _bind(l):
         "orc_robust_prune": (sz, [u32, vp, vp, sz, vp, sz, sz, vp, vp]),
         "orc_build_graph": (None, [vp, u32, vp, sz, vp, u64, C.c_int]),
         "orc_robust_stitch": (None, [vp, vp, sz, vp, u64]),
+        "orc_robust_stitch_order": (None, [vp, vp, sz, vp, vp]),
         "orc_pq_apply_transform": (None, [vp, vp, sz, vp]), "orc_pq_quantize_batch": (None, [vp, vp, sz, vp]),
         "orc_pq_preprocess_query": (None, [vp, vp, vp]), "orc_pq_adc": (None, [vp, sz, sz, vp, sz, vp]),
         "orc_beam_search": (sz, [vp, u32, vp, vp, vp, sz, sz, C.c_int, C.c_int, vp, vp, sz, vp]),
@@ -321,9 +322,15 @@ def build_graph(graph: IndexGraph, medioid_: int, x, config: BuildConfig, seed: 
     lib().orc_build_graph(graph._h, medioid_, _p(x16), x16.shape[1], C.byref(config), seed, int(parallel))
 
 
-def robust_stitch(graph: IndexGraph, x, config: BuildConfig, seed: int = 0):
+def robust_stitch(graph: IndexGraph, x, config: BuildConfig, seed: int = 0, order=None):
+    """diskann/src/lib.rs:326-374; `order` (query node ids in visiting order) replaces the seeded shuffle of :333-334."""
     x16 = as_u16(x)
-    lib().orc_robust_stitch(graph._h, _p(x16), x16.shape[1], C.byref(config), seed)
+    if order is not None:
+        o = _c(order, np.uint32)
+        assert o.size == graph.n - config.query_breakpoint
+        lib().orc_robust_stitch_order(graph._h, _p(x16), x16.shape[1], C.byref(config), _p(o))
+    else:
+        lib().orc_robust_stitch(graph._h, _p(x16), x16.shape[1], C.byref(config), seed)
 
 
 # ---------------------------------------------------------------- ProductQuantizer

@@ -368,3 +368,33 @@ def test_beam_search_dev_topk(mse, oracle, world):
                                 cm.data_ptr(), pc.data_ptr(), stream, d_luts=dl.data_ptr(), n_centroids=256)
     mse.diskann.greedy_search_check(vl, nq)
     compare(res, cmps, pqc)
+
+
+def test_robust_stitch_bit_exact(mse, oracle):
+    """robust_stitch (lib.rs:326-374) with the shuffled query order given: the GPU's per-base-node schedule must produce the
+    adjacency lists of the oracle's sequential loop, entry for entry.  Covers duplicate query targets inside one list, base
+    nodes with no query edge, full lists, and max_add_per_stitch_iter."""
+    n, qb, R = 1400, 1000, 16
+    x = clustered_f16(95, n, n_clusters=10)
+    rng = np.random.default_rng(3)
+    for max_add, fill in ((16, 10), (2, 12), (3, 16)):
+        g = oracle.IndexGraph(n, R)
+        adj = rng.integers(0, n, (n, R)).astype(np.uint32)
+        adj[:50, 3] = adj[:50, 1]                                  # duplicates inside a list
+        adj[50:80, :] = rng.integers(0, qb, (30, R))               # base nodes without query edges
+        deg = np.full(n, fill, np.uint32)
+        deg[100:200] = R
+        g.set(adj, deg)
+        order = (qb + rng.permutation(n - qb)).astype(np.uint32)
+        cfg_o = oracle.make_config(r=R, l=32, maxc=100, query_breakpoint=qb, max_add_per_stitch_iter=max_add)
+        cfg_g = mse.diskann.IndexBuildConfig(r=R, l=32, maxc=100, query_breakpoint=qb, max_add_per_stitch_iter=max_add)
+        vl = mse.diskann.VectorList.from_f16s(x)
+        vl.set_graph(adj.copy(), deg.copy())
+        oracle.robust_stitch(g, x, cfg_o, order=order)
+        mse.diskann.robust_stitch(vl, cfg_g, order=order)
+        ga, gd = vl.get_graph()
+        assert np.array_equal(gd, g.deg), (max_add, fill)
+        for i in range(n):
+            assert np.array_equal(ga[i, : gd[i]], g.adj[i, : g.deg[i]]), (max_add, fill, i)
+        assert (gd[:qb] >= 0).all() and not (np.concatenate([ga[i, : gd[i]] for i in range(qb)]) >= qb).any()
+        vl.close()
