@@ -398,3 +398,33 @@ def test_robust_stitch_bit_exact(mse, oracle):
             assert np.array_equal(ga[i, : gd[i]], g.adj[i, : g.deg[i]]), (max_add, fill, i)
         assert (gd[:qb] >= 0).all() and not (np.concatenate([ga[i, : gd[i]] for i in range(qb)]) >= qb).any()
         vl.close()
+
+
+def test_generate_index_shard_end_to_end(mse, oracle, tmp_path):
+    """The body of src/generate_index_shard.rs on the GPU: shard-input stream + queries.bin in, N.shard.bin + header out.
+    The graph that comes back must hold only base -> base edges (robust_stitch dropped the query edges), respect R, and
+    serve recall@10 >= 0.95 at L=48 through the ORACLE's greedy_search (i.e. a graph the reference's CPU code can use)."""
+    from mse_b200 import shard_io
+    n, nq_nodes, R = 2500, 300, 24
+    x = clustered_f16(33, n, n_clusters=20)
+    qn = clustered_f16(34, nq_nodes, n_clusters=20)
+    ids = (np.arange(n, dtype=np.uint32) * 7 + 3)
+    inp = str(tmp_path / "4.shard-input")
+    shard_io.write_shard_input(inp, 4, x.astype(np.float32).mean(axis=0), ids, x)
+    qn.tofile(str(tmp_path / "queries.bin"))
+    info = shard_io.generate_index_shard(inp, str(tmp_path), str(tmp_path / "queries.bin"), l=64, r=R, maxc=300, query_alpha=65536, seed=1)
+    assert info["vectors"] == n and info["queries"] == nq_nodes
+    hdr, adj, deg = shard_io.read_shard(str(tmp_path), 4)
+    assert hdr.id == 4 and hdr.max == int(ids.max()) and np.array_equal(hdr.mapping, ids) and hdr.medioid == info["medioid"]
+    assert deg.size == n and deg.max() <= R and deg.min() >= 1
+    assert all((adj[i, : deg[i]] < n).all() for i in range(n))
+    g = oracle.IndexGraph(n, R)
+    full = np.zeros((n, R), np.uint32)
+    full[:, : adj.shape[1]] = adj[:, :R]
+    g.set(full, deg)
+    cfg = oracle.make_config(r=R, l=48, maxc=300)
+    q = clustered_f16(35, 64, n_clusters=20)
+    got, _, _, _ = oracle.greedy_search_batch(hdr.medioid, q, x, g, cfg)
+    want, _ = oracle.flat_search(q.astype(np.float32), x, 10)
+    rec = np.mean([len(set(got[i, :10].tolist()) & set(want[i].tolist())) / 10 for i in range(64)])
+    assert rec >= 0.95, rec
