@@ -14,6 +14,7 @@
 #include "graph.cuh"
 #include "fastdot.cuh"
 #include <algorithm>
+#include <math.h>
 
 namespace mse {
 
@@ -246,12 +247,12 @@ __global__ void __launch_bounds__(kGsThreads) k_greedy_search(GraphArgs g, const
 // one query is a chain (pop -> adjacency -> visited set -> <= R row gathers -> inserts) with no parallelism across hops, so
 // a large batch is served best by many independent chains per SM: each warp owns one query and never waits at a CTA
 // barrier, 16 warps per SM keep >= 36 (two rows: 72) 64-byte row loads in flight each, which is what hides the
-// HBM gather latency.  The query slice of lane p (elements d = p mod 32, vector.rs:212-238) lives in registers.
+// HBM gather latency.  64 registers per thread -> 32 warps per SM, each with up to 36 128-byte row requests in flight.
 
 static constexpr int kWqWarps = 4;   // warps (queries in flight) per CTA
 
-__host__ __device__ static size_t wq_warp_bytes(uint32_t L, uint32_t stride, uint32_t d, bool q_in_smem) {
-    size_t o = (size_t)(L + 1) * 8 + (size_t)stride * 8 + (size_t)(L + 1) * 4 + (size_t)stride * 4 + (size_t)stride * 4 + (q_in_smem ? (size_t)d * 4 : 0) + (L + 1);
+__host__ __device__ static size_t wq_warp_bytes(uint32_t L, uint32_t stride, uint32_t d) {
+    size_t o = (size_t)(L + 1) * 8 + (size_t)stride * 8 + (size_t)(L + 1) * 4 + (size_t)stride * 4 + (size_t)stride * 4 + (size_t)d * 4 + (L + 1);
     return (o + 15) & ~(size_t)15;
 }
 
@@ -267,39 +268,67 @@ __device__ __forceinline__ bool hs_insert_nc(uint32_t *tab, uint32_t mask, uint3
     return false;
 }
 
-template <int NC>
-__device__ __forceinline__ void wq_score2(const float (&qr)[NC > 0 ? NC : 1], const float *qs, const __half *__restrict__ r0,
-                                          const __half *__restrict__ r1, uint32_t d, int lane, long long &s0, long long &s1) {
-    float p0 = 0.f, p1 = 0.f;
-    if constexpr (NC > 0) {
-        float a[NC], b[NC];
+// Two rows per pass, half a warp per row.  Every lane loads one half2 (elements 2*lane, 2*lane+1 of each 64-element chunk:
+// one 128-byte request per row and chunk); lane l < 16 then owns the reference's partial sums 2l and 2l+1 of row 0 and lane
+// 16 + l the same partials of row 1, so one shfl_xor(16) per chunk hands each half warp the other half of its row.  Partial i
+// still accumulates elements i, i+32, i+64, ... in that order with FMA (vector.rs:212-238), and the reduction below is the
+// tree of vector.rs:241-249 re-indexed for two partials per lane -- the scores are bit-identical to fast_dot.
+template <int NC2>   // 64-element chunks per row (d / 64), 0 = runtime d
+__device__ __forceinline__ void wq_score2(const float *qs, const __half *__restrict__ r0, const __half *__restrict__ r1, uint32_t d, int lane,
+                                          long long &s0, long long &s1) {
+    const unsigned full = 0xffffffffu;
+    const int l = lane & 15;
+    const bool upper = lane >= 16;
+    const uint32_t *a2 = reinterpret_cast<const uint32_t *>(r0) + lane;
+    const uint32_t *b2 = reinterpret_cast<const uint32_t *>(r1) + lane;
+    const float2 *q2 = reinterpret_cast<const float2 *>(qs);
+    float lo = 0.f, hi = 0.f;
+    auto step = [&](uint32_t va, uint32_t vb, uint32_t c) {
+        const uint32_t recv = __shfl_xor_sync(full, upper ? va : vb, 16);
+        const uint32_t first = upper ? recv : va, second = upper ? vb : recv;
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&first));
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&second));
+        const float2 qa = q2[32 * c + l], qb = q2[32 * c + 16 + l];
+        lo = fmaf(qa.x, f1.x, lo); hi = fmaf(qa.y, f1.y, hi);
+        lo = fmaf(qb.x, f2.x, lo); hi = fmaf(qb.y, f2.y, hi);
+    };
+    if constexpr (NC2 > 0) {
+        uint32_t va[NC2], vb[NC2];
 #pragma unroll
-        for (int c = 0; c < NC; c++) { a[c] = __half2float(r0[32 * c + lane]); b[c] = __half2float(r1[32 * c + lane]); }
+        for (int c = 0; c < NC2; c++) { va[c] = __ldg(a2 + 32 * c); vb[c] = __ldg(b2 + 32 * c); }
 #pragma unroll
-        for (int c = 0; c < NC; c++) { p0 = fmaf(qr[c], a[c], p0); p1 = fmaf(qr[c], b[c], p1); }
+        for (int c = 0; c < NC2; c++) step(va[c], vb[c], (uint32_t)c);
     } else {
+        const uint32_t nc = d >> 6;
 #pragma unroll 4
-        for (uint32_t c = lane; c < d; c += 32) { const float qv = qs[c]; p0 = fmaf(qv, __half2float(r0[c]), p0); p1 = fmaf(qv, __half2float(r1[c]), p1); }
+        for (uint32_t c = 0; c < nc; c++) step(__ldg(a2 + 32 * c), __ldg(b2 + 32 * c), c);
     }
-    s0 = fast_dot_fix(fast_dot_reduce(p0));
-    s1 = fast_dot_fix(fast_dot_reduce(p1));
+    lo += __shfl_down_sync(full, lo, 4);             // acc1+acc2 / acc3+acc4 (:241-242): valid at l in {0..3, 8..11}
+    hi += __shfl_down_sync(full, hi, 4);
+    const float pr = lo + hi;                        // hadd pairs (:243)
+    const float q4 = pr + __shfl_down_sync(full, pr, 2);   // lo + hi halves (:244-246): valid at l in {0, 1, 8, 9}
+    const int gb = lane & 16;
+    const float e0 = __shfl_sync(full, q4, gb), e1 = __shfl_sync(full, q4, gb + 1), e2 = __shfl_sync(full, q4, gb + 8), e3 = __shfl_sync(full, q4, gb + 9);
+    const float r = ((e0 + e1) + e2) + e3;           // :247-249
+    s0 = fast_dot_fix(__shfl_sync(full, r, 0));
+    s1 = fast_dot_fix(__shfl_sync(full, r, 16));
 }
 
-template <int NC>
-__global__ void __launch_bounds__(kWqWarps * 32, 4) k_greedy_search_wq(GraphArgs g, const __half *__restrict__ queries, const uint32_t *__restrict__ q_rows,
+template <int NC2>
+__global__ void __launch_bounds__(kWqWarps * 32, 8) k_greedy_search_wq(GraphArgs g, const __half *__restrict__ queries, const uint32_t *__restrict__ q_rows,
                                                                        uint32_t nq, const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L,
                                                                        uint32_t filter_from, uint32_t *htabs, uint32_t hcap, GreedyOut out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t S = g.stride;
-    uint8_t *base = smem_raw + (size_t)warp * wq_warp_bytes(L, S, g.d, NC == 0);
+    uint8_t *base = smem_raw + (size_t)warp * wq_warp_bytes(L, S, g.d);
     long long *nb_scores = (long long *)base;
     long long *pre_scores = nb_scores + (L + 1);
-    uint32_t *nb_ids = (uint32_t *)(pre_scores + S);
+    float *qs = (float *)(pre_scores + S);            // 8-byte aligned: read as float2
+    uint32_t *nb_ids = (uint32_t *)(qs + g.d);
     uint32_t *pre = nb_ids + (L + 1);
     uint32_t *raw = pre + S;
-    float *qs = (float *)(raw + S);
-    uint8_t *nb_vis = (uint8_t *)(qs + (NC == 0 ? g.d : 0));
+    uint8_t *nb_vis = (uint8_t *)(raw + S);
     const uint32_t gw = blockIdx.x * kWqWarps + warp, nw = gridDim.x * kWqWarps;
     uint32_t *htab = htabs + (size_t)gw * hcap;
     const uint32_t hmask = hcap - 1;
@@ -312,13 +341,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, 4) k_greedy_search_wq(GraphArgs
             for (uint32_t i = lane; i < hcap / 4; i += 32) t4[i] = e4;
         }
         const size_t qrow = q_rows ? q_rows[qi] : qi;
-        float qr[NC > 0 ? NC : 1];
-        if constexpr (NC > 0) {
-#pragma unroll
-            for (int c = 0; c < NC; c++) qr[c] = __half2float(queries[qrow * g.d + 32 * c + lane]);
-        } else {
-            for (uint32_t c = lane; c < g.d; c += 32) qs[c] = __half2float(queries[qrow * g.d + c]);
-        }
+        for (uint32_t c = lane; c < g.d; c += 32) qs[c] = __half2float(queries[qrow * g.d + c]);
         __syncwarp();
         NbView nb{nb_ids, nb_scores, nb_vis, 0, (int)L, -1};
         const uint32_t start = starts ? starts[qi] : start_all;
@@ -327,7 +350,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, 4) k_greedy_search_wq(GraphArgs
         {
             long long sc, sc_dup;
             const __half *r = g.x + (size_t)start * g.d;
-            wq_score2<NC>(qr, qs, r, r, g.d, lane, sc, sc_dup);
+            wq_score2<NC2>(qs, r, r, g.d, lane, sc, sc_dup);
             nb_insert(nb, start, sc, lane);                                          // :188
             if (lane == 0) hs_insert_nc(htab, hmask, start);                         // :189
             __syncwarp();
@@ -336,13 +359,16 @@ __global__ void __launch_bounds__(kWqWarps * 32, 4) k_greedy_search_wq(GraphArgs
             const uint32_t pt = nb_next_unvisited(nb, lane);
             if (pt == kEmpty || hfill * 4 > hcap * 3) break;
             // out-neighbours not seen before, first occurrence first (:193-200)
-            const uint32_t dg = min(g.deg[pt], S);
+            const uint32_t dgl = g.deg[pt];
             const uint32_t *nbrs = g.adj + (size_t)pt * S;
             int n_pre = 0;
-            for (uint32_t b0 = 0; b0 < dg; b0 += 32) {
+            for (uint32_t b0 = 0; b0 < S; b0 += 32) {
                 const uint32_t i = b0 + lane;
+                const uint32_t rawid = i < S ? nbrs[i] : kEmpty;                      // issued before the degree is known
+                const uint32_t dg = min(dgl, S);
+                if (b0 >= dg) break;
                 const bool have = i < dg;
-                const uint32_t id = have ? nbrs[i] : kEmpty;
+                const uint32_t id = have ? rawid : kEmpty;
                 const unsigned same = __match_any_sync(full, id);
                 bool ins = false;
                 if (have && (same & ((1u << lane) - 1)) == 0) ins = hs_insert_nc(htab, hmask, id);   // a copy in a lower lane wins
@@ -357,7 +383,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, 4) k_greedy_search_wq(GraphArgs
             for (int i = 0; i < n_pre; i += 2) {
                 const int j = i + 1 < n_pre ? i + 1 : i;
                 long long s0, s1;
-                wq_score2<NC>(qr, qs, g.x + (size_t)pre[i] * g.d, g.x + (size_t)pre[j] * g.d, g.d, lane, s0, s1);
+                wq_score2<NC2>(qs, g.x + (size_t)pre[i] * g.d, g.x + (size_t)pre[j] * g.d, g.d, lane, s0, s1);
                 if (lane == 0) { pre_scores[i] = s0; pre_scores[j] = s1; }
             }
             __syncwarp();
@@ -405,9 +431,26 @@ struct BeamArgs {
     int disable_pq;
     const float *code_scale;  // [n] or NULL: candidate score = f32 sum of LUT entries * code_scale[id] + code_bias[q] (RabitQ estimate)
     const float *code_bias;   // [nq] (used with code_scale)
-    const float *qtm;         // [nq][rq_O + 1] or NULL: RabitQ query side (P q, <mean,q>); the byte tables are built in shared memory
-    uint32_t rq_O, rq_D;
+    const float *qtm;         // [nq][rq_O + 1] or NULL: RabitQ query side (P q, <mean,q>), evaluated directly against the sign codes
+    uint32_t rq_O;            // 512
+    float rq_scale;           // 1 / sqrt(n_dims), rounded to f32 on the host
 };
+
+// RabitQ estimate straight from the sign code, no tables (diskann/rabitq.py:42-48): lane l holds (P q)[16l .. 16l+15] and the
+// 16 sign bits of outputs 16l .. 16l+15 (bit i of byte b = output 8b + i); the signed sum runs in bit order per lane, then
+// an xor butterfly (16, 8, 4, 2, 1) -- every lane ends with the same f32.  One 64-byte coalesced request per candidate.
+static constexpr int kRqPerLane = 16;   // output_dims = 512
+__device__ __forceinline__ float rabitq_signed_sum(const float (&qt)[kRqPerLane], uint32_t bits16) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRqPerLane; j++) t += ((bits16 >> j) & 1u) ? qt[j] : -qt[j];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+}
+__device__ __forceinline__ long long rabitq_score(float signed_sum, float rq_scale, float code_scale, float bias) {
+    return fast_dot_fix(fmaf(rq_scale * signed_sum, code_scale, bias));
+}
 struct BeamOut {
     uint32_t *ids;            // [nq][cap] expanded-and-recorded nodes in visit order
     long long *scores;        // [nq][cap] exact scores
@@ -446,19 +489,12 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
     for (uint32_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
         for (uint32_t i = threadIdx.x; i < 2 * hcap; i += blockDim.x) hadj[i] = kEmpty;
         for (uint32_t i = threadIdx.x; i < g.d; i += blockDim.x) s.q[i] = __half2float(queries[(size_t)qi * g.d + i]);
-        if (!ba.disable_pq) {
-            if (ba.qtm) {                                                            // same expression as pq.cu k_rabitq_lut
-                const float *qt = ba.qtm + (size_t)qi * (ba.rq_O + 1);
-                const float rscale = rsqrtf((float)ba.rq_D);
-                for (uint32_t i = threadIdx.x; i < lut_n; i += blockDim.x) {
-                    const uint32_t b = i >> 8, val = i & 255;
-                    float t = 0.f;
-                    for (int j = 0; j < 8; j++) t += ((val >> j) & 1) ? qt[b * 8 + j] : -qt[b * 8 + j];
-                    lut[i] = rscale * t;
-                }
-            } else {
-                for (uint32_t i = threadIdx.x; i < lut_n; i += blockDim.x) lut[i] = luts[(size_t)qi * lut_n + i];
-            }
+        float qt[kRqPerLane];
+        if (ba.qtm) {
+#pragma unroll
+            for (int j = 0; j < kRqPerLane; j++) qt[j] = ba.qtm[(size_t)qi * (ba.rq_O + 1) + kRqPerLane * lane + j];
+        } else if (!ba.disable_pq) {
+            for (uint32_t i = threadIdx.x; i < lut_n; i += blockDim.x) lut[i] = luts[(size_t)qi * lut_n + i];
         }
         if (threadIdx.x == 0) { fill_adj = 0; fill_vis = 0; }
         __syncthreads();
@@ -512,6 +548,12 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
                     for (int i = warp; i < n_pre; i += kGsWarps) {
                         long long sc = score_row(s.q, g.x + (size_t)s.pre[i] * g.d, g.d, lane);
                         if (lane == 0) s.pre_scores[i] = sc;
+                    }
+                } else if (ba.qtm) {
+                    for (int i = warp; i < n_pre; i += kGsWarps) {                   // one warp per candidate code
+                        const uint32_t id = s.pre[i];
+                        const float t = rabitq_signed_sum(qt, ((const uint16_t *)(ba.codes + (size_t)id * ba.M))[lane]);
+                        if (lane == 0) s.pre_scores[i] = rabitq_score(t, ba.rq_scale, ba.code_scale[id], code_bias_q);
                     }
                 } else {
                     for (int i = threadIdx.x; i < n_pre; i += blockDim.x) {        // asymmetric_dot_product vector.rs:387-405
@@ -575,6 +617,167 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
     }
 }
 
+// ------------------------------------------------------------------ beam search over RabitQ codes, one WARP per query
+//
+// Same traversal as k_beam_search (query_disk_index.rs:144-212) in the warp-per-query schedule of k_greedy_search_wq: the W
+// expanded nodes of an iteration are scored exactly two rows per pass (their scores do not depend on the inserts in between),
+// candidates are ranked by the RabitQ estimate computed straight from their 64-byte sign codes with (P q) in registers.
+// No per-query table exists anywhere, so a warp's state is ~7 KB of shared memory and 24-32 queries run per SM.
+
+__host__ __device__ static size_t bq_warp_bytes(uint32_t L, uint32_t stride, uint32_t d, uint32_t W) {
+    size_t o = (size_t)(L + 1) * 8 + (size_t)stride * 8 + (size_t)W * 8 + (size_t)d * 4 + (size_t)(L + 1) * 4 + (size_t)stride * 4 + (size_t)W * 4 + (L + 1);
+    return (o + 15) & ~(size_t)15;
+}
+
+template <int NC2>
+__global__ void __launch_bounds__(kWqWarps * 32, 6) k_beam_search_wq(GraphArgs g, BeamArgs ba, const __half *__restrict__ queries,
+                                                                     const float *__restrict__ desc_scales, uint32_t nq,
+                                                                     const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L, uint32_t W,
+                                                                     uint32_t *htabs, uint32_t hcap, BeamOut out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t S = g.stride;
+    uint8_t *base = smem_raw + (size_t)warp * bq_warp_bytes(L, S, g.d, W);
+    long long *nb_scores = (long long *)base;
+    long long *pre_scores = nb_scores + (L + 1);
+    long long *pt_scores = pre_scores + S;
+    float *qs = (float *)(pt_scores + W);
+    uint32_t *nb_ids = (uint32_t *)(qs + g.d);
+    uint32_t *pre = nb_ids + (L + 1);
+    uint32_t *pts = pre + S;
+    uint8_t *nb_vis = (uint8_t *)(pts + W);
+    const uint32_t gw = blockIdx.x * kWqWarps + warp, nw = gridDim.x * kWqWarps;
+    uint32_t *hadj = htabs + (size_t)gw * 2 * hcap, *hvis = hadj + hcap;
+    const uint32_t hmask = hcap - 1;
+    const unsigned full = 0xffffffffu;
+
+    for (uint32_t qi = gw; qi < nq; qi += nw) {
+        {
+            uint4 *t4 = (uint4 *)hadj;
+            const uint4 e4 = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+            for (uint32_t i = lane; i < hcap / 2; i += 32) t4[i] = e4;       // both tables (2 * hcap words)
+        }
+        for (uint32_t c = lane; c < g.d; c += 32) qs[c] = __half2float(queries[(size_t)qi * g.d + c]);
+        float qt[kRqPerLane];
+#pragma unroll
+        for (int j = 0; j < kRqPerLane; j++) qt[j] = ba.qtm[(size_t)qi * (ba.rq_O + 1) + kRqPerLane * lane + j];
+        const float bias = ba.qtm[(size_t)qi * (ba.rq_O + 1) + ba.rq_O];
+        const float *scales = desc_scales ? desc_scales + (size_t)qi * ba.n_desc : nullptr;
+        __syncwarp();
+        NbView nb{nb_ids, nb_scores, nb_vis, 0, (int)L, -1};
+        const uint32_t start = starts ? starts[qi] : start_all;
+        unsigned long long cmps = 0, pq_cmps = 0;
+        uint32_t n_out = 0, fill_adj = 1;
+        nb_insert(nb, start, 0, lane);                                               // :153 seeds with score 0
+        if (lane == 0) hs_insert_nc(hadj, hmask, start);
+        __syncwarp();
+        for (;;) {
+            uint32_t np = 0;                                                         // next_several_unvisited :83-97
+            while (np < W) {
+                const uint32_t pt = nb_next_unvisited(nb, lane);
+                if (pt == kEmpty) break;
+                if (lane == 0) pts[np] = pt;
+                np++;
+            }
+            __syncwarp();
+            if (np == 0 || fill_adj * 4 > hcap * 3) break;
+            for (uint32_t i = 0; i < np; i += 2) {                                   // exact scores of the expanded nodes :169
+                const uint32_t j = i + 1 < np ? i + 1 : i;
+                long long s0, s1;
+                wq_score2<NC2>(qs, g.x + (size_t)pts[i] * g.d, g.x + (size_t)pts[j] * g.d, g.d, lane, s0, s1);
+                if (lane == 0) { pt_scores[i] = s0; pt_scores[j] = s1; }
+            }
+            __syncwarp();
+            for (uint32_t b = 0; b < np; b++) {
+                const uint32_t id = pts[b];
+                long long sc = pt_scores[b];
+                if (ba.n_desc) sc += descriptor_product(ba, scales, id);             // :170
+                cmps++;
+                bool rec = false;
+                if (lane == 0) rec = hs_insert_nc(hvis, hmask, id) && (!ba.has_url || ba.has_url[id]);   // :172
+                rec = __shfl_sync(full, rec, 0);
+                if (rec) {
+                    if (lane == 0 && n_out < out.cap) {
+                        out.ids[(size_t)qi * out.cap + n_out] = id;
+                        out.scores[(size_t)qi * out.cap + n_out] = sc;
+                    }
+                    n_out++;
+                }
+                // out-neighbours not seen as a neighbour before, first occurrence first
+                const uint32_t dgl = g.deg[id];
+                const uint32_t *nbrs = g.adj + (size_t)id * S;
+                int n_pre = 0;
+                for (uint32_t b0 = 0; b0 < S; b0 += 32) {
+                    const uint32_t i = b0 + lane;
+                    const uint32_t rawid = i < S ? nbrs[i] : kEmpty;                  // issued before the degree is known
+                    const uint32_t dg = min(dgl, S);
+                    if (b0 >= dg) break;
+                    const bool have = i < dg;
+                    const uint32_t nid = have ? rawid : kEmpty;
+                    const unsigned same = __match_any_sync(full, nid);
+                    bool ins = false;
+                    if (have && (same & ((1u << lane) - 1)) == 0) ins = hs_insert_nc(hadj, hmask, nid);
+                    const unsigned m = __ballot_sync(full, ins);
+                    if (ins) pre[n_pre + __popc(m & ((1u << lane) - 1))] = nid;
+                    n_pre += __popc(m);
+                    __syncwarp();
+                }
+                fill_adj += n_pre;
+                // RabitQ estimates, four codes in flight
+                for (int i = 0; i < n_pre; i += 4) {
+                    uint32_t bits[4], cid[4];
+                    float csc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        cid[u] = pre[min(i + u, n_pre - 1)];
+                        bits[u] = ((const uint16_t *)(ba.codes + (size_t)cid[u] * ba.M))[lane];
+                        csc[u] = ba.code_scale[cid[u]];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const float t = rabitq_signed_sum(qt, bits[u]);
+                        if (lane == 0 && i + u < n_pre) pre_scores[i + u] = rabitq_score(t, ba.rq_scale, csc[u], bias);
+                    }
+                }
+                __syncwarp();
+                if (ba.n_desc) {
+                    for (int i = lane; i < n_pre; i += 32) pre_scores[i] += descriptor_product(ba, scales, pre[i]);   // :202
+                    __syncwarp();
+                }
+                const bool full0 = nb.len == nb.cap;
+                const long long last0 = full0 ? nb.scores[nb.len - 1] : 0;
+                for (int i = 0; i < n_pre; i++) {
+                    const long long cs = pre_scores[i];
+                    if (!(full0 && last0 > cs)) nb_insert(nb, pre[i], cs, lane);
+                }
+                pq_cmps += n_pre;
+                __syncwarp();
+            }
+        }
+        const uint32_t m = min(n_out, out.cap);
+        if (lane == 0) {
+            out.len[qi] = n_out;
+            out.cmps[qi] = cmps;
+            out.pq_cmps[qi] = pq_cmps;
+            out.status[qi] = ((fill_adj * 4 > hcap * 3) ? 1u : 0u) | (n_out > out.cap ? 2u : 0u);
+        }
+        __syncwarp();
+        if (out.topk) {
+            const uint32_t *vi = out.ids + (size_t)qi * out.cap;
+            const long long *vs = out.scores + (size_t)qi * out.cap;
+            for (uint32_t i = lane; i < m; i += 32) {
+                const long long si = vs[i];
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < m; j++) { const long long sj = vs[j]; rank += (sj > si) || (sj == si && j < i); }
+                if (rank < out.topk) { out.top_ids[(size_t)qi * out.topk + rank] = vi[i]; out.top_scores[(size_t)qi * out.topk + rank] = si; }
+            }
+            for (uint32_t i = m + lane; i < out.topk; i += 32) { out.top_ids[(size_t)qi * out.topk + i] = kEmpty; out.top_scores[(size_t)qi * out.topk + i] = 0; }
+            if (lane == 0) out.top_len[qi] = min(m, out.topk);
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------ evaluator brute force (query_disk_index.rs:262-273)
 
 __global__ void __launch_bounds__(256) k_scores_i64(const __half *__restrict__ x, uint64_t n, uint32_t d, const __half *__restrict__ q,
@@ -608,7 +811,7 @@ static bool use_wq(const mse_index *ix, uint32_t nq) {
 // number of workers (= visited-set tables) a launch for nq queries uses; non-decreasing in nq
 uint32_t greedy_grid(const mse_index *ix, uint32_t nq) {
     const uint32_t sms = (uint32_t)sm_count(ix->device);
-    if (use_wq(ix, nq)) return std::min<uint32_t>((nq + kWqWarps - 1) / kWqWarps, sms * 4) * kWqWarps;
+    if (use_wq(ix, nq)) return std::min<uint32_t>((nq + kWqWarps - 1) / kWqWarps, sms * 8) * kWqWarps;
     return std::min<uint32_t>(nq, sms * 2);
 }
 
@@ -618,12 +821,12 @@ int greedy_search_launch(mse_index *ix, const __half *d_queries, const uint32_t 
     GraphArgs g{ix->x, ix->adj, ix->deg, ix->graph_stride, ix->d, ix->n};
     if (use_wq(ix, nq) && workers >= (uint32_t)kWqWarps) {
         const bool fixed = ix->d == 1152;
-        const size_t smem = wq_warp_bytes(L, ix->graph_stride, ix->d, !fixed) * kWqWarps;
+        const size_t smem = wq_warp_bytes(L, ix->graph_stride, ix->d) * kWqWarps;
         if (smem <= 200 * 1024) {
             const uint32_t grid = std::min<uint32_t>(workers / kWqWarps, (nq + kWqWarps - 1) / kWqWarps);
             if (fixed) {
-                MSE_CUDA(cudaFuncSetAttribute(k_greedy_search_wq<36>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_greedy_search_wq<36><<<grid, kWqWarps * 32, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, d_htabs, hcap, o);
+                MSE_CUDA(cudaFuncSetAttribute(k_greedy_search_wq<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_greedy_search_wq<18><<<grid, kWqWarps * 32, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, d_htabs, hcap, o);
             } else {
                 MSE_CUDA(cudaFuncSetAttribute(k_greedy_search_wq<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 k_greedy_search_wq<0><<<grid, kWqWarps * 32, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, d_htabs, hcap, o);
@@ -847,7 +1050,7 @@ static int search_beam_impl(mse_index *ix, const uint16_t *q_f16, const float *l
         if (starts) cudaMemcpy(b_starts.p, starts, (size_t)nq * 4, cudaMemcpyHostToDevice);
         if (ix->n_desc) cudaMemcpy(b_ds.p, desc_scales, (size_t)nq * ix->n_desc * 4, cudaMemcpyHostToDevice);
         GraphArgs g{ix->x, ix->adj, ix->deg, ix->graph_stride, ix->d, ix->n};
-        BeamArgs ba{ix->pq_codes, M, C, ix->desc, ix->has_url, ix->n_desc, disable_pq, code_bias ? ix->code_scale : nullptr, b_cb.as<float>(), nullptr, 0, 0};
+        BeamArgs ba{ix->pq_codes, M, C, ix->desc, ix->has_url, ix->n_desc, disable_pq, code_bias ? ix->code_scale : nullptr, b_cb.as<float>(), nullptr, 0, 0.f};
         BeamOut o{b_ids.as<uint32_t>(), b_sc.as<long long>(), b_len.as<uint32_t>(), out_cap, b_c.as<unsigned long long>(),
                   b_p.as<unsigned long long>(), b_st.as<uint32_t>(), 0, nullptr, nullptr, nullptr};
         k_beam_search<<<grid, kGsThreads, smem>>>(g, ba, b_q.as<__half>(), b_lut.as<float>(), ix->n_desc ? b_ds.as<float>() : nullptr, nq,
@@ -904,24 +1107,45 @@ MSE_API int mse_search_beam_dev(mse_index *ix, const uint16_t *d_q_f16, const fl
     MSE_REQUIRE(!ix->n_desc || d_desc_scales, MSE_ERR_INVALID, "search_beam_dev: the index has descriptors but d_desc_scales is NULL");
     if (nq == 0) return MSE_OK;
     MSE_CHECK(use_device(ix->device));
-    const uint32_t M = ix->code_size, C = d_qtm ? 256u : n_centroids;
-    MSE_REQUIRE(C >= 1, MSE_ERR_INVALID, "search_beam_dev: n_centroids is 0");
-    const size_t smem = ((gs_smem_bytes(L, ix->d, ix->graph_stride) + 15) & ~(size_t)15) + (size_t)M * C * 4;
-    MSE_REQUIRE(smem <= 220 * 1024, MSE_ERR_UNSUPPORTED, "search_beam_dev: L=%u with a %zu-byte LUT does not fit shared memory", L, (size_t)M * C * 4);
-    MSE_CUDA(cudaFuncSetAttribute(k_beam_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(3, (size_t)(224 * 1024) / (smem + 1024)));
-    const uint32_t grid = std::min<uint32_t>(nq, (uint32_t)sm_count(ix->device) * per_sm);
+    const uint32_t M = ix->code_size, C = d_qtm ? 0u : n_centroids;
+    MSE_REQUIRE(d_qtm || C >= 1, MSE_ERR_INVALID, "search_beam_dev: n_centroids is 0");
+    MSE_REQUIRE(!d_qtm || rabitq_output_dims == 32 * kRqPerLane, MSE_ERR_UNSUPPORTED, "search_beam_dev: RabitQ traversal supports output_dims = %d", 32 * kRqPerLane);
     const uint32_t hcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * ix->graph_stride * 8);
     const uint32_t cap = std::max<uint32_t>(8 * L + 64, topk);
-    MSE_CHECK(ix->gw_htabs.ensure((size_t)grid * 2 * hcap * 4));
     MSE_CHECK(ix->gw_status.ensure((size_t)nq * 4));
     MSE_CHECK(ix->gw_vis_ids.ensure((size_t)nq * cap * 4));
     MSE_CHECK(ix->gw_vis_sc.ensure((size_t)nq * cap * 8));
     MSE_CHECK(ix->gw_vis_len.ensure((size_t)nq * 4));
     GraphArgs g{ix->x, ix->adj, ix->deg, ix->graph_stride, ix->d, ix->n};
-    BeamArgs ba{ix->pq_codes, M, C, ix->desc, ix->has_url, ix->n_desc, 0, d_qtm ? ix->code_scale : nullptr, nullptr, d_qtm, rabitq_output_dims, rabitq_n_dims};
+    BeamArgs ba{ix->pq_codes, M, C, ix->desc, ix->has_url, ix->n_desc, 0, d_qtm ? ix->code_scale : nullptr, nullptr, d_qtm, rabitq_output_dims,
+                d_qtm ? (float)(1.0 / sqrt((double)rabitq_n_dims)) : 0.f};
     BeamOut o{ix->gw_vis_ids.as<uint32_t>(), ix->gw_vis_sc.as<long long>(), ix->gw_vis_len.as<uint32_t>(), cap, (unsigned long long *)d_cmps,
               (unsigned long long *)d_pq_cmps, ix->gw_status.as<uint32_t>(), topk, d_top_ids, (long long *)d_top_scores, d_top_len};
+    const uint32_t sms = (uint32_t)sm_count(ix->device);
+    const size_t wsmem = bq_warp_bytes(L, ix->graph_stride, ix->d, W) * kWqWarps;
+    if (d_qtm && use_wq(ix, nq) && wsmem <= 200 * 1024) {
+        // one warp per query
+        const uint32_t grid = std::min<uint32_t>((nq + kWqWarps - 1) / kWqWarps, sms * 6);
+        MSE_CHECK(ix->gw_htabs.ensure((size_t)grid * kWqWarps * 2 * hcap * 4));
+        if (ix->d == 1152) {
+            MSE_CUDA(cudaFuncSetAttribute(k_beam_search_wq<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            k_beam_search_wq<18><<<grid, kWqWarps * 32, wsmem, (cudaStream_t)stream>>>(g, ba, (const __half *)d_q_f16, ix->n_desc ? d_desc_scales : nullptr, nq,
+                                                                                       d_starts, start, L, W, ix->gw_htabs.as<uint32_t>(), hcap, o);
+        } else {
+            MSE_CUDA(cudaFuncSetAttribute(k_beam_search_wq<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            k_beam_search_wq<0><<<grid, kWqWarps * 32, wsmem, (cudaStream_t)stream>>>(g, ba, (const __half *)d_q_f16, ix->n_desc ? d_desc_scales : nullptr, nq,
+                                                                                      d_starts, start, L, W, ix->gw_htabs.as<uint32_t>(), hcap, o);
+        }
+        MSE_LAUNCH_OK();
+        return MSE_OK;
+    }
+    // one CTA per query (small batches, or PQ tables: M x n_centroids f32 in shared memory)
+    const size_t smem = ((gs_smem_bytes(L, ix->d, ix->graph_stride) + 15) & ~(size_t)15) + (size_t)M * C * 4 + 16;
+    MSE_REQUIRE(smem <= 220 * 1024, MSE_ERR_UNSUPPORTED, "search_beam_dev: L=%u with a %zu-byte LUT does not fit shared memory", L, (size_t)M * C * 4);
+    MSE_CUDA(cudaFuncSetAttribute(k_beam_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
+    const uint32_t grid = std::min<uint32_t>(nq, sms * per_sm);
+    MSE_CHECK(ix->gw_htabs.ensure((size_t)grid * 2 * hcap * 4));
     k_beam_search<<<grid, kGsThreads, smem, (cudaStream_t)stream>>>(g, ba, (const __half *)d_q_f16, d_luts, ix->n_desc ? d_desc_scales : nullptr, nq,
                                                                     d_starts, start, L, W, ix->gw_htabs.as<uint32_t>(), hcap, o);
     MSE_LAUNCH_OK();

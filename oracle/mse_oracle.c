@@ -960,10 +960,28 @@ static int64_t descriptor_product(const orc_disk_index *ix, const float *scales,
  * faithful_prebuffer != 0 reproduces :157 (the pre-buffer is cleared once per beam iteration, so later nodes
  * of a beam re-score earlier nodes' neighbours); 0 clears it per expanded node.
  */
+/* RabitQ signed sum straight from a 512-bit sign code, in the summation order of the GPU's warp: "lane" l adds its 16 terms
+ * (outputs 16l .. 16l+15, bit i of byte b = output 8b + i) in bit order, then an xor butterfly over the 32 lane sums
+ * (offsets 16, 8, 4, 2, 1).  f32 throughout; the order is part of the definition because f32 addition is not associative. */
+static float rabitq_direct_sum(const float *qt, const uint8_t *code) {
+    float s[32], t[32];
+    for (int l = 0; l < 32; l++) {
+        uint32_t bits = (uint32_t)code[2 * l] | ((uint32_t)code[2 * l + 1] << 8);
+        float a = 0.0f;
+        for (int j = 0; j < 16; j++) a += ((bits >> j) & 1u) ? qt[16 * l + j] : -qt[16 * l + j];
+        s[l] = a;
+    }
+    for (int o = 16; o; o >>= 1) {
+        for (int l = 0; l < 32; l++) t[l] = s[l] + s[l ^ o];
+        memcpy(s, t, sizeof(s));
+    }
+    return s[0];
+}
+
 static size_t beam_search_impl(const orc_disk_index *ix, uint32_t start, const uint16_t *query, const float *lut,
                                const float *desc_scales, size_t L, size_t beamwidth, int disable_pq, int faithful_prebuffer,
                                uint32_t *out_ids, int64_t *out_scores, size_t out_cap, uint64_t *counts,
-                               const float *code_scale, float code_bias) {
+                               const float *code_scale, float code_bias, const float *rq_qt, float rq_scale) {
     size_t n = ix->n, d = ix->d;
     uint8_t *vadj = (uint8_t *)calloc(n + 1, 1), *vis = (uint8_t *)calloc(n + 1, 1);
     orc_nb *nb = orc_nb_new(L);
@@ -1016,7 +1034,8 @@ static size_t beam_search_impl(const orc_disk_index *ix, uint32_t start, const u
                 } else {
                     float s = 0.0f;
                     const uint8_t *code = ix->pq_codes + (size_t)t * M;
-                    for (size_t m = 0; m < M; m++) s += lut[m * ix->n_centroids + code[m]];
+                    if (rq_qt) s = rq_scale * rabitq_direct_sum(rq_qt, code);
+                    else for (size_t m = 0; m < M; m++) s += lut[m * ix->n_centroids + code[m]];
                     if (code_scale) s = fmaf(s, code_scale[t], code_bias); /* RabitQ estimate, rabitq.py:47-48 */
                     sc = sat_trunc_f32(s * 4294967296.0f);
                     pq_cmps++;
@@ -1035,7 +1054,7 @@ ORC_API size_t orc_beam_search(const orc_disk_index *ix, uint32_t start, const u
                                const float *desc_scales, size_t L, size_t beamwidth, int disable_pq, int faithful_prebuffer,
                                uint32_t *out_ids, int64_t *out_scores, size_t out_cap, uint64_t *counts) {
     return beam_search_impl(ix, start, query, lut, desc_scales, L, beamwidth, disable_pq, faithful_prebuffer, out_ids, out_scores, out_cap,
-                            counts, NULL, 0.0f);
+                            counts, NULL, 0.0f, NULL, 0.0f);
 }
 
 /* candidates ranked by (sum of LUT entries) * code_scale[id] + code_bias: the traversal over RabitQ codes (diskann/rabitq.py:42-48
@@ -1043,5 +1062,21 @@ ORC_API size_t orc_beam_search(const orc_disk_index *ix, uint32_t start, const u
 ORC_API size_t orc_beam_search_scaled(const orc_disk_index *ix, uint32_t start, const uint16_t *query, const float *lut,
                                       const float *code_scale, float code_bias, const float *desc_scales, size_t L, size_t beamwidth,
                                       uint32_t *out_ids, int64_t *out_scores, size_t out_cap, uint64_t *counts) {
-    return beam_search_impl(ix, start, query, lut, desc_scales, L, beamwidth, 0, 0, out_ids, out_scores, out_cap, counts, code_scale, code_bias);
+    return beam_search_impl(ix, start, query, lut, desc_scales, L, beamwidth, 0, 0, out_ids, out_scores, out_cap, counts, code_scale, code_bias,
+                            NULL, 0.0f);
+}
+
+/* candidates ranked by the RabitQ estimate computed straight from the sign codes: qtm = (P q)[512] followed by <mean, q>;
+ * estimate = fma(rq_scale * signed_sum, code_scale[id], <mean, q>)  (the device-pointer entry mse_search_beam_dev) */
+ORC_API size_t orc_beam_search_rabitq(const orc_disk_index *ix, uint32_t start, const uint16_t *query, const float *qtm, float rq_scale,
+                                      const float *code_scale, const float *desc_scales, size_t L, size_t beamwidth,
+                                      uint32_t *out_ids, int64_t *out_scores, size_t out_cap, uint64_t *counts) {
+    return beam_search_impl(ix, start, query, NULL, desc_scales, L, beamwidth, 0, 0, out_ids, out_scores, out_cap, counts, code_scale, qtm[512],
+                            qtm, rq_scale);
+}
+
+/* the direct RabitQ estimate for n codes (test hook: lets the CPU suite compare the summation-order-pinned f32 value with
+ * the numpy restatement of rabitq.py:42-48) */
+ORC_API void orc_rabitq_direct_estimates(const float *qtm, float rq_scale, const uint8_t *codes, size_t n, const float *code_scale, float *out) {
+    for (size_t i = 0; i < n; i++) out[i] = fmaf(rq_scale * rabitq_direct_sum(qtm, codes + i * 64), code_scale[i], qtm[512]);
 }

@@ -93,6 +93,8 @@ def _bind(l):
         "orc_pq_preprocess_query": (None, [vp, vp, vp]), "orc_pq_adc": (None, [vp, sz, sz, vp, sz, vp]),
         "orc_beam_search": (sz, [vp, u32, vp, vp, vp, sz, sz, C.c_int, C.c_int, vp, vp, sz, vp]),
         "orc_beam_search_scaled": (sz, [vp, u32, vp, vp, vp, C.c_float, vp, sz, sz, vp, vp, sz, vp]),
+        "orc_rabitq_direct_estimates": (None, [vp, C.c_float, vp, sz, vp, vp]),
+        "orc_beam_search_rabitq": (sz, [vp, u32, vp, vp, C.c_float, vp, vp, sz, sz, vp, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(l, name)
@@ -376,7 +378,8 @@ class ProductQuantizer:
 # ---------------------------------------------------------------- packed-index beam search
 
 def beam_search(vectors, adj, offsets, pq_codes, lut, start, query, L, beamwidth, descriptors=None, desc_scales=None,
-                has_url=None, disable_pq=False, faithful_prebuffer=False, n_centroids=256, code_scale=None, code_bias=0.0):
+                has_url=None, disable_pq=False, faithful_prebuffer=False, n_centroids=256, code_scale=None, code_bias=0.0,
+                rabitq_qtm=None, rabitq_scale=0.0):
     """src/query_disk_index.rs:144-212 over in-memory node records.
     -> (ids, scores) of expanded nodes in visit order, (cmps, pq_cmps)."""
     v16 = as_u16(vectors)
@@ -384,7 +387,7 @@ def beam_search(vectors, adj, offsets, pq_codes, lut, start, query, L, beamwidth
     adj = _c(adj, np.uint32)
     offsets = _c(offsets, np.uint64)
     codes = _c(pq_codes, np.uint8)
-    lut = _c(lut, np.float32)
+    lut = _c(lut, np.float32) if lut is not None else np.zeros(1, np.float32)
     q16 = as_u16(query)
     desc = _c(descriptors, np.uint8) if descriptors is not None else None
     scales = _c(desc_scales, np.float32) if desc_scales is not None else np.zeros(1, np.float32)
@@ -395,7 +398,12 @@ def beam_search(vectors, adj, offsets, pq_codes, lut, start, query, L, beamwidth
     cap = n
     ids, sc = np.empty(cap, np.uint32), np.empty(cap, np.int64)
     counts = np.zeros(2, np.uint64)
-    if code_scale is not None:
+    if rabitq_qtm is not None:
+        cs, qtm = _c(code_scale, np.float32), _c(rabitq_qtm, np.float32)
+        assert qtm.size == 513 and codes.shape[1] == 64
+        m = lib().orc_beam_search_rabitq(C.byref(ix), start, _p(q16), _p(qtm), C.c_float(rabitq_scale), _p(cs), _p(scales), L, beamwidth,
+                                         _p(ids), _p(sc), cap, _p(counts))
+    elif code_scale is not None:
         cs = _c(code_scale, np.float32)
         m = lib().orc_beam_search_scaled(C.byref(ix), start, _p(q16), _p(lut), _p(cs), C.c_float(code_bias), _p(scales), L, beamwidth,
                                          _p(ids), _p(sc), cap, _p(counts))
@@ -403,3 +411,11 @@ def beam_search(vectors, adj, offsets, pq_codes, lut, start, query, L, beamwidth
         m = lib().orc_beam_search(C.byref(ix), start, _p(q16), _p(lut), _p(scales), L, beamwidth, int(disable_pq),
                                   int(faithful_prebuffer), _p(ids), _p(sc), cap, _p(counts))
     return ids[:m].copy(), sc[:m].copy(), (int(counts[0]), int(counts[1]))
+
+
+def rabitq_direct_estimates(qtm, rq_scale, codes, code_scale) -> np.ndarray:
+    """f32 RabitQ estimates straight from 64-byte sign codes in the GPU's summation order (mse_search_beam_dev)."""
+    qtm, codes, cs = _c(qtm, np.float32), _c(codes, np.uint8), _c(code_scale, np.float32)
+    out = np.empty(codes.shape[0], np.float32)
+    lib().orc_rabitq_direct_estimates(_p(qtm), C.c_float(rq_scale), _p(codes), codes.shape[0], _p(cs), _p(out))
+    return out

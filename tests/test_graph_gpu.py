@@ -307,9 +307,11 @@ def test_beam_search_over_rabitq_codes(mse, oracle, world):
             assert int(cmps[i]) == c and int(pqc[i]) == pc
 
 
-def test_beam_search_dev_topk(mse, oracle, world):
-    """Device-pointer beam search (what bench.py times): RabitQ tables built in shared memory from (P q, <mean,q>) and PQ tables
-    from HBM; the on-device top-k must equal the stable sort (score desc, visit order) of the host-API visit list."""
+def test_beam_search_dev_topk(mse, oracle, world, graph_mode):
+    """Device-pointer beam search (what bench.py times), in both schedules.  RabitQ codes: candidates are ranked by the
+    estimate computed straight from the sign codes (no tables); given (P q, <mean,q>) the traversal is pinned bit for bit by
+    the C oracle's lane-ordered restatement.  PQ codes: tables from HBM, same result as the host-pointer entry.  The on-device
+    top-k must equal the stable sort (score desc, visit order) of the visit list."""
     import torch
     from oracle.rabitq_np import RabitQ as NpRabitQ
     w = world
@@ -325,39 +327,42 @@ def test_beam_search_dev_topk(mse, oracle, world):
     cm = torch.zeros(nq, dtype=torch.int64, device=dev)
     pc = torch.zeros(nq, dtype=torch.int64, device=dev)
     vl.set_descriptors(None, None)
-
-    def expect(res):
-        out = []
-        for ids, sc in res:
-            o = np.argsort(-sc, kind="stable")[:k]
-            out.append((ids[o], sc[o]))
-        return out
+    adj, off = w["g"].to_csr()
 
     def compare(res, cmps, pqc):
         ti, ts, tl = top_ids.cpu().numpy().view(np.uint32), top_sc.cpu().numpy(), top_len.cpu().numpy()
-        for i, (ids, sc) in enumerate(expect(res)):
+        for i, (ids, sc) in enumerate(res):
+            o = np.argsort(-sc, kind="stable")[:k]
             m = int(tl[i])
-            assert m == len(ids) and np.array_equal(ti[i, :m], ids) and np.array_equal(ts[i, :m], sc), i
+            assert m == len(o) and np.array_equal(ti[i, :m], ids[o]) and np.array_equal(ts[i, :m], sc[o]), i
             assert (ti[i, m:] == 0xFFFFFFFF).all()
-        assert np.array_equal(cm.cpu().numpy().view(np.uint64), cmps) and np.array_equal(pc.cpu().numpy().view(np.uint64), pqc)
+        assert np.array_equal(cm.cpu().numpy().view(np.uint64), np.asarray(cmps, np.uint64))
+        assert np.array_equal(pc.cpu().numpy().view(np.uint64), np.asarray(pqc, np.uint64))
 
     # RabitQ codes
     ref = NpRabitQ.train(x[:1000].astype(np.float32), output_dims=512, seed=4)
     g = mse.diskann.RabitQ(ref.mean, ref.p)
     codes, norms, dots = g.quantize(x)
+    scale = (norms * dots).astype(np.float32)
     vl.set_pq_codes(codes)
-    vl.set_code_scales(norms * dots)
-    luts, bias = g.preprocess_query(q.astype(np.float32))
-    res, cmps, pqc = mse.diskann.beam_search(vl, q, luts, w["med"], L, W, code_bias=bias)
+    vl.set_code_scales(scale)
     dq32 = torch.from_numpy(q.astype(np.float32)).to(dev)
     qtm = torch.empty((nq, 513), dtype=torch.float32, device=dev)
     g.query_dev(dq32.data_ptr(), nq, qtm.data_ptr(), stream)
     mse.diskann.beam_search_dev(vl, dq16.data_ptr(), nq, L, W, w["med"], k, top_ids.data_ptr(), top_sc.data_ptr(), top_len.data_ptr(),
                                 cm.data_ptr(), pc.data_ptr(), stream, d_qtm=qtm.data_ptr(), rabitq=g)
     mse.diskann.greedy_search_check(vl, nq)
+    qtm_h = qtm.cpu().numpy()
+    # (P q, <mean, q>) is floating point: against numpy in f64
+    assert np.abs(qtm_h[:, :512] - (ref.p.astype(np.float64) @ q.astype(np.float64).T).T).max() < 2e-5
+    res, cmps, pqc = [], [], []
+    for i in range(nq):
+        ids, sc, (c, p_) = oracle.beam_search(x, adj, off, codes, None, w["med"], q[i], L, W, code_scale=scale, rabitq_qtm=qtm_h[i],
+                                              rabitq_scale=np.float32(1.0 / np.sqrt(1152.0)))
+        res.append((ids, sc)); cmps.append(c); pqc.append(p_)
     compare(res, cmps, pqc)
 
-    # PQ codes, tables in HBM
+    # PQ codes, tables in HBM (one CTA per query in every mode: the 64 KB table lives in shared memory)
     po, pg, _, _ = _pq_setup(oracle, mse, x)
     pcodes = pg.quantize_batch(x.astype(np.float32))
     vl.set_pq_codes(pcodes)
@@ -368,6 +373,7 @@ def test_beam_search_dev_topk(mse, oracle, world):
                                 cm.data_ptr(), pc.data_ptr(), stream, d_luts=dl.data_ptr(), n_centroids=256)
     mse.diskann.greedy_search_check(vl, nq)
     compare(res, cmps, pqc)
+
 
 
 def test_robust_stitch_bit_exact(mse, oracle):

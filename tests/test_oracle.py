@@ -284,3 +284,21 @@ def test_greedy_search_batch_equals_single(oracle):
         assert m == len(s.neighbour_ids) and d == int(dist[i])
         assert np.array_equal(ids[i, :m], s.neighbour_ids) and np.array_equal(sc[i, :m], s.neighbour_scores)
         assert (ids[i, m:] == 0xFFFFFFFF).all()
+
+
+def test_rabitq_direct_estimate_matches_numpy(oracle):
+    """The table-free RabitQ estimate the GPU traversal uses (lane-ordered f32 sums) against the numpy restatement of
+    diskann/rabitq.py:42-48 (f64): |difference| < 2e-5 for unit vectors."""
+    from oracle.rabitq_np import RabitQ as NpRabitQ
+    x = clustered_f16(41, 600, n_clusters=8)
+    ref = NpRabitQ.train(x[:300].astype(np.float32), output_dims=512, seed=2)
+    bits, norms, dots, _ = ref.quantize(x)
+    codes = NpRabitQ.pack(bits)
+    q = unit_rows(42, 2)
+    for i in range(2):
+        qt = (ref.p.astype(np.float64) @ q[i].astype(np.float64)).astype(np.float32)
+        mq = np.float32(np.dot(ref.mean.astype(np.float64), q[i].astype(np.float64)))
+        qtm = np.concatenate([qt, [mq]]).astype(np.float32)
+        got = oracle.rabitq_direct_estimates(qtm, np.float32(1.0 / np.sqrt(1152.0)), codes, (norms * dots).astype(np.float32))
+        want = ref.approx_dot(bits, norms, dots, q[i])
+        assert np.abs(got - want).max() < 2e-5
