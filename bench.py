@@ -413,13 +413,18 @@ def main():
 
         vl = dk.VectorList(D, device=local_rank)
         vl.reserve(n_local)
-        x_host = np.empty((n_local, D), np.float16)
+        want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline and n_local <= 4_000_000
+        x_host = np.empty((n_local, D), np.float16) if want_cpu else None   # only the CPU oracle leg needs the rows on the host
+        x_head = None
         chunk = 1 << 18
         for c0 in range(0, n_local, chunk):
             m = min(chunk, n_local - c0)
             xb = draw(m, 4_000_003 + lo + c0)
             vl.add_f16_dev(xb.data_ptr(), m, stream)
-            x_host[c0:c0 + m] = xb.cpu().numpy()
+            if want_cpu:
+                x_host[c0:c0 + m] = xb.cpu().numpy()
+            if c0 == 0:
+                x_head = xb[: min(m, 100_000)].float().mean(dim=0).cpu().numpy()      # RabitQ "training": the dataset mean (rabitq.py:14)
             del xb
         q16 = draw(nq, 5)
         q32 = q16.float().contiguous()
@@ -505,12 +510,10 @@ def main():
         try:
             gm = torch.Generator(device=dev).manual_seed(11)
             P = torch.linalg.qr(torch.randn((D, D), generator=gm, device=dev))[0][:512].contiguous()
-            mean = torch.from_numpy(x_host[: min(n_local, 100_000)].astype(np.float32)).mean(dim=0)
-            rq = dk.RabitQ(mean.numpy(), P.cpu().numpy(), device=local_rank)
+            rq = dk.RabitQ(x_head, P.cpu().numpy(), device=local_rank)
             t0 = time.perf_counter()
-            codes, norms, dots = rq.quantize(x_host)
+            rq.encode_index(vl, 0)                                   # rows are encoded where they lie in HBM
             enc_s = time.perf_counter() - t0
-            vl.set_pq_codes(codes)
             qtm = torch.empty((nq, 513), dtype=torch.float32, device=dev)
             top_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
             top_sc = torch.empty((nq, k), dtype=torch.int64, device=dev)
@@ -527,10 +530,12 @@ def main():
                 return beam_resident
 
             variants = {}
-            scale_script, scale_paper = (norms * dots).astype(np.float32), (norms / dots).astype(np.float32)
-            for name, scale, Lb in (("script (norms * dots, rabitq.py:48) L=64", scale_script, L), ("paper (norms / dots) L=64", scale_paper, L),
-                                    ("script L=128", scale_script, 2 * L), ("script L=256", scale_script, 4 * L)):
-                vl.set_code_scales(scale)
+            est_now = 0
+            for name, est, Lb in (("script (norms * dots, rabitq.py:48) L=64", 0, L), ("script L=128", 0, 2 * L), ("script L=256", 0, 4 * L),
+                                  ("paper (norms / dots) L=64", 1, L)):
+                if est != est_now:
+                    rq.encode_index(vl, est)
+                    est_now = est
                 ms_b, launches_b = timed(make_beam(Lb), min(warmup, 2), steps)
                 dk.greedy_search_check(vl, nq)
                 exact_b = float(cm_d.double().sum().item()) * D * 2
@@ -546,7 +551,7 @@ def main():
             rq.close()
         except Exception as e:  # the exact path above is the graph headline; report, do not hide
             graph["rabitq_beam"] = {"error": repr(e)}
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if want_cpu:
             from oracle import oracle as O
             O.build()
             adj, deg = vl.get_graph()

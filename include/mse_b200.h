@@ -208,6 +208,9 @@ int mse_rabitq_estimate(mse_rabitq *r, const float *q, const uint8_t *codes, con
 /* query side of approx_dot (rabitq.py:42-46) as byte tables for mse_search_beam_scaled: luts [nq][output_dims/8][256]
  * (entry v of table b = (1/sqrt(n_dims)) * sum_j (+-) (P q)[8b+j], sign from bit j of v), bias [nq] = <mean, q> */
 int mse_rabitq_preprocess_query(mse_rabitq *r, const float *q, uint32_t nq, float *luts, float *bias);
+/* encode the index's own rows in HBM: codes -> the index's code store, norms*dots (estimator 0, rabitq.py:48) or norms/dots
+ * (estimator 1, the RabitQ paper) -> its code scales; equivalent to mse_rabitq_encode + mse_index_set_pq_codes + _set_code_scales */
+int mse_index_encode_rabitq(mse_index *ix, mse_rabitq *r, int estimator);
 /* the same query side kept in HBM: d_qtm [nq][output_dims + 1] = (P q, <mean, q>), asynchronous on `stream` */
 int mse_rabitq_query_dev(mse_rabitq *r, const float *d_q, uint32_t nq, float *d_qtm, void *stream);
 void mse_rabitq_destroy(mse_rabitq *r);

@@ -90,6 +90,7 @@ _SIGS = {
     "mse_rabitq_encode": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "mse_rabitq_estimate": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "mse_rabitq_preprocess_query": (_i32, [_vp, _vp, _u32, _vp, _vp]),
+    "mse_index_encode_rabitq": (_i32, [_vp, _vp, _i32]),
     "mse_rabitq_query_dev": (_i32, [_vp, _vp, _u32, _vp, _vp]),
     "mse_rabitq_destroy": (None, [_vp]),
     "mse_encoder_create": (_i32, [C.c_char_p, _i32, _i32, C.POINTER(_vp)]),

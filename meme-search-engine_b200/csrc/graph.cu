@@ -474,20 +474,20 @@ __device__ __forceinline__ long long descriptor_product(const BeamArgs &b, const
 __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArgs ba, const __half *__restrict__ queries,
                                                             const float *__restrict__ luts, const float *__restrict__ desc_scales,
                                                             uint32_t nq, const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L,
-                                                            uint32_t W, uint32_t *htabs, uint32_t hcap, BeamOut out) {
+                                                            uint32_t W, uint32_t *htabs, uint32_t hcap, uint32_t vcap, BeamOut out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     GsSmem s = carve(smem_raw, L, g.d, g.stride);
     float *lut = (float *)(smem_raw + ((gs_smem_bytes(L, g.d, g.stride) + 15) & ~(size_t)15));
     // two exact sets like the reference: visited_adjacent (seen as a neighbour) and visited (expanded)
-    uint32_t *hadj = htabs + (size_t)blockIdx.x * 2 * hcap, *hvis = hadj + hcap;
-    const uint32_t hmask = hcap - 1;
+    uint32_t *hadj = htabs + (size_t)blockIdx.x * (hcap + vcap), *hvis = hadj + hcap;   // vcap slots for the expanded set (~1.5 L nodes)
+    const uint32_t hmask = hcap - 1, vmask = vcap - 1;
     __shared__ uint32_t fill_adj, fill_vis;
     __shared__ uint32_t pts[64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lut_n = ba.M * ba.C;
 
     for (uint32_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
-        for (uint32_t i = threadIdx.x; i < 2 * hcap; i += blockDim.x) hadj[i] = kEmpty;
+        for (uint32_t i = threadIdx.x; i < hcap + vcap; i += blockDim.x) hadj[i] = kEmpty;
         for (uint32_t i = threadIdx.x; i < g.d; i += blockDim.x) s.q[i] = __half2float(queries[(size_t)qi * g.d + i]);
         float qt[kRqPerLane];
         if (ba.qtm) {
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
             }
             __syncthreads();
             const uint32_t np = (uint32_t)s.ctl[2];
-            if (np == 0 || fill_adj * 4 > hcap * 3) break;
+            if (np == 0 || fill_adj * 4 > hcap * 3 || fill_vis * 4 > vcap * 3) break;
             for (uint32_t b = 0; b < np; b++) {
                 const uint32_t id = pts[b];
                 // exact score of the expanded node (+ descriptor bias) :169-170
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
                     if (ba.n_desc) sc += descriptor_product(ba, scales, id);
                     if (lane == 0) {
                         cmps++;
-                        if (hs_insert(hvis, hmask, id, &fill_vis) && (!ba.has_url || ba.has_url[id])) {  // :172
+                        if (hs_insert(hvis, vmask, id, &fill_vis) && (!ba.has_url || ba.has_url[id])) {  // :172
                             if (n_out < out.cap) {
                                 out.ids[(size_t)qi * out.cap + n_out] = id;
                                 out.scores[(size_t)qi * out.cap + n_out] = sc;
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
             out.len[qi] = n_out;
             out.cmps[qi] = cmps;
             out.pq_cmps[qi] = pq_cmps;
-            out.status[qi] = ((fill_adj * 4 > hcap * 3) ? 1u : 0u) | (n_out > out.cap ? 2u : 0u);
+            out.status[qi] = ((fill_adj * 4 > hcap * 3 || fill_vis * 4 > vcap * 3) ? 1u : 0u) | (n_out > out.cap ? 2u : 0u);
             s.ctl[2] = (int)min(n_out, out.cap);
         }
         __syncthreads();
@@ -630,10 +630,10 @@ __host__ __device__ static size_t bq_warp_bytes(uint32_t L, uint32_t stride, uin
 }
 
 template <int NC2>
-__global__ void __launch_bounds__(kWqWarps * 32, 6) k_beam_search_wq(GraphArgs g, BeamArgs ba, const __half *__restrict__ queries,
+__global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g, BeamArgs ba, const __half *__restrict__ queries,
                                                                      const float *__restrict__ desc_scales, uint32_t nq,
                                                                      const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L, uint32_t W,
-                                                                     uint32_t *htabs, uint32_t hcap, BeamOut out) {
+                                                                     uint32_t *htabs, uint32_t hcap, uint32_t vcap, BeamOut out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t S = g.stride;
@@ -647,15 +647,15 @@ __global__ void __launch_bounds__(kWqWarps * 32, 6) k_beam_search_wq(GraphArgs g
     uint32_t *pts = pre + S;
     uint8_t *nb_vis = (uint8_t *)(pts + W);
     const uint32_t gw = blockIdx.x * kWqWarps + warp, nw = gridDim.x * kWqWarps;
-    uint32_t *hadj = htabs + (size_t)gw * 2 * hcap, *hvis = hadj + hcap;
-    const uint32_t hmask = hcap - 1;
+    uint32_t *hadj = htabs + (size_t)gw * (hcap + vcap), *hvis = hadj + hcap;
+    const uint32_t hmask = hcap - 1, vmask = vcap - 1;
     const unsigned full = 0xffffffffu;
 
     for (uint32_t qi = gw; qi < nq; qi += nw) {
         {
             uint4 *t4 = (uint4 *)hadj;
             const uint4 e4 = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-            for (uint32_t i = lane; i < hcap / 2; i += 32) t4[i] = e4;       // both tables (2 * hcap words)
+            for (uint32_t i = lane; i < (hcap + vcap) / 4; i += 32) t4[i] = e4;   // both tables
         }
         for (uint32_t c = lane; c < g.d; c += 32) qs[c] = __half2float(queries[(size_t)qi * g.d + c]);
         float qt[kRqPerLane];
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, 6) k_beam_search_wq(GraphArgs g
         NbView nb{nb_ids, nb_scores, nb_vis, 0, (int)L, -1};
         const uint32_t start = starts ? starts[qi] : start_all;
         unsigned long long cmps = 0, pq_cmps = 0;
-        uint32_t n_out = 0, fill_adj = 1;
+        uint32_t n_out = 0, fill_adj = 1, fill_vis = 0;
         nb_insert(nb, start, 0, lane);                                               // :153 seeds with score 0
         if (lane == 0) hs_insert_nc(hadj, hmask, start);
         __syncwarp();
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, 6) k_beam_search_wq(GraphArgs g
                 np++;
             }
             __syncwarp();
-            if (np == 0 || fill_adj * 4 > hcap * 3) break;
+            if (np == 0 || fill_adj * 4 > hcap * 3 || fill_vis * 4 > vcap * 3) break;
             for (uint32_t i = 0; i < np; i += 2) {                                   // exact scores of the expanded nodes :169
                 const uint32_t j = i + 1 < np ? i + 1 : i;
                 long long s0, s1;
@@ -693,9 +693,11 @@ __global__ void __launch_bounds__(kWqWarps * 32, 6) k_beam_search_wq(GraphArgs g
                 long long sc = pt_scores[b];
                 if (ba.n_desc) sc += descriptor_product(ba, scales, id);             // :170
                 cmps++;
-                bool rec = false;
-                if (lane == 0) rec = hs_insert_nc(hvis, hmask, id) && (!ba.has_url || ba.has_url[id]);   // :172
-                rec = __shfl_sync(full, rec, 0);
+                bool fresh_v = false;
+                if (lane == 0) fresh_v = hs_insert_nc(hvis, vmask, id);
+                fresh_v = __shfl_sync(full, fresh_v, 0);
+                fill_vis += fresh_v;
+                const bool rec = fresh_v && (!ba.has_url || ba.has_url[id]);              // :172
                 if (rec) {
                     if (lane == 0 && n_out < out.cap) {
                         out.ids[(size_t)qi * out.cap + n_out] = id;
@@ -759,7 +761,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, 6) k_beam_search_wq(GraphArgs g
             out.len[qi] = n_out;
             out.cmps[qi] = cmps;
             out.pq_cmps[qi] = pq_cmps;
-            out.status[qi] = ((fill_adj * 4 > hcap * 3) ? 1u : 0u) | (n_out > out.cap ? 2u : 0u);
+            out.status[qi] = ((fill_adj * 4 > hcap * 3 || fill_vis * 4 > vcap * 3) ? 1u : 0u) | (n_out > out.cap ? 2u : 0u);
         }
         __syncwarp();
         if (out.topk) {
@@ -793,8 +795,11 @@ __global__ void __launch_bounds__(256) k_scores_i64(const __half *__restrict__ x
     }
 }
 
+// visited-set capacity: a search evaluates ~25 x L rows at R = 64 (1.6 k at L = 64, 4-5 k at L = 192); 4 x L x R slots keep the
+// table under ~15 % full, and the kernels stop with an overflow status at 75 % rather than degrade (the tables are cleared per
+// query, so their size is HBM write traffic)
 uint32_t greedy_hash_capacity(uint32_t L, uint32_t stride) {
-    uint64_t v = (uint64_t)(L > 64 ? L : 64) * stride * 8;
+    uint64_t v = (uint64_t)(L > 64 ? L : 64) * stride * 4;
     uint32_t p = 1024;
     while (p < v && p < (1u << 30)) p <<= 1;
     return p;
@@ -1031,7 +1036,8 @@ static int search_beam_impl(mse_index *ix, const uint16_t *q_f16, const float *l
     MSE_REQUIRE(smem <= 220 * 1024, MSE_ERR_UNSUPPORTED, "search_beam: L=%u with a %zu-byte LUT does not fit shared memory", L, lut_bytes);
     MSE_CUDA(cudaFuncSetAttribute(k_beam_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t grid = std::min<uint32_t>(nq, (uint32_t)sm_count(ix->device) * 2);
-    const uint32_t hcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * ix->graph_stride * 8);
+    const uint32_t hcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * ix->graph_stride * 4);
+    const uint32_t vcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * 16);
     DevBuf b_q, b_lut, b_ds, b_ids, b_sc, b_len, b_c, b_p, b_st, b_h, b_starts, b_cb;
     int rc = MSE_OK;
     std::vector<uint32_t> status(nq);
@@ -1041,7 +1047,7 @@ static int search_beam_impl(mse_index *ix, const uint16_t *q_f16, const float *l
         if ((rc = b_q.ensure((size_t)nq * ix->d * 2)) || (rc = b_lut.ensure(std::max<size_t>((size_t)nq * M * C * 4, 16))) ||
             (rc = b_ids.ensure((size_t)nq * out_cap * 4)) || (rc = b_sc.ensure((size_t)nq * out_cap * 8)) || (rc = b_len.ensure((size_t)nq * 4)) ||
             (rc = b_c.ensure((size_t)nq * 8)) || (rc = b_p.ensure((size_t)nq * 8)) || (rc = b_st.ensure((size_t)nq * 4)) ||
-            (rc = b_h.ensure((size_t)grid * 2 * hcap * 4)))
+            (rc = b_h.ensure((size_t)grid * (hcap + vcap) * 4)))
             break;
         if (starts && (rc = b_starts.ensure((size_t)nq * 4))) break;
         if (ix->n_desc && (rc = b_ds.ensure((size_t)nq * ix->n_desc * 4))) break;
@@ -1054,7 +1060,7 @@ static int search_beam_impl(mse_index *ix, const uint16_t *q_f16, const float *l
         BeamOut o{b_ids.as<uint32_t>(), b_sc.as<long long>(), b_len.as<uint32_t>(), out_cap, b_c.as<unsigned long long>(),
                   b_p.as<unsigned long long>(), b_st.as<uint32_t>(), 0, nullptr, nullptr, nullptr};
         k_beam_search<<<grid, kGsThreads, smem>>>(g, ba, b_q.as<__half>(), b_lut.as<float>(), ix->n_desc ? b_ds.as<float>() : nullptr, nq,
-                                                 starts ? b_starts.as<uint32_t>() : nullptr, start, L, W, b_h.as<uint32_t>(), hcap, o);
+                                                 starts ? b_starts.as<uint32_t>() : nullptr, start, L, W, b_h.as<uint32_t>(), hcap, vcap, o);
         count_launch();
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { set_error("search_beam: %s", cudaGetErrorString(e)); rc = MSE_ERR_CUDA; break; }
@@ -1110,7 +1116,8 @@ MSE_API int mse_search_beam_dev(mse_index *ix, const uint16_t *d_q_f16, const fl
     const uint32_t M = ix->code_size, C = d_qtm ? 0u : n_centroids;
     MSE_REQUIRE(d_qtm || C >= 1, MSE_ERR_INVALID, "search_beam_dev: n_centroids is 0");
     MSE_REQUIRE(!d_qtm || rabitq_output_dims == 32 * kRqPerLane, MSE_ERR_UNSUPPORTED, "search_beam_dev: RabitQ traversal supports output_dims = %d", 32 * kRqPerLane);
-    const uint32_t hcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * ix->graph_stride * 8);
+    const uint32_t hcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * ix->graph_stride * 4);
+    const uint32_t vcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * 16);
     const uint32_t cap = std::max<uint32_t>(8 * L + 64, topk);
     MSE_CHECK(ix->gw_status.ensure((size_t)nq * 4));
     MSE_CHECK(ix->gw_vis_ids.ensure((size_t)nq * cap * 4));
@@ -1125,16 +1132,16 @@ MSE_API int mse_search_beam_dev(mse_index *ix, const uint16_t *d_q_f16, const fl
     const size_t wsmem = bq_warp_bytes(L, ix->graph_stride, ix->d, W) * kWqWarps;
     if (d_qtm && use_wq(ix, nq) && wsmem <= 200 * 1024) {
         // one warp per query
-        const uint32_t grid = std::min<uint32_t>((nq + kWqWarps - 1) / kWqWarps, sms * 6);
-        MSE_CHECK(ix->gw_htabs.ensure((size_t)grid * kWqWarps * 2 * hcap * 4));
+        const uint32_t grid = std::min<uint32_t>((nq + kWqWarps - 1) / kWqWarps, sms * 8);
+        MSE_CHECK(ix->gw_htabs.ensure((size_t)grid * kWqWarps * (hcap + vcap) * 4));
         if (ix->d == 1152) {
             MSE_CUDA(cudaFuncSetAttribute(k_beam_search_wq<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
             k_beam_search_wq<18><<<grid, kWqWarps * 32, wsmem, (cudaStream_t)stream>>>(g, ba, (const __half *)d_q_f16, ix->n_desc ? d_desc_scales : nullptr, nq,
-                                                                                       d_starts, start, L, W, ix->gw_htabs.as<uint32_t>(), hcap, o);
+                                                                                       d_starts, start, L, W, ix->gw_htabs.as<uint32_t>(), hcap, vcap, o);
         } else {
             MSE_CUDA(cudaFuncSetAttribute(k_beam_search_wq<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
             k_beam_search_wq<0><<<grid, kWqWarps * 32, wsmem, (cudaStream_t)stream>>>(g, ba, (const __half *)d_q_f16, ix->n_desc ? d_desc_scales : nullptr, nq,
-                                                                                      d_starts, start, L, W, ix->gw_htabs.as<uint32_t>(), hcap, o);
+                                                                                      d_starts, start, L, W, ix->gw_htabs.as<uint32_t>(), hcap, vcap, o);
         }
         MSE_LAUNCH_OK();
         return MSE_OK;
@@ -1145,9 +1152,9 @@ MSE_API int mse_search_beam_dev(mse_index *ix, const uint16_t *d_q_f16, const fl
     MSE_CUDA(cudaFuncSetAttribute(k_beam_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
     const uint32_t grid = std::min<uint32_t>(nq, sms * per_sm);
-    MSE_CHECK(ix->gw_htabs.ensure((size_t)grid * 2 * hcap * 4));
+    MSE_CHECK(ix->gw_htabs.ensure((size_t)grid * (hcap + vcap) * 4));
     k_beam_search<<<grid, kGsThreads, smem, (cudaStream_t)stream>>>(g, ba, (const __half *)d_q_f16, d_luts, ix->n_desc ? d_desc_scales : nullptr, nq,
-                                                                    d_starts, start, L, W, ix->gw_htabs.as<uint32_t>(), hcap, o);
+                                                                    d_starts, start, L, W, ix->gw_htabs.as<uint32_t>(), hcap, vcap, o);
     MSE_LAUNCH_OK();
     return MSE_OK;
 }

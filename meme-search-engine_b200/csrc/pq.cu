@@ -207,6 +207,12 @@ __global__ void __launch_bounds__(256) k_rabitq_lut(const float *__restrict__ qt
     if (threadIdx.x == 0) bias[v] = qt[O];
 }
 
+// scales[v] = norms[v] * dots[v] (diskann/rabitq.py:48 as written) or norms[v] / dots[v] (the RabitQ paper's estimator)
+__global__ void k_rabitq_scales(const float *__restrict__ norms, const float *__restrict__ dots, uint64_t n, int divide, float *__restrict__ out) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n) out[v] = divide ? norms[v] / dots[v] : norms[v] * dots[v];
+}
+
 // ---- minimal msgpack reader for opq.msgpack / rabitq.msgpack (maps of str -> int | float array)
 struct MpReader {
     const uint8_t *p, *end;
@@ -544,4 +550,41 @@ MSE_API int mse_rabitq_query_dev(mse_rabitq *r, const float *d_q, uint32_t nq, f
     k_rabitq_query<<<nq, 256, r->D * 4, (cudaStream_t)stream>>>(r->mean, r->Pt, d_q, r->D, r->O, d_qtm);
     MSE_LAUNCH_OK();
     return MSE_OK;
+}
+
+// Encodes the index's own rows where they lie in HBM (no host round trip): codes go to the index's code store
+// (mse_index_set_pq_codes), the per-vector factor norms * dots (estimator 0, diskann/rabitq.py:48) or norms / dots
+// (estimator 1, the RabitQ paper) to its code scales (mse_index_set_code_scales).
+MSE_API int mse_index_encode_rabitq(mse_index *ix, mse_rabitq *r, int estimator) {
+    MSE_REQUIRE(ix && r, MSE_ERR_INVALID, "index_encode_rabitq: NULL argument");
+    MSE_REQUIRE(ix->d == r->D && ix->device == r->device, MSE_ERR_INVALID, "index_encode_rabitq: codec (d=%u, device %d) does not match the index (d=%u, device %d)",
+                r->D, r->device, ix->d, ix->device);
+    MSE_REQUIRE(estimator == 0 || estimator == 1, MSE_ERR_INVALID, "index_encode_rabitq: estimator %d (0 = norms*dots, 1 = norms/dots)", estimator);
+    MSE_CHECK(use_device(ix->device));
+    const uint64_t n = ix->n;
+    const uint32_t cs = r->O / 8;
+    if (ix->pq_codes) cudaFree(ix->pq_codes);
+    if (ix->code_scale) cudaFree(ix->code_scale);
+    ix->pq_codes = nullptr; ix->code_scale = nullptr; ix->code_size = 0;
+    MSE_CUDA(cudaMalloc(&ix->pq_codes, std::max<size_t>(n * cs, 16)));
+    MSE_CUDA(cudaMalloc(&ix->code_scale, std::max<size_t>(n * 4, 16)));
+    ix->code_size = cs;
+    if (n == 0) return MSE_OK;
+    DevBuf bn, bd;
+    int rc = MSE_OK;
+    do {
+        if ((rc = bn.ensure(n * 4)) || (rc = bd.ensure(n * 4))) break;
+        const uint64_t step = 1u << 20;   // grid.x per launch
+        for (uint64_t v0 = 0; v0 < n; v0 += step) {
+            const uint32_t m = (uint32_t)std::min<uint64_t>(step, n - v0);
+            k_rabitq_encode<<<m, 256, r->D * 4>>>(r->mean, r->Pt, ix->x + v0 * ix->d, r->D, r->O, ix->pq_codes + v0 * cs, bn.as<float>() + v0, bd.as<float>() + v0);
+            count_launch();
+        }
+        k_rabitq_scales<<<(uint32_t)((n + 255) / 256), 256>>>(bn.as<float>(), bd.as<float>(), n, estimator, ix->code_scale);
+        count_launch();
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { set_error("index_encode_rabitq: %s", cudaGetErrorString(e)); rc = MSE_ERR_CUDA; }
+    } while (0);
+    bn.release(); bd.release();
+    return rc;
 }

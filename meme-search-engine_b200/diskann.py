@@ -313,6 +313,10 @@ class RabitQ:
         check(lib().mse_rabitq_preprocess_query(self._h, _p(q), q.shape[0], _p(luts), _p(bias)), "mse_rabitq_preprocess_query")
         return luts, bias
 
+    def encode_index(self, vecs: "VectorList", estimator: int = 0):
+        """Encode the rows of `vecs` where they lie in HBM and attach codes + scales to it (0: norms*dots as rabitq.py:48, 1: norms/dots)."""
+        check(lib().mse_index_encode_rabitq(vecs._h, self._h, int(estimator)), "mse_index_encode_rabitq")
+
     def query_dev(self, d_q_f32: int, nq: int, d_qtm: int, stream: int = 0):
         """(P q, <mean, q>) rows [nq][output_dims + 1] in HBM for beam_search_dev(d_qtm=...)."""
         check(lib().mse_rabitq_query_dev(self._h, d_q_f32, nq, d_qtm, stream or None), "mse_rabitq_query_dev")
