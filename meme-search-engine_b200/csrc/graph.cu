@@ -35,15 +35,15 @@ struct NbView {
 __device__ __forceinline__ void nb_insert(NbView &b, uint32_t id, long long score, int lane) {
     if (b.cap == 0) return;
     if (b.len == b.cap && b.scores[b.len - 1] > score) return;                     // :118
-    int g = 0, e = 0;                                                              // binary_search_by on the descending list
-    for (int i = lane; i < b.len; i += 32) {
-        long long s = b.scores[i];
-        g += s > score;
-        e += s == score;
-    }
-    for (int o = 16; o; o >>= 1) {
-        g += __shfl_xor_sync(0xffffffffu, g, o);
-        e += __shfl_xor_sync(0xffffffffu, e, o);
+    int g = 0, e = 0;                                                              // binary_search_by on the descending list:
+    for (int i0 = 0; i0 < b.len; i0 += 32) {                                       // g = #entries > score, e = #entries == score
+        const int i = i0 + lane;
+        const bool in = i < b.len;
+        const long long s = in ? b.scores[i] : 0;
+        const unsigned mg = __ballot_sync(0xffffffffu, in && s > score), me = __ballot_sync(0xffffffffu, in && s == score);
+        g += __popc(mg);
+        e += __popc(me);
+        if ((mg | me) != 0xffffffffu) break;                                       // sorted: everything further down is smaller
     }
     const int loc = e > 0 ? g + e - 1 : g;                                         // Ok(last equal) / Err(insertion point)
     if (loc < b.len && b.ids[loc] == id) return;                                   // :127
