@@ -37,6 +37,14 @@ METRIC = "SigLIP ViT-SO400M-14/384 images/sec (image tower, batch 256 fp16)"
 GRAPH_METRIC = "queries/sec@recall10 (Vamana graph search, 4096 batched queries, L=64)"
 SEARCH_METRIC = "queries/sec (flat top-100, 1024 queries x 10M x 1152 fp16 index)"
 FLOP_PER_IMAGE = 670.35e9  # 27 layers 665.46 + patch-embed 0.99 + MAP head 3.90 GFLOP
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels, taken from the committed `ncu --set full`
+# captures -- a number measured under a profiler on an earlier run of the same configuration, not by this run.
+NCU_TRAFFIC = {
+    # profiles/r01b_tower_ncu_full.md: one block at batch 256 = fc1 2.065 + fc2 3.454 + QKV 1.682 + out-proj 1.262 GB; x 27 blocks
+    "tower_gemm_bytes_per_step_b256": 27 * (2.065 + 3.454 + 1.682 + 1.262) * 1e9,
+    # profiles/r01_flat_gemm_ncu_full.md: 3.745 GB read + 5.6 MB written for the 3.74 GB of rows the launch scored
+    "flat_gemm_bytes_per_row_byte": (3.745176 + 0.005563) / 3.74,
+}
 
 
 def peaks():
@@ -226,7 +234,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("MSE_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        if "MSE_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["MSE_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)   # NCCL_DEBUG=WARN/VERSION prints a version banner on stdout; stdout carries the one JSON line
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
@@ -297,7 +308,10 @@ def main():
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sustained"] if gemm_tf else None,
                 "peak_source": pk["src"] + " (sustained bf16 cuBLAS)", "frac_of_burst": gemm_tf / pk["tf_burst"] if gemm_tf else None,
                 "launches_per_step": st["gemm_launches"], "kernel_ms_per_step": st["gemm_ns"] * 1e-6,
-                "kernel_share_of_step": st["gemm_ns"] * 1e-6 / ms_step, "traffic": None,
+                "kernel_share_of_step": st["gemm_ns"] * 1e-6 / ms_step,
+                "traffic": NCU_TRAFFIC["tower_gemm_bytes_per_step_b256"] * B / 256 / max(st["gemm_launches"], 1),
+                "traffic_note": "bytes per launch (mean over the step's GEMM launches), from profiles/r01b_tower_ncu_full.md x 27 blocks; algorithmic A+B+C "
+                                "(+ residual) bytes are 7.55 GB per block vs 8.46 GB measured",
                 "attention": {"kernel": "k_mha_tc (tcgen05 flash attention)", "ms_per_step": st["attn_ns"] * 1e-6, "launches": st["attn_launches"],
                               "achieved_tflops": attn_flop / (st["attn_ns"] * 1e-9) / 1e12 if st["attn_ns"] else None,
                               "share_of_step": st["attn_ns"] * 1e-6 / ms_step},
@@ -382,7 +396,10 @@ def main():
                                "peak_source": pk["src"] + " (sustained bf16 cuBLAS)", "frac_of_burst": tf / pk["tf_burst"] if tf else None,
                                "hbm_gbs": n_local * D * 2 / (st["scoring_ns"] * 1e-9) / 1e9 if st["scoring_ns"] else None,
                                "launches_per_step": st["scoring_launches"], "kernel_ms_per_step": st["scoring_ns"] * 1e-6,
-                               "kernel_share_of_step": st["scoring_ns"] * 1e-6 / ms_step, "traffic": None},
+                               "kernel_share_of_step": st["scoring_ns"] * 1e-6 / ms_step,
+                               "traffic": NCU_TRAFFIC["flat_gemm_bytes_per_row_byte"] * n_local * D * 2 / max(st["scoring_launches"], 1),
+                               "traffic_note": "bytes per launch (mean over the step's chunk launches), ratio from profiles/r01_flat_gemm_ncu_full.md: "
+                                               "each index row leaves HBM once"},
                   "search_stats": st}
         if result:
             result["search"] = search

@@ -571,7 +571,8 @@ MSE_API int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_bu
             GreedyOut o{b_ids.as<uint32_t>(), b_sc.as<long long>(), b_len.as<uint32_t>(), b_dist.as<unsigned long long>(), b_vi.as<uint32_t>(),
                         b_vs.as<long long>(), b_vl.as<uint32_t>(), vl_cap, b_st.as<uint32_t>()};
             // greedy_search(medioid -> point) (lib.rs:299); query points search base vectors only (:298)
-            if ((rc = greedy_search_launch(ix, ix->x, pts, nb, nullptr, medioid, L, 0xFFFFFFFFu, b_h.as<uint32_t>(), hcap, greedy_grid(ix, nb), o, nullptr))) break;
+            if ((rc = greedy_search_launch(ix, ix->x, pts, nb, nullptr, medioid, L, cfg->query_breakpoint, cfg->query_breakpoint, b_h.as<uint32_t>(), hcap,
+                                           greedy_grid(ix, nb), o, nullptr))) break;
             k_prune_batch<<<std::min(nb, sms * 2), kPruneThreads, psmem>>>(ix->x, ix->d, pts, nb, b_vi.as<uint32_t>(), b_vs.as<long long>(), b_vl.as<uint32_t>(),
                                                                           vl_cap, ix->adj, ix->deg, stride, pc, b_na.as<uint32_t>(), b_nd.as<uint32_t>());
             count_launch();

@@ -165,7 +165,8 @@ __device__ __forceinline__ int collect_new_neighbours(const GraphArgs &g, GsSmem
 
 __global__ void __launch_bounds__(kGsThreads) k_greedy_search(GraphArgs g, const __half *__restrict__ queries, const uint32_t *__restrict__ q_rows, uint32_t nq,
                                                               const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L,
-                                                              uint32_t filter_from, uint32_t *htabs, uint32_t hcap, GreedyOut out) {
+                                                              uint32_t filter_from_all, uint32_t filter_self_from, uint32_t *htabs, uint32_t hcap,
+                                                              GreedyOut out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     GsSmem s = carve(smem_raw, L, g.d, g.stride);
     uint32_t *htab = htabs + (size_t)blockIdx.x * hcap;
@@ -176,6 +177,8 @@ __global__ void __launch_bounds__(kGsThreads) k_greedy_search(GraphArgs g, const
     for (uint32_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
         for (uint32_t i = threadIdx.x; i < hcap; i += blockDim.x) htab[i] = kEmpty;
         const size_t qrow = q_rows ? q_rows[qi] : qi;
+        // base_vectors_only (lib.rs:196-199) applies to the searches of query nodes only (build_graph :297-298)
+        const uint32_t filter_from = (q_rows && qrow < filter_self_from) ? 0xFFFFFFFFu : filter_from_all;
         for (uint32_t i = threadIdx.x; i < g.d; i += blockDim.x) s.q[i] = __half2float(queries[qrow * g.d + i]);
         if (threadIdx.x == 0) hfill = 0;
         __syncthreads();
@@ -317,7 +320,8 @@ __device__ __forceinline__ void wq_score2(const float *qs, const __half *__restr
 template <int NC2>
 __global__ void __launch_bounds__(kWqWarps * 32, 8) k_greedy_search_wq(GraphArgs g, const __half *__restrict__ queries, const uint32_t *__restrict__ q_rows,
                                                                        uint32_t nq, const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L,
-                                                                       uint32_t filter_from, uint32_t *htabs, uint32_t hcap, GreedyOut out) {
+                                                                       uint32_t filter_from_all, uint32_t filter_self_from, uint32_t *htabs, uint32_t hcap,
+                                                                       GreedyOut out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t S = g.stride;
@@ -341,6 +345,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_greedy_search_wq(GraphArgs
             for (uint32_t i = lane; i < hcap / 4; i += 32) t4[i] = e4;
         }
         const size_t qrow = q_rows ? q_rows[qi] : qi;
+        const uint32_t filter_from = (q_rows && qrow < filter_self_from) ? 0xFFFFFFFFu : filter_from_all;   // lib.rs:297-298
         for (uint32_t c = lane; c < g.d; c += 32) qs[c] = __half2float(queries[qrow * g.d + c]);
         __syncwarp();
         NbView nb{nb_ids, nb_scores, nb_vis, 0, (int)L, -1};
@@ -821,8 +826,8 @@ uint32_t greedy_grid(const mse_index *ix, uint32_t nq) {
 }
 
 int greedy_search_launch(mse_index *ix, const __half *d_queries, const uint32_t *d_q_rows, uint32_t nq, const uint32_t *d_starts,
-                         uint32_t start, uint32_t L, uint32_t filter_from, uint32_t *d_htabs, uint32_t hcap, uint32_t workers, GreedyOut o,
-                         cudaStream_t st) {
+                         uint32_t start, uint32_t L, uint32_t filter_from, uint32_t filter_self_from, uint32_t *d_htabs, uint32_t hcap, uint32_t workers,
+                         GreedyOut o, cudaStream_t st) {
     GraphArgs g{ix->x, ix->adj, ix->deg, ix->graph_stride, ix->d, ix->n};
     if (use_wq(ix, nq) && workers >= (uint32_t)kWqWarps) {
         const bool fixed = ix->d == 1152;
@@ -831,10 +836,10 @@ int greedy_search_launch(mse_index *ix, const __half *d_queries, const uint32_t 
             const uint32_t grid = std::min<uint32_t>(workers / kWqWarps, (nq + kWqWarps - 1) / kWqWarps);
             if (fixed) {
                 MSE_CUDA(cudaFuncSetAttribute(k_greedy_search_wq<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_greedy_search_wq<18><<<grid, kWqWarps * 32, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, d_htabs, hcap, o);
+                k_greedy_search_wq<18><<<grid, kWqWarps * 32, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, filter_self_from, d_htabs, hcap, o);
             } else {
                 MSE_CUDA(cudaFuncSetAttribute(k_greedy_search_wq<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_greedy_search_wq<0><<<grid, kWqWarps * 32, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, d_htabs, hcap, o);
+                k_greedy_search_wq<0><<<grid, kWqWarps * 32, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, filter_self_from, d_htabs, hcap, o);
             }
             MSE_LAUNCH_OK();
             return MSE_OK;
@@ -843,7 +848,7 @@ int greedy_search_launch(mse_index *ix, const __half *d_queries, const uint32_t 
     const size_t smem = gs_smem_bytes(L, ix->d, ix->graph_stride);
     MSE_REQUIRE(smem <= 200 * 1024, MSE_ERR_UNSUPPORTED, "greedy_search: L=%u does not fit shared memory", L);
     MSE_CUDA(cudaFuncSetAttribute(k_greedy_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_greedy_search<<<std::min(workers, nq), kGsThreads, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, d_htabs, hcap, o);
+    k_greedy_search<<<std::min(workers, nq), kGsThreads, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, filter_self_from, d_htabs, hcap, o);
     MSE_LAUNCH_OK();
     return MSE_OK;
 }
@@ -953,7 +958,7 @@ MSE_API int mse_search_graph(mse_index *ix, const uint16_t *q_f16, uint32_t nq, 
                     want_vl ? b_vi.as<uint32_t>() : nullptr, want_vl ? b_vs.as<long long>() : nullptr, want_vl ? b_vl.as<uint32_t>() : nullptr,
                     want_vl ? visited_cap : 0, b_st.as<uint32_t>()};
         if ((rc = greedy_search_launch(ix, b_q.as<__half>(), nullptr, nq, starts ? b_starts.as<uint32_t>() : nullptr, start, L,
-                                       base_vectors_only ? query_breakpoint : 0xFFFFFFFFu, b_h.as<uint32_t>(), hcap, grid, o, nullptr)))
+                                       base_vectors_only ? query_breakpoint : 0xFFFFFFFFu, 0, b_h.as<uint32_t>(), hcap, grid, o, nullptr)))
             break;
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { set_error("search_graph: %s", cudaGetErrorString(e)); rc = MSE_ERR_CUDA; break; }
@@ -996,7 +1001,7 @@ MSE_API int mse_search_graph_dev(mse_index *ix, const uint16_t *d_q_f16, uint32_
     MSE_CHECK(ix->gw_htabs.ensure((size_t)workers * hcap * 4));
     MSE_CHECK(ix->gw_status.ensure((size_t)nq * 4));
     GreedyOut o{d_ids, (long long *)d_scores, d_len, (unsigned long long *)d_distances, nullptr, nullptr, nullptr, 0, ix->gw_status.as<uint32_t>()};
-    return greedy_search_launch(ix, (const __half *)d_q_f16, nullptr, nq, d_starts, start, L, base_vectors_only ? query_breakpoint : 0xFFFFFFFFu,
+    return greedy_search_launch(ix, (const __half *)d_q_f16, nullptr, nq, d_starts, start, L, base_vectors_only ? query_breakpoint : 0xFFFFFFFFu, 0,
                                 ix->gw_htabs.as<uint32_t>(), hcap, workers, o, (cudaStream_t)stream);
 }
 

@@ -25,10 +25,11 @@ struct GreedyOut {
 };
 
 // greedy_search (lib.rs:183-211) for nq queries, all device pointers.  Query i is queries[q_rows ? q_rows[i] : i].
-// htabs: grid * hcap u32 scratch (hcap a power of two).
+// htabs: workers * hcap u32 scratch (hcap a power of two).  Neighbours >= filter_from are not evaluated (base_vectors_only,
+// lib.rs:196-199) -- for every query, or with d_q_rows only for the queries whose row is >= filter_self_from (build_graph :297-298).
 int greedy_search_launch(mse_index *ix, const __half *d_queries, const uint32_t *d_q_rows, uint32_t nq, const uint32_t *d_starts,
-                         uint32_t start, uint32_t L, uint32_t filter_from, uint32_t *d_htabs, uint32_t hcap, uint32_t grid, GreedyOut o,
-                         cudaStream_t st);
+                         uint32_t start, uint32_t L, uint32_t filter_from, uint32_t filter_self_from, uint32_t *d_htabs, uint32_t hcap, uint32_t workers,
+                         GreedyOut o, cudaStream_t st);
 uint32_t greedy_hash_capacity(uint32_t L, uint32_t stride);
 uint32_t greedy_grid(const mse_index *ix, uint32_t nq);
 
