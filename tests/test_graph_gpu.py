@@ -441,3 +441,25 @@ def test_generate_index_shard_end_to_end(mse, oracle, tmp_path):
     want, _ = oracle.flat_search(q.astype(np.float32), x, 10)
     rec = np.mean([len(set(got[i, :10].tolist()) & set(want[i].tolist())) / 10 for i in range(64)])
     assert rec >= 0.9, rec
+
+
+def test_build_with_query_nodes_is_base_only_for_queries(mse, oracle):
+    """build_graph searches for a QUERY node with base_vectors_only (lib.rs:297-298): its candidates are base vectors plus whatever
+    its current list holds, so query -> query edges are rare.  Same statistic from the oracle's build for comparison."""
+    n, nqn, R = 2000, 300, 16
+    x = np.concatenate([clustered_f16(51, n, n_clusters=12), clustered_f16(52, nqn, n_clusters=12)])
+    cfg_g = mse.diskann.IndexBuildConfig(r=R, l=48, maxc=200, query_breakpoint=n)
+    vl = mse.diskann.VectorList.from_f16s(x)
+    mse.diskann.random_fill_graph(vl, R, seed=2)
+    mse.diskann.build_graph(vl, mse.diskann.medioid(vl), cfg_g, seed=3)
+    adj, deg = vl.get_graph()
+    valid = np.arange(adj.shape[1])[None, :] < deg[:, None]
+    frac_gpu = ((adj[n:] >= n) & valid[n:]).sum() / max(valid[n:].sum(), 1)
+    g = oracle.IndexGraph(n + nqn, R)
+    oracle.random_fill_graph(g, R, seed=2)
+    cfg_o = oracle.make_config(r=R, l=48, maxc=200, query_breakpoint=n)
+    oracle.build_graph(g, oracle.medioid(x), x, cfg_o, seed=3)
+    vo = np.arange(R)[None, :] < g.deg[:, None]
+    frac_cpu = ((g.adj[n:] >= n) & vo[n:]).sum() / max(vo[n:].sum(), 1)
+    assert frac_gpu < 0.08 and frac_cpu < 0.08, (frac_gpu, frac_cpu)
+    vl.close()
