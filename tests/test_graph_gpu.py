@@ -463,3 +463,33 @@ def test_build_with_query_nodes_is_base_only_for_queries(mse, oracle):
     frac_cpu = ((g.adj[n:] >= n) & vo[n:]).sum() / max(vo[n:].sum(), 1)
     assert frac_gpu < 0.08 and frac_cpu < 0.08, (frac_gpu, frac_cpu)
     vl.close()
+
+
+def test_graph_search_edge_cases(mse, oracle, graph_mode):
+    """Empty batch, L = 1, L larger than the graph (the buffer never fills), a start node without out-edges, nodes of degree 0."""
+    n, R = 300, 8
+    x = clustered_f16(97, n, n_clusters=4)
+    g = oracle.IndexGraph(n, R)
+    oracle.random_fill_graph(g, R, seed=4)
+    deg = g.deg
+    deg[5] = 0                                                     # isolated start
+    deg[10:40] = 0                                                 # dead ends
+    deg[40:60] = 3                                                 # ragged lists
+    vl = mse.diskann.VectorList.from_f16s(x)
+    vl.set_graph(g.adj.copy(), g.deg.copy())
+    q = clustered_f16(98, 9, n_clusters=4)
+    empty = mse.diskann.greedy_search(vl, q[:0], 0, mse.diskann.IndexBuildConfig(r=R, l=8, maxc=50))
+    assert empty.ids.shape == (0, 8)
+    for L, start in ((1, 0), (8, 5), (500, 1), (33, 45)):
+        cfg_o = oracle.make_config(r=R, l=L, maxc=50)
+        res = mse.diskann.greedy_search(vl, q, start, mse.diskann.IndexBuildConfig(r=R, l=L, maxc=50), visited_cap=1024)
+        s = oracle.Scratch(n, cfg_o)
+        for i in range(q.shape[0]):
+            d = oracle.greedy_search(s, start, False, q[i], x, g, cfg_o)
+            m = int(res.len[i])
+            assert m == len(s.neighbour_ids) and int(res.distances[i]) == d, (L, start, i)
+            assert np.array_equal(res.ids[i, :m], s.neighbour_ids) and np.array_equal(res.scores[i, :m], s.neighbour_scores)
+            assert (res.ids[i, m:] == 0xFFFFFFFF).all()
+            vi, vs = s.visited_list()
+            assert np.array_equal(res.visited[i][0], vi) and np.array_equal(res.visited[i][1], vs)
+    vl.close()

@@ -302,3 +302,44 @@ def test_rabitq_direct_estimate_matches_numpy(oracle):
         got = oracle.rabitq_direct_estimates(qtm, np.float32(1.0 / np.sqrt(1152.0)), codes, (norms * dots).astype(np.float32))
         want = ref.approx_dot(bits, norms, dots, q[i])
         assert np.abs(got - want).max() < 2e-5
+
+
+def test_robust_stitch_vs_python_model(oracle):
+    """orc_robust_stitch_order against a line-by-line Python model of diskann/src/lib.rs:326-374 (sequential loop over the
+    shuffled query order; stable descending sort; `contains` check; max_add and r limits)."""
+    n, qb, R, max_add = 90, 60, 6, 2
+    x = clustered_f16(77, n, n_clusters=4, d=64)
+    rng = np.random.default_rng(9)
+    adj = rng.integers(0, n, (n, R)).astype(np.uint32)
+    deg = rng.integers(2, R + 1, n).astype(np.uint32)
+    order = (qb + rng.permutation(n - qb)).astype(np.uint32)
+    g = oracle.IndexGraph(n, R)
+    g.set(adj, deg)
+    cfg = oracle.make_config(r=R, l=16, maxc=50, query_breakpoint=qb, max_add_per_stitch_iter=max_add)
+    oracle.robust_stitch(g, x, cfg, order=order)
+    # model
+    lists = [adj[i, : deg[i]].tolist() for i in range(n)]
+    in_edges = [[] for _ in range(n - qb)]
+    for b in range(qb):                                            # :339-347
+        keep = []
+        for t in lists[b]:
+            if t >= qb:
+                in_edges[t - qb].append(b)
+            else:
+                keep.append(t)
+        lists[b] = keep
+    for q in order.tolist():                                       # :349-372
+        qn = lists[q]
+        for b in in_edges[q - qb]:
+            cands = [(nb, np_fast_dot(x[b], x[nb])) for nb in qn]
+            cands = [c for _, c in sorted(enumerate(cands), key=lambda t: (-t[1][1], t[0]))]
+            added = 0
+            for nb, _ in cands:
+                if added >= max_add or len(lists[b]) >= R:
+                    break
+                if nb in lists[b]:
+                    continue
+                lists[b].append(nb)
+                added += 1
+    for i in range(n):
+        assert g.adj[i, : g.deg[i]].tolist() == lists[i], i
