@@ -187,6 +187,9 @@ def main():
     ap.add_argument("--graph-L", type=int, default=64, help="search list size (C4 'beam 64')")
     ap.add_argument("--graph-W", type=int, default=4, help="beam width of the compressed traversal")
     ap.add_argument("--cpu-sample-graph-queries", type=int, default=2048)
+    ap.add_argument("--graph-data", default="mixture", choices=["mixture", "latent"],
+                    help="mixture: SURVEY 8d C4 (4096 Gaussians, sigma 0.3); latent: unit rows on a 48-dimensional latent subspace + 5 %% noise "
+                         "(neighbourhoods a 64-byte code can resolve; used to judge the compressed traversal)")
     ap.add_argument("--batch", type=int, default=256, help="images per rank per step")
     ap.add_argument("--rows", type=int, default=10_000_000, help="flat: total index rows (all shards)")
     ap.add_argument("--queries", type=int, default=1024)
@@ -414,7 +417,9 @@ def main():
         lo, hi = n_total * rank // world, n_total * (rank + 1) // world
         n_local = hi - lo
         gcfg = {"workload": "vamana_graph_search", "index_rows": n_total, "dim": D, "R": R, "L_build": 192, "maxc": 750, "alpha": 1.0,
-                "queries": nq, "L": L, "k": k, "data": "mixture of 4096 Gaussians (sigma 0.3), unit rows, fp16 (SURVEY 8d C4)",
+                "queries": nq, "L": L, "k": k,
+                "data": "mixture of 4096 Gaussians (sigma 0.3), unit rows, fp16 (SURVEY 8d C4)" if args.graph_data == "mixture" else
+                        "unit rows on a 48-dimensional latent subspace + 5 % isotropic noise, fp16",
                 "sharding": f"id-range x{world}, one independent sub-graph per GPU, all-gather + merge of per-shard top-{k}",
                 "l2_policy": "index larger than L2 (rows x 2304 B >> 126 MB)",
                 "note": "BASELINE configs[3] names 1e8 rows on 8 GPUs; the default run holds index_rows on this GPU count"}
@@ -422,10 +427,16 @@ def main():
         cent = torch.randn((4096, D), generator=g4, device=dev)
         cent /= cent.norm(dim=1, keepdim=True)
 
+        basis = torch.linalg.qr(torch.randn((D, 48), generator=g4, device=dev))[0].T.contiguous()   # 48 orthonormal directions
+
         def draw(m, seed):
             gg = torch.Generator(device=dev).manual_seed(seed)
-            a = torch.randint(0, 4096, (m,), generator=gg, device=dev)
-            xx = cent[a] + 0.3 * torch.randn((m, D), generator=gg, device=dev) / D ** 0.5
+            if args.graph_data == "latent":
+                z = torch.randn((m, 48), generator=gg, device=dev)
+                xx = (z / z.norm(dim=1, keepdim=True)) @ basis + 0.05 * torch.randn((m, D), generator=gg, device=dev) / D ** 0.5
+            else:
+                a = torch.randint(0, 4096, (m,), generator=gg, device=dev)
+                xx = cent[a] + 0.3 * torch.randn((m, D), generator=gg, device=dev) / D ** 0.5
             return (xx / xx.norm(dim=1, keepdim=True)).to(torch.float16).contiguous()
 
         vl = dk.VectorList(D, device=local_rank)
