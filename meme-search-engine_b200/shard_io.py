@@ -135,3 +135,33 @@ def generate_index_shard(input_file: str, out_dir: str, queries_bin: str | None 
     write_shard(out_dir, si.id, si.centroid, med, adj, deg, si.original_ids)
     return {"id": si.id, "vectors": int(query_breakpoint), "queries": int(len(vectors) - query_breakpoint), "medioid": med, "build": stats,
             "mean_degree": float(deg[:query_breakpoint].mean()) if query_breakpoint else 0.0}
+
+
+def main(argv=None) -> int:
+    """CLI with the reference binary's arguments (generate_index_shard.rs:13-37): input_file out_dir [queries_bin] -L -R -C -A -Q -B -s."""
+    import argparse
+    import json
+    ap = argparse.ArgumentParser(description="Generate indices from shard files (GPU)")
+    ap.add_argument("input_file")
+    ap.add_argument("out_dir")
+    ap.add_argument("queries_bin", nargs="?")
+    ap.add_argument("-L", dest="l", type=int, default=192, help="search list size (higher is better but slower)")
+    ap.add_argument("-R", dest="r", type=int, default=64, help="graph degree")
+    ap.add_argument("-C", dest="maxc", type=int, default=750, help="max candidate list size")
+    ap.add_argument("-A", dest="alpha", type=int, default=65536, help="first pass relaxation factor (times 2^16)")
+    ap.add_argument("-Q", dest="query_alpha", type=int, default=65536, help="query set special relaxation factor (times 2^16)")
+    ap.add_argument("-B", dest="alpha_2", type=int, default=65536, help="second pass relaxation factor (times 2^16)")
+    ap.add_argument("-s", dest="second_pass", action="store_true", help="do second pass")
+    ap.add_argument("-N", dest="n", type=int, default=None, help="number of vectors to allocate for (accepted for compatibility; unused)")
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=0)
+    a = ap.parse_args(argv)
+    info = generate_index_shard(a.input_file, a.out_dir, a.queries_bin, l=a.l, r=a.r, maxc=a.maxc, alpha=a.alpha, query_alpha=a.query_alpha,
+                                alpha_2=a.alpha_2, second_pass=a.second_pass, seed=a.seed, device=a.device)
+    print(json.dumps(info))
+    print(f"{info['vectors']} vectors")                                     # generate_index_shard.rs:167
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
