@@ -175,18 +175,45 @@ def random_openclip_state_dict(dev, depth_v=27, seed=42):
     return sd
 
 
+def random_openclip_text_state_dict(dev, depth_t=27, seed=43, vocab=32000, ctx=64):
+    """Random init of the text tower (OpenCLIP TextTransformer names, clip_server.py:98)."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    F = 4304
+
+    def mat(*shape, std=0.02):
+        return (torch.randn(shape, generator=g, device=dev) * std).to(torch.float16).cpu().numpy()
+
+    def vec(n, base=0.0, std=0.02):
+        return (base + std * torch.randn((n,), generator=g, device=dev)).float().cpu().numpy()
+
+    sd = {"text.token_embedding.weight": mat(vocab, D), "text.positional_embedding": mat(ctx, D, std=D ** -0.5)}
+    for i in range(depth_t):
+        p = f"text.transformer.resblocks.{i}."
+        sd[p + "ln_1.weight"], sd[p + "ln_1.bias"] = vec(D, 1.0, 0.05), vec(D)
+        sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"] = mat(3 * D, D), vec(3 * D)
+        sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"] = mat(D, D), vec(D)
+        sd[p + "ln_2.weight"], sd[p + "ln_2.bias"] = vec(D, 1.0, 0.05), vec(D)
+        sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"] = mat(F, D), vec(F)
+        sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"] = mat(D, F), vec(D)
+    sd["text.ln_final.weight"], sd["text.ln_final.bias"] = vec(D, 1.0, 0.05), vec(D)
+    sd["text.text_projection.weight"], sd["text.text_projection.bias"] = mat(D, D), vec(D)
+    return sd
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workloads", default="tower,flat,graph", help="comma list of tower, flat, graph")
+    ap.add_argument("--workloads", default="tower,flat,graph", help="comma list of tower, flat, graph, e2e (e2e = BASELINE configs[4] at reduced scale; not in the default set)")
     ap.add_argument("--graph-rows", type=int, default=1_000_000, help="graph: total index rows (all shards); C4's 1e8 needs 8 GPUs x 12.5M and a long build")
     ap.add_argument("--graph-queries", type=int, default=4096)
     ap.add_argument("--graph-L", type=int, default=64, help="search list size (C4 'beam 64')")
     ap.add_argument("--graph-W", type=int, default=4, help="beam width of the compressed traversal")
     ap.add_argument("--cpu-sample-graph-queries", type=int, default=2048)
+    ap.add_argument("--e2e-images", type=int, default=32768, help="e2e workload (not in the default set): images per rank to encode and index")
     ap.add_argument("--graph-data", default="mixture", choices=["mixture", "latent"],
                     help="mixture: SURVEY 8d C4 (4096 Gaussians, sigma 0.3); latent: unit rows on a 48-dimensional latent subspace + 5 %% noise "
                          "(neighbourhoods a 64-byte code can resolve; used to judge the compressed traversal)")
@@ -601,6 +628,94 @@ def main():
         else:
             result = dict(graph, steps=steps, warmup=warmup, vs_baseline=None, data="synthetic")
         vl.close()
+
+    # ============================================================ end to end (C5 at reduced scale): encode -> index -> build -> serve
+    if "e2e" in wl:
+        from mse_b200 import diskann as dk
+        B, n_img, nq_t, nq_i, Ls, k = 256, args.e2e_images // 256 * 256, 500, 500, 64, 10
+        wpath = os.path.join(tempfile.gettempdir(), f"mse_bench_e2e_rank{rank}.msew")
+        sd = random_openclip_state_dict(dev)
+        sd.update(random_openclip_text_state_dict(dev))
+        mse_b200.weights.save_weights(wpath, sd, mse_b200.weights.config_for(sd))
+        del sd
+        enc = mse_b200.Encoder(wpath, device=local_rank, max_batch=B)
+        os.remove(wpath)
+        vl = dk.VectorList(D, device=local_rank)
+        vl.reserve(n_img)
+        feat = torch.empty((B, D), dtype=torch.float16, device=dev)
+        g6 = torch.Generator(device=dev).manual_seed(6 + rank)
+        base_imgs = torch.randint(0, 256, (B, 24, 24, 3), generator=g6, device=dev, dtype=torch.uint8)
+
+        def make_batch():
+            # blocky pattern + per-pixel noise so that images (and their embeddings) differ from each other
+            up = base_imgs[torch.randperm(B, generator=g6, device=dev)].repeat_interleave(16, 1).repeat_interleave(16, 2).to(torch.int16)
+            noise = torch.randint(-40, 41, (B, 384, 384, 3), generator=g6, device=dev, dtype=torch.int16)
+            return (up + noise).clamp_(0, 255).to(torch.uint8).contiguous()
+
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        imgs = make_batch()
+        enc.encode_image_dev(imgs.data_ptr(), B, feat.data_ptr(), stream)      # warm-up
+        barrier()
+        t_wall0 = time.perf_counter()
+        enc_ms = 0.0
+        for b0 in range(0, n_img, B):
+            imgs = make_batch()
+            ev[0].record()
+            enc.encode_image_dev(imgs.data_ptr(), B, feat.data_ptr(), stream)
+            vl.add_f16_dev(feat.data_ptr(), B, stream)
+            ev[1].record()
+            ev[1].synchronize()
+            enc_ms += ev[0].elapsed_time(ev[1])
+        t0 = time.perf_counter()
+        dk.random_fill_graph(vl, 64, seed=1 + rank)
+        med = dk.medioid(vl)
+        bst = dk.build_graph(vl, med, dk.IndexBuildConfig(r=64, l=192, maxc=750), seed=7 + rank)
+        build_s = time.perf_counter() - t0
+        # serve: 500 text queries (token ids: no tokenizer model offline) + 500 image queries, one search batch each
+        gid = torch.Generator(device="cpu").manual_seed(8)
+        ids = torch.ones((nq_t, 64), dtype=torch.int32)
+        for i in range(nq_t):
+            Lt = int(torch.randint(3, 17, (1,), generator=gid))
+            ids[i, :Lt] = torch.randint(2, 32000, (Lt,), generator=gid, dtype=torch.int32)
+        ids_dev = ids.to(dev)
+        q_feat = torch.empty((nq_t + nq_i, D), dtype=torch.float16, device=dev)
+        q_imgs = [make_batch() for _ in range((nq_i + B - 1) // B)]
+        out_ids = torch.empty((nq_t + nq_i, Ls), dtype=torch.int32, device=dev)
+        out_sc = torch.empty((nq_t + nq_i, Ls), dtype=torch.int64, device=dev)
+        out_len = torch.empty(nq_t + nq_i, dtype=torch.int32, device=dev)
+        out_dist = torch.empty(nq_t + nq_i, dtype=torch.int64, device=dev)
+        res_host = torch.empty((nq_t + nq_i, k), dtype=torch.int32).pin_memory()
+
+        def serve():
+            for b0 in range(0, nq_t, B):
+                m = min(B, nq_t - b0)
+                enc.encode_text_dev(ids_dev[b0:b0 + m].data_ptr(), m, q_feat[b0:b0 + m].data_ptr(), stream)
+            for bi, b0 in enumerate(range(0, nq_i, B)):
+                m = min(B, nq_i - b0)
+                enc.encode_image_dev(q_imgs[bi].data_ptr(), m, q_feat[nq_t + b0:nq_t + b0 + m].data_ptr(), stream)
+            dk.greedy_search_dev(vl, q_feat.data_ptr(), nq_t + nq_i, Ls, med, out_ids.data_ptr(), out_sc.data_ptr(), out_len.data_ptr(),
+                                 out_dist.data_ptr(), stream)
+            res_host.copy_(out_ids[:, :k], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        serve()
+        ms_serve, _ = timed(serve, 1, 3)
+        dk.greedy_search_check(vl, nq_t + nq_i)
+        wall = time.perf_counter() - t_wall0
+        e2e = {"metric": "end to end: encode + index + build + serve (BASELINE configs[4] at reduced scale)", "n_gpus": world,
+               "config": {"workload": "e2e_encode_build_serve", "images_per_gpu": n_img, "graph": "R 64, L 192, C 750", "queries": "500 text (token ids) + 500 image, L = 64, top-10",
+                          "note": "configs[4] names 1M images on 8 GPUs (>= 61 s of encoder work at the tensor roofline); this run encodes images_per_gpu per rank"},
+               "encode": {"images_per_s": world * n_img / (enc_ms * 1e-3), "seconds": enc_ms * 1e-3},
+               "build": {"seconds": build_s, "points_per_s": n_img / build_s, "stats": bst},
+               "serve": {"queries_per_s": (nq_t + nq_i) / (ms_serve * 1e-3), "ms_per_batch_of_1000": ms_serve,
+                         "includes": "text tower (500) + image tower (500) + graph search + D2H of top-10 ids"},
+               "wall_seconds_total": wall}
+        if result:
+            result["e2e_pipeline"] = e2e
+        else:
+            result = dict(e2e, steps=steps, warmup=warmup, vs_baseline=None, data="synthetic")
+        vl.close()
+        enc.close()
 
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
