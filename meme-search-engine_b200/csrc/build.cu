@@ -57,6 +57,7 @@ __device__ __forceinline__ void bitonic_sort_cands(long long *sc, uint32_t *ord,
 // One CTA prunes one point.  Candidates arrive as up to two segments (visited list, then extra ids whose scores are
 // computed here with fast_dot against the point: merge_existing_neighbours lib.rs:215-221).
 //   seg A: a_ids/a_scores [a_len]           seg B: b_ids [b_len] (scored here)
+template <int NC2>   // 64-element chunks per row (d / 64) known at compile time, or 0 for a runtime d
 __device__ void prune_point(const __half *__restrict__ x, uint32_t d, uint32_t p, const uint32_t *a_ids, const long long *a_scores, uint32_t a_len,
                             const uint32_t *b_ids, uint32_t b_len, const PruneCfg &cfg, uint32_t *out, uint32_t *out_len, uint8_t *smem) {
     long long *sc = (long long *)smem;                 // [kSortN]
@@ -73,12 +74,11 @@ __device__ void prune_point(const __half *__restrict__ x, uint32_t d, uint32_t p
     if (b_len) {
         for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) pv[i] = __half2float(x[(size_t)p * d + i]);
         __syncthreads();
-        for (uint32_t i = warp; i < b_len; i += kPruneWarps) {
-            float acc = 0.f;
-            const __half *row = x + (size_t)b_ids[i] * d;
-            for (uint32_t c = lane; c < d; c += 32) acc = fmaf(pv[c], __half2float(row[c]), acc);
-            const long long s = fast_dot_fix(fast_dot_reduce(acc));
-            if (lane == 0) bsc[i] = s;
+        for (uint32_t i = 2 * warp; i < b_len; i += 2 * kPruneWarps) {          // two rows per pass (fastdot.cuh wq_score2)
+            const uint32_t j = i + 1 < b_len ? i + 1 : i;
+            long long s0, s1;
+            wq_score2<NC2>(pv, x + (size_t)b_ids[i] * d, x + (size_t)b_ids[j] * d, d, lane, s0, s1);
+            if (lane == 0) { bsc[i] = s0; bsc[j] = s1; }
         }
         __syncthreads();
     }
@@ -91,10 +91,12 @@ __device__ void prune_point(const __half *__restrict__ x, uint32_t d, uint32_t p
     while (done < a_len || first) {
         first = false;
         const uint32_t take = min((uint32_t)kSortN - filled, a_len - done);
+        uint32_t sortn = 64;                                   // the window is only as large as what it has to hold
+        while (sortn < filled + take) sortn <<= 1;
         for (uint32_t i = threadIdx.x; i < take; i += blockDim.x) { sc[filled + i] = a_scores[done + i]; ord[filled + i] = done + i; }
-        for (uint32_t i = filled + take + threadIdx.x; i < (uint32_t)kSortN; i += blockDim.x) { sc[i] = kDead; ord[i] = 0xFFFFFFFFu; }
+        for (uint32_t i = filled + take + threadIdx.x; i < sortn; i += blockDim.x) { sc[i] = kDead; ord[i] = 0xFFFFFFFFu; }
         __syncthreads();
-        bitonic_sort_cands(sc, ord, kSortN);
+        bitonic_sort_cands(sc, ord, (int)sortn);
         done += take;
         filled = min((uint32_t)kKeep, filled + take);
     }
@@ -130,18 +132,27 @@ __device__ void prune_point(const __half *__restrict__ x, uint32_t d, uint32_t p
         if (from < s_n) {
             for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) pv[i] = __half2float(x[(size_t)p_star * d + i]);
             __syncthreads();
-            for (int i = from + warp; i < s_n; i += kPruneWarps) {
-                const long long pps = sc[i];
-                if (pps == kDead) continue;  // warp-uniform
-                const uint32_t p_prime = cid[i];
-                // fast_dot(p', p*): operand order does not matter, each lane multiplies the same pair of values
-                float acc = 0.f;
-                const __half *row = x + (size_t)p_prime * d;
-                for (uint32_t c = lane; c < d; c += 32) acc = fmaf(__half2float(row[c]), pv[c], acc);
-                const long long sps = fast_dot_fix(fast_dot_reduce(acc));
-                const long long a = p_prime >= cfg.query_breakpoint ? cfg.query_alpha : cfg.alpha;
-                const long long scaled = (long long)((unsigned long long)a * (unsigned long long)sps) >> 16;  // wrapping mul, arithmetic shift
-                if (lane == 0 && scaled >= pps) sc[i] = kDead;
+            // fast_dot(p', p*) for every live later candidate, two per pass (operand order does not matter: each product is
+            // of the same pair of values).  Each warp owns a fixed pair of positions per stride, so no two warps touch one entry.
+            for (int i = from + 2 * warp; i < s_n; i += 2 * kPruneWarps) {
+                const int j = i + 1;
+                const long long pps0 = sc[i], pps1 = j < s_n ? sc[j] : kDead;
+                if (pps0 == kDead && pps1 == kDead) continue;  // warp-uniform
+                const int i0 = pps0 != kDead ? i : j, i1 = pps1 != kDead ? j : i;     // a dead slot borrows the live row (result unused)
+                long long sps0, sps1;
+                wq_score2<NC2>(pv, x + (size_t)cid[i0] * d, x + (size_t)cid[i1] * d, d, lane, sps0, sps1);
+                if (lane == 0) {
+                    if (pps0 != kDead) {
+                        const long long a = cid[i] >= cfg.query_breakpoint ? cfg.query_alpha : cfg.alpha;
+                        const long long scaled = (long long)((unsigned long long)a * (unsigned long long)sps0) >> 16;  // wrapping mul, arithmetic shift
+                        if (scaled >= pps0) sc[i] = kDead;
+                    }
+                    if (pps1 != kDead) {
+                        const long long a = cid[j] >= cfg.query_breakpoint ? cfg.query_alpha : cfg.alpha;
+                        const long long scaled = (long long)((unsigned long long)a * (unsigned long long)sps1) >> 16;
+                        if (scaled >= pps1) sc[j] = kDead;
+                    }
+                }
             }
         }
         __syncthreads();
@@ -167,14 +178,16 @@ __device__ void prune_point(const __half *__restrict__ x, uint32_t d, uint32_t p
 static size_t prune_smem_bytes(uint32_t d, uint32_t r) { (void)r; return (size_t)kSortN * 12 + (size_t)kKeep * 4 + (((size_t)d * 4 + 256 * 4 + 15) & ~(size_t)15) + 512 * 8 + 64; }
 
 // standalone: one point, explicit candidates with scores (unit parity against the oracle)
+template <int NC2>
 __global__ void __launch_bounds__(kPruneThreads) k_robust_prune_one(const __half *x, uint32_t d, uint32_t p, const uint32_t *ids, const long long *scores,
                                                                     uint32_t n, PruneCfg cfg, uint32_t *out, uint32_t *out_len) {
     extern __shared__ __align__(16) uint8_t smem[];
-    prune_point(x, d, p, ids, scores, n, nullptr, 0, cfg, out, out_len, smem);
+    prune_point<NC2>(x, d, p, ids, scores, n, nullptr, 0, cfg, out, out_len, smem);
 }
 
 // batch step 1 (lib.rs:299-309): for batch point b: candidates = visited list of its search ++ its current neighbours; prune;
 // the result goes to new_adj[b] (applied after the whole batch was pruned)
+template <int NC2>
 __global__ void __launch_bounds__(kPruneThreads) k_prune_batch(const __half *x, uint32_t d, const uint32_t *points, uint32_t nb, const uint32_t *vl_ids,
                                                                const long long *vl_scores, const uint32_t *vl_len, uint32_t vl_cap, const uint32_t *adj,
                                                                const uint32_t *deg, uint32_t stride, PruneCfg cfg, uint32_t *new_adj, uint32_t *new_deg) {
@@ -182,7 +195,7 @@ __global__ void __launch_bounds__(kPruneThreads) k_prune_batch(const __half *x, 
     for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
         const uint32_t p = points[b];
         const uint32_t n_vl = min(vl_len[b], vl_cap);
-        prune_point(x, d, p, vl_ids + (size_t)b * vl_cap, vl_scores + (size_t)b * vl_cap, n_vl, adj + (size_t)p * stride, min(deg[p], stride), cfg,
+        prune_point<NC2>(x, d, p, vl_ids + (size_t)b * vl_cap, vl_scores + (size_t)b * vl_cap, n_vl, adj + (size_t)p * stride, min(deg[p], stride), cfg,
                     new_adj + (size_t)b * stride, new_deg + b, smem);
     }
 }
@@ -207,6 +220,7 @@ __global__ void k_apply_and_backedges(const uint32_t *points, uint32_t nb, const
 // once the list is full, re-prune n over its neighbours ++ the remaining incoming points.
 // (The reference re-prunes once per incoming edge under the node's lock; merging them into one prune per batch is the
 // batch-synchronous restatement.)
+template <int NC2>
 __global__ void __launch_bounds__(kPruneThreads) k_merge_backedges(const __half *x, uint32_t d, const uint32_t *touched, uint32_t n_touched,
                                                                    uint32_t *incoming, uint32_t *in_cnt, uint32_t *adj, uint32_t *deg, uint32_t stride,
                                                                    PruneCfg cfg) {
@@ -241,7 +255,7 @@ __global__ void __launch_bounds__(kPruneThreads) k_merge_backedges(const __half 
             if (threadIdx.x == 0) deg[n] = cnt;
             __syncthreads();
         } else {
-            prune_point(x, d, n, nullptr, nullptr, 0, s_list, cnt, cfg, s_out, &s_outlen, smem);
+            prune_point<NC2>(x, d, n, nullptr, nullptr, 0, s_list, cnt, cfg, s_out, &s_outlen, smem);
             for (uint32_t i = threadIdx.x; i < s_outlen; i += blockDim.x) nl[i] = s_out[i];
             if (threadIdx.x == 0) deg[n] = s_outlen;
             __syncthreads();
@@ -462,15 +476,16 @@ MSE_API int mse_robust_prune(mse_index *ix, uint32_t p, const uint32_t *cand_ids
     MSE_REQUIRE(ix->d % 64 == 0, MSE_ERR_UNSUPPORTED, "robust_prune: d %% 64 != 0");
     MSE_CHECK(use_device(ix->device));
     const size_t smem = prune_smem_bytes(ix->d, (uint32_t)cfg->r);
-    MSE_CUDA(cudaFuncSetAttribute(k_robust_prune_one, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool fixed = ix->d == 1152;
+    MSE_CUDA(cudaFuncSetAttribute(fixed ? k_robust_prune_one<18> : k_robust_prune_one<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DevBuf bi, bs, bo;
     int rc = MSE_OK;
     do {
         if ((rc = bi.ensure(std::max<size_t>(n_cand, 1) * 4)) || (rc = bs.ensure(std::max<size_t>(n_cand, 1) * 8)) || (rc = bo.ensure((cfg->r + 1) * 4))) break;
         cudaMemcpy(bi.p, cand_ids, (size_t)n_cand * 4, cudaMemcpyHostToDevice);
         cudaMemcpy(bs.p, cand_scores, (size_t)n_cand * 8, cudaMemcpyHostToDevice);
-        k_robust_prune_one<<<1, kPruneThreads, smem>>>(ix->x, ix->d, p, bi.as<uint32_t>(), bs.as<long long>(), n_cand, to_prune_cfg(*cfg),
-                                                      bo.as<uint32_t>(), bo.as<uint32_t>() + cfg->r);
+        (fixed ? k_robust_prune_one<18> : k_robust_prune_one<0>)<<<1, kPruneThreads, smem>>>(ix->x, ix->d, p, bi.as<uint32_t>(), bs.as<long long>(), n_cand,
+                                                                                            to_prune_cfg(*cfg), bo.as<uint32_t>(), bo.as<uint32_t>() + cfg->r);
         count_launch();
         std::vector<uint32_t> h(cfg->r + 1);
         cudaError_t e = cudaMemcpy(h.data(), bo.p, (cfg->r + 1) * 4, cudaMemcpyDeviceToHost);
@@ -545,8 +560,11 @@ MSE_API int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_bu
     const uint32_t grid_s = greedy_grid(ix, max_batch);
     const uint32_t hcap = greedy_hash_capacity(L, stride);
     const size_t psmem = prune_smem_bytes(ix->d, (uint32_t)cfg->r);
-    MSE_CUDA(cudaFuncSetAttribute(k_prune_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-    MSE_CUDA(cudaFuncSetAttribute(k_merge_backedges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    const bool fixed = ix->d == 1152;
+    auto prune_batch = fixed ? k_prune_batch<18> : k_prune_batch<0>;
+    auto merge_backedges = fixed ? k_merge_backedges<18> : k_merge_backedges<0>;
+    MSE_CUDA(cudaFuncSetAttribute(prune_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    MSE_CUDA(cudaFuncSetAttribute(merge_backedges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     DevBuf b_sigma, b_ids, b_sc, b_len, b_dist, b_st, b_h, b_vi, b_vs, b_vl, b_na, b_nd, b_in, b_ic, b_t, b_nt;
     int rc = MSE_OK;
     uint64_t st_batches = 0, st_search = 0, st_merge = 0, st_dist = 0;
@@ -573,7 +591,7 @@ MSE_API int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_bu
             // greedy_search(medioid -> point) (lib.rs:299); query points search base vectors only (:298)
             if ((rc = greedy_search_launch(ix, ix->x, pts, nb, nullptr, medioid, L, cfg->query_breakpoint, cfg->query_breakpoint, b_h.as<uint32_t>(), hcap,
                                            greedy_grid(ix, nb), o, nullptr))) break;
-            k_prune_batch<<<std::min(nb, sms * 2), kPruneThreads, psmem>>>(ix->x, ix->d, pts, nb, b_vi.as<uint32_t>(), b_vs.as<long long>(), b_vl.as<uint32_t>(),
+            prune_batch<<<std::min(nb, sms * 4), kPruneThreads, psmem>>>(ix->x, ix->d, pts, nb, b_vi.as<uint32_t>(), b_vs.as<long long>(), b_vl.as<uint32_t>(),
                                                                           vl_cap, ix->adj, ix->deg, stride, pc, b_na.as<uint32_t>(), b_nd.as<uint32_t>());
             count_launch();
             cudaMemsetAsync(b_nt.p, 0, 4);
@@ -584,7 +602,7 @@ MSE_API int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_bu
             cudaError_t e = cudaMemcpy(&nt, b_nt.p, 4, cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) { set_error("build_vamana: %s", cudaGetErrorString(e)); rc = MSE_ERR_CUDA; break; }
             if (nt) {
-                k_merge_backedges<<<std::min(nt, sms * 2), kPruneThreads, psmem>>>(ix->x, ix->d, b_t.as<uint32_t>(), nt, b_in.as<uint32_t>(), b_ic.as<uint32_t>(),
+                merge_backedges<<<std::min(nt, sms * 4), kPruneThreads, psmem>>>(ix->x, ix->d, b_t.as<uint32_t>(), nt, b_in.as<uint32_t>(), b_ic.as<uint32_t>(),
                                                                                   ix->adj, ix->deg, stride, pc);
                 count_launch();
             }

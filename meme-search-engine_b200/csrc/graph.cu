@@ -271,52 +271,6 @@ __device__ __forceinline__ bool hs_insert_nc(uint32_t *tab, uint32_t mask, uint3
     return false;
 }
 
-// Two rows per pass, half a warp per row.  Every lane loads one half2 (elements 2*lane, 2*lane+1 of each 64-element chunk:
-// one 128-byte request per row and chunk); lane l < 16 then owns the reference's partial sums 2l and 2l+1 of row 0 and lane
-// 16 + l the same partials of row 1, so one shfl_xor(16) per chunk hands each half warp the other half of its row.  Partial i
-// still accumulates elements i, i+32, i+64, ... in that order with FMA (vector.rs:212-238), and the reduction below is the
-// tree of vector.rs:241-249 re-indexed for two partials per lane -- the scores are bit-identical to fast_dot.
-template <int NC2>   // 64-element chunks per row (d / 64), 0 = runtime d
-__device__ __forceinline__ void wq_score2(const float *qs, const __half *__restrict__ r0, const __half *__restrict__ r1, uint32_t d, int lane,
-                                          long long &s0, long long &s1) {
-    const unsigned full = 0xffffffffu;
-    const int l = lane & 15;
-    const bool upper = lane >= 16;
-    const uint32_t *a2 = reinterpret_cast<const uint32_t *>(r0) + lane;
-    const uint32_t *b2 = reinterpret_cast<const uint32_t *>(r1) + lane;
-    const float2 *q2 = reinterpret_cast<const float2 *>(qs);
-    float lo = 0.f, hi = 0.f;
-    auto step = [&](uint32_t va, uint32_t vb, uint32_t c) {
-        const uint32_t recv = __shfl_xor_sync(full, upper ? va : vb, 16);
-        const uint32_t first = upper ? recv : va, second = upper ? vb : recv;
-        const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&first));
-        const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&second));
-        const float2 qa = q2[32 * c + l], qb = q2[32 * c + 16 + l];
-        lo = fmaf(qa.x, f1.x, lo); hi = fmaf(qa.y, f1.y, hi);
-        lo = fmaf(qb.x, f2.x, lo); hi = fmaf(qb.y, f2.y, hi);
-    };
-    if constexpr (NC2 > 0) {
-        uint32_t va[NC2], vb[NC2];
-#pragma unroll
-        for (int c = 0; c < NC2; c++) { va[c] = __ldg(a2 + 32 * c); vb[c] = __ldg(b2 + 32 * c); }
-#pragma unroll
-        for (int c = 0; c < NC2; c++) step(va[c], vb[c], (uint32_t)c);
-    } else {
-        const uint32_t nc = d >> 6;
-#pragma unroll 4
-        for (uint32_t c = 0; c < nc; c++) step(__ldg(a2 + 32 * c), __ldg(b2 + 32 * c), c);
-    }
-    lo += __shfl_down_sync(full, lo, 4);             // acc1+acc2 / acc3+acc4 (:241-242): valid at l in {0..3, 8..11}
-    hi += __shfl_down_sync(full, hi, 4);
-    const float pr = lo + hi;                        // hadd pairs (:243)
-    const float q4 = pr + __shfl_down_sync(full, pr, 2);   // lo + hi halves (:244-246): valid at l in {0, 1, 8, 9}
-    const int gb = lane & 16;
-    const float e0 = __shfl_sync(full, q4, gb), e1 = __shfl_sync(full, q4, gb + 1), e2 = __shfl_sync(full, q4, gb + 8), e3 = __shfl_sync(full, q4, gb + 9);
-    const float r = ((e0 + e1) + e2) + e3;           // :247-249
-    s0 = fast_dot_fix(__shfl_sync(full, r, 0));
-    s1 = fast_dot_fix(__shfl_sync(full, r, 16));
-}
-
 template <int NC2>
 __global__ void __launch_bounds__(kWqWarps * 32, 8) k_greedy_search_wq(GraphArgs g, const __half *__restrict__ queries, const uint32_t *__restrict__ q_rows,
                                                                        uint32_t nq, const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L,
