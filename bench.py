@@ -44,6 +44,8 @@ NCU_TRAFFIC = {
     "tower_gemm_bytes_per_step_b256": 27 * (2.065 + 3.454 + 1.682 + 1.262) * 1e9,
     # profiles/r01_flat_gemm_ncu_full.md: 3.745 GB read + 5.6 MB written for the 3.74 GB of rows the launch scored
     "flat_gemm_bytes_per_row_byte": (3.745176 + 0.005563) / 3.74,
+    # profiles/r01i_greedy_1m_ncu_full.md: 14.376 GB read + 0.652 GB written for 15.00 GB of gathered rows (1 M rows, 4096 queries, L = 64)
+    "greedy_bytes_per_row_byte": (14.376188 + 0.651920) / (1589.4404296875 * 4096 * 2304 / 1e9),
 }
 
 
@@ -559,7 +561,9 @@ def main():
                  "roofline": {"kernel": "k_greedy_search_wq<18> (one warp per query, half a warp per gathered row, exact fp16 rows)", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"],
                               "unit": "GB/s", "frac": gbs / pk["hbm"], "peak_source": pk["src"] + " (HBM copy)",
                               "algorithmic_bytes": "distances x 2304 B (gathered rows; adjacency lists and the query are < 2 %)",
-                              "launches_per_step": 1, "kernel_ms_per_step": ms_kernel, "kernel_share_of_step": ms_kernel / ms_g, "traffic": None},
+                              "launches_per_step": 1, "kernel_ms_per_step": ms_kernel, "kernel_share_of_step": ms_kernel / ms_g,
+                              "traffic": NCU_TRAFFIC["greedy_bytes_per_row_byte"] * row_bytes,
+                              "traffic_note": "ratio measured at 1 M rows (profiles/r01i_greedy_1m_ncu_full.md): every gathered row leaves HBM once"},
                  "build": {"seconds": build_s, "points_per_s": n_local / build_s, "stats": bst, "mean_degree": None}}
         # compressed traversal (C4: RabitQ codes, beam W): candidates by the RabitQ estimate, expanded nodes exact
         try:
