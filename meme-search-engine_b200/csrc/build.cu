@@ -292,11 +292,23 @@ __global__ void k_random_fill(uint32_t *adj, uint32_t *deg, uint64_t n, uint32_t
 __global__ void k_centroid(const __half *__restrict__ x, uint64_t n, uint32_t d, __half *__restrict__ out16) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d) return;
+    // the running mean is a sequential recurrence per dimension (that order is the definition, lib.rs:55-58); only the loads
+    // can run ahead: 32 rows are fetched before the 32 dependent updates
     float c = 0.f;
-    for (uint64_t i = 0; i < n; i++) {
+    uint64_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        __half v[32];
+#pragma unroll
+        for (int u = 0; u < 32; u++) v[u] = x[(i + u) * d + j];
+#pragma unroll
+        for (int u = 0; u < 32; u++) {
+            const float w = __fdiv_rn(1.0f, (float)(i + u + 1));
+            c = __fadd_rn(c, __fmul_rn(__fsub_rn(__half2float(v[u]), c), w));
+        }
+    }
+    for (; i < n; i++) {
         const float w = __fdiv_rn(1.0f, (float)(i + 1));
-        const float v = __half2float(x[i * d + j]);
-        c = __fadd_rn(c, __fmul_rn(__fsub_rn(v, c), w));
+        c = __fadd_rn(c, __fmul_rn(__fsub_rn(__half2float(x[i * d + j]), c), w));
     }
     out16[j] = __float2half_rn(c);
 }
