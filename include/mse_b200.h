@@ -154,6 +154,12 @@ int mse_search_beam(mse_index *ix, const uint16_t *q_f16, const float *luts, con
 int mse_search_beam_scaled(mse_index *ix, const uint16_t *q_f16, const float *luts, const float *code_bias, const float *desc_scales,
                            uint32_t nq, uint32_t L, uint32_t W, const uint32_t *starts, uint32_t start, uint32_t n_centroids,
                            uint32_t *out_ids, int64_t *out_scores, uint32_t *out_len, uint32_t out_cap, uint64_t *cmps, uint64_t *pq_cmps);
+/* Runtime de-duplication + top-k over the visit lists the last mse_search_beam_dev call on this handle left in HBM
+ * (query_disk_index.rs:99,486-529): walking the expanded nodes in visit order, a node is dropped when an earlier KEPT node has
+ * dot product (cosine of the unit fp16 rows, f32) > threshold (the reference's DUPLICATES_THRESHOLD is 0.95); the kept nodes are
+ * ranked by (score desc, visit order).  d_kept (optional): kept nodes per query.  Same stream as the search. */
+int mse_dedup_topk_dev(mse_index *ix, uint32_t nq, float threshold, uint32_t topk, uint32_t *d_top_ids, int64_t *d_top_scores,
+                       uint32_t *d_top_len, uint32_t *d_kept, void *stream);
 int mse_index_set_code_scales(mse_index *ix, const float *scales);
 /* Beam search with every buffer in HBM, asynchronous on `stream`; the best `topk` expanded nodes are selected on the device
  * ((score desc, visit order asc): the stable sort of query_disk_index.rs:303).  Candidate scores: d_luts ([nq][M*n_centroids],

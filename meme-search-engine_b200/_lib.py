@@ -70,6 +70,7 @@ _SIGS = {
     "mse_search_beam": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _u32, _i32, _u32, _vp, _vp, _vp, _u32, _vp, _vp]),
     "mse_search_beam_scaled": (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _u32, _vp, _vp]),
     "mse_index_set_code_scales": (_i32, [_vp, _vp]),
+    "mse_dedup_topk_dev": (_i32, [_vp, _u32, C.c_float, _u32, _vp, _vp, _vp, _vp, _vp]),
     "mse_search_beam_dev": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _vp, _u32, _u32, _u32, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mse_scores_i64": (_i32, [_vp, _vp, _vp]),
     "mse_robust_prune": (_i32, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),

@@ -50,8 +50,8 @@ __device__ __forceinline__ float fast_dot_warp_q(const float (&qreg)[NCH], const
 // still accumulates elements i, i+32, i+64, ... in that order with FMA (vector.rs:212-238), and the reduction below is the
 // tree of vector.rs:241-249 re-indexed for two partials per lane -- the scores are bit-identical to fast_dot.
 template <int NC2>   // 64-element chunks per row (d / 64), 0 = runtime d
-__device__ __forceinline__ void wq_score2(const float *qs, const __half *__restrict__ r0, const __half *__restrict__ r1, uint32_t d, int lane,
-                                          long long &s0, long long &s1) {
+__device__ __forceinline__ void wq_dot2(const float *qs, const __half *__restrict__ r0, const __half *__restrict__ r1, uint32_t d, int lane,
+                                        float &f0, float &f1) {
     const unsigned full = 0xffffffffu;
     const int l = lane & 15;
     const bool upper = lane >= 16;
@@ -86,8 +86,17 @@ __device__ __forceinline__ void wq_score2(const float *qs, const __half *__restr
     const int gb = lane & 16;
     const float e0 = __shfl_sync(full, q4, gb), e1 = __shfl_sync(full, q4, gb + 1), e2 = __shfl_sync(full, q4, gb + 8), e3 = __shfl_sync(full, q4, gb + 9);
     const float r = ((e0 + e1) + e2) + e3;           // :247-249
-    s0 = fast_dot_fix(__shfl_sync(full, r, 0));
-    s1 = fast_dot_fix(__shfl_sync(full, r, 16));
+    f0 = __shfl_sync(full, r, 0);
+    f1 = __shfl_sync(full, r, 16);
+}
+// the same as fixed-point scores (vector.rs:249-250)
+template <int NC2>
+__device__ __forceinline__ void wq_score2(const float *qs, const __half *__restrict__ r0, const __half *__restrict__ r1, uint32_t d, int lane,
+                                          long long &s0, long long &s1) {
+    float f0, f1;
+    wq_dot2<NC2>(qs, r0, r1, d, lane, f0, f1);
+    s0 = fast_dot_fix(f0);
+    s1 = fast_dot_fix(f1);
 }
 
 }  // namespace mse

@@ -739,6 +739,55 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
     }
 }
 
+// ------------------------------------------------------------------ runtime de-duplication of the visit list + top-k
+//
+// query_disk_index.rs:99,486-529: a visited node is kept unless an EARLIER KEPT node has cosine (= dot product of the unit
+// fp16 rows, f32) above DUPLICATES_THRESHOLD = 0.95; the kept nodes are then sorted by score.  The reference forms the whole
+// n_visited x n_visited matrix with sgemm; only the entries against kept predecessors are ever read, so one warp per query
+// walks the list in visit order and scores row i against the kept rows two at a time (fast_dot summation order; sgemm's order
+// is unspecified, so decisions can differ only for cosines within an ulp of the threshold).
+template <int NC2>
+__global__ void __launch_bounds__(kWqWarps * 32) k_dedup_topk(const __half *__restrict__ x, uint32_t d, const uint32_t *__restrict__ vis_ids,
+                                                              const long long *__restrict__ vis_scores, const uint32_t *__restrict__ vis_len, uint32_t cap,
+                                                              uint32_t nq, float thr, uint32_t topk, uint32_t *top_ids, long long *top_scores,
+                                                              uint32_t *top_len, uint32_t *kept_count) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *base = smem_raw + (size_t)warp * (((size_t)d * 4 + (size_t)cap * 4 + 15) & ~(size_t)15);
+    float *row = (float *)base;                 // row i as f32
+    uint32_t *kept = (uint32_t *)(row + d);     // positions (visit order) of the kept nodes
+    for (uint32_t q = blockIdx.x * kWqWarps + warp; q < nq; q += gridDim.x * kWqWarps) {
+        const uint32_t m = min(vis_len[q], cap);
+        const uint32_t *ids = vis_ids + (size_t)q * cap;
+        const long long *scs = vis_scores + (size_t)q * cap;
+        uint32_t nk = 0;
+        for (uint32_t i = 0; i < m; i++) {
+            const __half *ri = x + (size_t)ids[i] * d;
+            for (uint32_t c = lane; c < d; c += 32) row[c] = __half2float(ri[c]);
+            __syncwarp();
+            bool dup = false;
+            for (uint32_t t = 0; t < nk && !dup; t += 2) {
+                const uint32_t j0 = kept[t], j1 = kept[t + 1 < nk ? t + 1 : t];
+                float f0, f1;
+                wq_dot2<NC2>(row, x + (size_t)ids[j0] * d, x + (size_t)ids[j1] * d, d, lane, f0, f1);
+                dup = f0 > thr || f1 > thr;
+            }
+            if (!dup) { if (lane == 0) kept[nk] = i; nk++; }
+            __syncwarp();
+        }
+        // kept nodes by (score desc, visit order asc): the stable sort of :529
+        for (uint32_t t = lane; t < nk; t += 32) {
+            const long long st = scs[kept[t]];
+            uint32_t rank = 0;
+            for (uint32_t u = 0; u < nk; u++) { const long long su = scs[kept[u]]; rank += (su > st) || (su == st && u < t); }
+            if (rank < topk) { top_ids[(size_t)q * topk + rank] = ids[kept[t]]; top_scores[(size_t)q * topk + rank] = st; }
+        }
+        for (uint32_t t = nk + lane; t < topk; t += 32) { top_ids[(size_t)q * topk + t] = kEmpty; top_scores[(size_t)q * topk + t] = 0; }
+        if (lane == 0) { top_len[q] = min(nk, topk); if (kept_count) kept_count[q] = nk; }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------ evaluator brute force (query_disk_index.rs:262-273)
 
 __global__ void __launch_bounds__(256) k_scores_i64(const __half *__restrict__ x, uint64_t n, uint32_t d, const __half *__restrict__ q,
@@ -1082,6 +1131,7 @@ MSE_API int mse_search_beam_dev(mse_index *ix, const uint16_t *d_q_f16, const fl
     MSE_CHECK(ix->gw_vis_ids.ensure((size_t)nq * cap * 4));
     MSE_CHECK(ix->gw_vis_sc.ensure((size_t)nq * cap * 8));
     MSE_CHECK(ix->gw_vis_len.ensure((size_t)nq * 4));
+    ix->gw_vis_cap = cap;
     GraphArgs g{ix->x, ix->adj, ix->deg, ix->graph_stride, ix->d, ix->n};
     BeamArgs ba{ix->pq_codes, M, C, ix->desc, ix->has_url, ix->n_desc, 0, d_qtm ? ix->code_scale : nullptr, nullptr, d_qtm, rabitq_output_dims,
                 d_qtm ? (float)(1.0 / sqrt((double)rabitq_n_dims)) : 0.f};
@@ -1114,6 +1164,31 @@ MSE_API int mse_search_beam_dev(mse_index *ix, const uint16_t *d_q_f16, const fl
     MSE_CHECK(ix->gw_htabs.ensure((size_t)grid * (hcap + vcap) * 4));
     k_beam_search<<<grid, kGsThreads, smem, (cudaStream_t)stream>>>(g, ba, (const __half *)d_q_f16, d_luts, ix->n_desc ? d_desc_scales : nullptr, nq,
                                                                     d_starts, start, L, W, ix->gw_htabs.as<uint32_t>(), hcap, vcap, o);
+    MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
+// De-duplicated top-k of the visit lists the last mse_search_beam_dev call on this handle left in HBM
+// (query_disk_index.rs:99,486-529: drop a visited node when an earlier kept one has cosine > threshold, then sort by score).
+// d_kept (optional) receives the number of nodes kept per query.  Asynchronous on `stream` (same stream as the search).
+MSE_API int mse_dedup_topk_dev(mse_index *ix, uint32_t nq, float threshold, uint32_t topk, uint32_t *d_top_ids, int64_t *d_top_scores,
+                               uint32_t *d_top_len, uint32_t *d_kept, void *stream) {
+    MSE_REQUIRE(ix != nullptr && d_top_ids && d_top_scores && d_top_len && topk >= 1, MSE_ERR_INVALID, "dedup_topk_dev: NULL buffer");
+    MSE_REQUIRE(ix->gw_vis_cap && ix->gw_vis_ids.p && (size_t)nq * 4 <= ix->gw_vis_len.cap, MSE_ERR_STATE,
+                "dedup_topk_dev: no visit lists (call mse_search_beam_dev with at least nq queries first)");
+    MSE_REQUIRE(ix->d % 64 == 0, MSE_ERR_UNSUPPORTED, "dedup_topk_dev: d %% 64 != 0");
+    if (nq == 0) return MSE_OK;
+    MSE_CHECK(use_device(ix->device));
+    const uint32_t cap = ix->gw_vis_cap;
+    const size_t per_warp = ((size_t)ix->d * 4 + (size_t)cap * 4 + 15) & ~(size_t)15;
+    const size_t smem = per_warp * kWqWarps;
+    MSE_REQUIRE(smem <= 200 * 1024, MSE_ERR_UNSUPPORTED, "dedup_topk_dev: visit lists of %u entries do not fit shared memory", cap);
+    const uint32_t grid = std::min<uint32_t>((nq + kWqWarps - 1) / kWqWarps, (uint32_t)sm_count(ix->device) * 8);
+    auto kern = ix->d == 1152 ? k_dedup_topk<18> : k_dedup_topk<0>;
+    MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kWqWarps * 32, smem, (cudaStream_t)stream>>>(ix->x, ix->d, ix->gw_vis_ids.as<uint32_t>(), ix->gw_vis_sc.as<long long>(),
+                                                             ix->gw_vis_len.as<uint32_t>(), cap, nq, threshold, topk, d_top_ids, (long long *)d_top_scores,
+                                                             d_top_len, d_kept);
     MSE_LAUNCH_OK();
     return MSE_OK;
 }

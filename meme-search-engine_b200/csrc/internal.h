@@ -50,7 +50,8 @@ struct mse_index {
     size_t prof_used = 0;
     uint64_t stats[8] = {0};
     mse::FlatWork fw;
-    mse::DevBuf gw_htabs, gw_status, gw_vis_ids, gw_vis_sc, gw_vis_len;  // graph search workspace of the device-pointer API (visited-set tables, per-query status)
+    mse::DevBuf gw_htabs, gw_status, gw_vis_ids, gw_vis_sc, gw_vis_len;
+    uint32_t gw_vis_cap = 0;          // entries per query of the visit lists the last mse_search_beam_dev call wrote  // graph search workspace of the device-pointer API (visited-set tables, per-query status)
     cudaStream_t stream = nullptr;  // handle-owned stream for the host-pointer API
     // tensor-map cache for the tensor path (encoded lazily, invalidated on growth)
     bool tmap_valid = false;

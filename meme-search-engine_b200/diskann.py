@@ -266,6 +266,16 @@ def beam_search_dev(vecs: VectorList, d_queries16: int, nq: int, L: int, beamwid
                                     topk, d_top_ids, d_top_scores, d_top_len, d_cmps, d_pq_cmps, stream or None), "mse_search_beam_dev")
 
 
+DUPLICATES_THRESHOLD = 0.95  # src/query_disk_index.rs:99
+
+
+def dedup_topk_dev(vecs: VectorList, nq: int, topk: int, d_top_ids: int, d_top_scores: int, d_top_len: int, d_kept: int = 0,
+                   threshold: float = DUPLICATES_THRESHOLD, stream: int = 0):
+    """query_disk_index.rs:486-529 over the visit lists of the last beam_search_dev call: drop near-duplicates, rank the rest."""
+    check(lib().mse_dedup_topk_dev(vecs._h, nq, threshold, topk, d_top_ids, d_top_scores, d_top_len, d_kept or None, stream or None),
+          "mse_dedup_topk_dev")
+
+
 class RabitQ:
     """diskann/rabitq.py:8-48 (codec from rabitq.msgpack: mean + truncated orthogonal transform)."""
 
