@@ -1080,3 +1080,18 @@ ORC_API size_t orc_beam_search_rabitq(const orc_disk_index *ix, uint32_t start, 
 ORC_API void orc_rabitq_direct_estimates(const float *qtm, float rq_scale, const uint8_t *codes, size_t n, const float *code_scale, float *out) {
     for (size_t i = 0; i < n; i++) out[i] = fmaf(rq_scale * rabitq_direct_sum(qtm, codes + i * 64), code_scale[i], qtm[512]);
 }
+
+/* ------------------------------------------------------------------ runtime de-duplication (src/query_disk_index.rs:99,486-529)
+ * keep[i] = 1 unless an earlier KEPT visited node has dot product (f32, fast_dot summation order; the reference uses sgemm, whose
+ * order is unspecified) above `threshold`.  ids: visited nodes in visit order.  Returns the number kept. */
+ORC_API size_t orc_dedup_visited(const uint16_t *x, size_t d, const uint32_t *ids, size_t m, float threshold, uint8_t *keep) {
+    size_t nk = 0;
+    for (size_t i = 0; i < m; i++) {
+        int dup = 0;
+        for (size_t j = 0; j < i && !dup; j++)
+            if (keep[j] && fast_dot_f32(x + (size_t)ids[i] * d, x + (size_t)ids[j] * d, d) > threshold) dup = 1;
+        keep[i] = (uint8_t)!dup;
+        nk += !dup;
+    }
+    return nk;
+}

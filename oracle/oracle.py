@@ -93,6 +93,7 @@ def _bind(l):
         "orc_pq_preprocess_query": (None, [vp, vp, vp]), "orc_pq_adc": (None, [vp, sz, sz, vp, sz, vp]),
         "orc_beam_search": (sz, [vp, u32, vp, vp, vp, sz, sz, C.c_int, C.c_int, vp, vp, sz, vp]),
         "orc_beam_search_scaled": (sz, [vp, u32, vp, vp, vp, C.c_float, vp, sz, sz, vp, vp, sz, vp]),
+        "orc_dedup_visited": (sz, [vp, sz, vp, sz, C.c_float, vp]),
         "orc_rabitq_direct_estimates": (None, [vp, C.c_float, vp, sz, vp, vp]),
         "orc_beam_search_rabitq": (sz, [vp, u32, vp, vp, C.c_float, vp, vp, sz, sz, vp, vp, sz, vp]),
     }
@@ -419,3 +420,11 @@ def rabitq_direct_estimates(qtm, rq_scale, codes, code_scale) -> np.ndarray:
     out = np.empty(codes.shape[0], np.float32)
     lib().orc_rabitq_direct_estimates(_p(qtm), C.c_float(rq_scale), _p(codes), codes.shape[0], _p(cs), _p(out))
     return out
+
+
+def dedup_visited(x, ids, threshold: float = 0.95) -> np.ndarray:
+    """src/query_disk_index.rs:486-527: boolean keep mask over the visited nodes (visit order)."""
+    x16, ids = as_u16(x), _c(ids, np.uint32)
+    keep = np.zeros(ids.size, np.uint8)
+    lib().orc_dedup_visited(_p(x16), x16.shape[1], _p(ids), ids.size, C.c_float(threshold), _p(keep))
+    return keep.astype(bool)

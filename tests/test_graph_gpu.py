@@ -493,3 +493,61 @@ def test_graph_search_edge_cases(mse, oracle, graph_mode):
             vi, vs = s.visited_list()
             assert np.array_equal(res.visited[i][0], vi) and np.array_equal(res.visited[i][1], vs)
     vl.close()
+
+
+def test_dedup_topk_dev(mse, oracle, graph_mode):
+    """Runtime de-duplication + top-k on the device (query_disk_index.rs:99,486-529) over the visit lists of a beam search, against
+    the oracle: an index with planted near-duplicates (cosine > 0.95), RabitQ traversal, keep mask and ranked results must match."""
+    import torch
+    from oracle.rabitq_np import RabitQ as NpRabitQ
+    n, R, L, W, k = 1200, 16, 32, 3, 12
+    rng = np.random.default_rng(8)
+    protos = clustered_f16(111, 300, n_clusters=6).astype(np.float32)
+    x = protos[rng.integers(0, 300, n)] + rng.standard_normal((n, 1152)).astype(np.float32) * 0.003   # ~4 near-copies of each prototype
+    x = (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float16)
+    g = oracle.IndexGraph(n, R)
+    oracle.random_fill_graph(g, R, seed=1)
+    med = oracle.medioid(x)
+    oracle.build_graph(g, med, x, oracle.make_config(r=R, l=48, maxc=200), seed=2)
+    vl = mse.diskann.VectorList.from_f16s(x)
+    vl.set_graph(g.adj.copy(), g.deg.copy())
+    ref = NpRabitQ.train(x[:600].astype(np.float32), output_dims=512, seed=4)
+    rq = mse.diskann.RabitQ(ref.mean, ref.p)
+    rq.encode_index(vl, 0)
+    codes, norms, dots = rq.quantize(x)
+    scale = (norms * dots).astype(np.float32)
+    q = clustered_f16(112, 40, n_clusters=6)
+    nq = q.shape[0]
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    dq16 = torch.from_numpy(q.view(np.int16)).to(dev)
+    dq32 = torch.from_numpy(q.astype(np.float32)).to(dev)
+    qtm = torch.empty((nq, 513), dtype=torch.float32, device=dev)
+    top_ids = torch.zeros((nq, k), dtype=torch.int32, device=dev)
+    top_sc = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+    top_len = torch.zeros(nq, dtype=torch.int32, device=dev)
+    kept = torch.zeros(nq, dtype=torch.int32, device=dev)
+    cm = torch.zeros(nq, dtype=torch.int64, device=dev)
+    pc = torch.zeros(nq, dtype=torch.int64, device=dev)
+    rq.query_dev(dq32.data_ptr(), nq, qtm.data_ptr(), stream)
+    mse.diskann.beam_search_dev(vl, dq16.data_ptr(), nq, L, W, med, k, top_ids.data_ptr(), top_sc.data_ptr(), top_len.data_ptr(), cm.data_ptr(),
+                                pc.data_ptr(), stream, d_qtm=qtm.data_ptr(), rabitq=rq)
+    mse.diskann.dedup_topk_dev(vl, nq, k, top_ids.data_ptr(), top_sc.data_ptr(), top_len.data_ptr(), kept.data_ptr(), stream=stream)
+    mse.diskann.greedy_search_check(vl, nq)
+    adj, off = g.to_csr()
+    qtm_h = qtm.cpu().numpy()
+    ti, ts, tl, kc = top_ids.cpu().numpy().view(np.uint32), top_sc.cpu().numpy(), top_len.cpu().numpy(), kept.cpu().numpy()
+    dropped = 0
+    for i in range(nq):
+        ids, sc, _ = oracle.beam_search(x, adj, off, codes, None, med, q[i], L, W, code_scale=scale, rabitq_qtm=qtm_h[i],
+                                        rabitq_scale=np.float32(1.0 / np.sqrt(1152.0)))
+        keep = oracle.dedup_visited(x, ids, 0.95)
+        dropped += int((~keep).sum())
+        kid, ksc = ids[keep], sc[keep]
+        o = np.argsort(-ksc, kind="stable")[:k]
+        m = int(tl[i])
+        assert int(kc[i]) == int(keep.sum()) and m == len(o), i
+        assert np.array_equal(ti[i, :m], kid[o]) and np.array_equal(ts[i, :m], ksc[o]), i
+        assert (ti[i, m:] == 0xFFFFFFFF).all()
+    assert dropped > nq                                            # the planted duplicates were actually met and dropped
+    vl.close()

@@ -343,3 +343,27 @@ def test_robust_stitch_vs_python_model(oracle):
                 added += 1
     for i in range(n):
         assert g.adj[i, : g.deg[i]].tolist() == lists[i], i
+
+
+def test_dedup_visited_model(oracle):
+    """orc_dedup_visited against the reference's formulation (query_disk_index.rs:486-527): full similarity matrix, then the
+    sequential retain with the `included` bit vector."""
+    rng = np.random.default_rng(5)
+    base = unit_rows(44, 12)
+    rows = []
+    for i in range(40):                                            # near-duplicates of 12 prototypes + a few unrelated rows
+        b = base[rng.integers(0, 12)]
+        v = b + rng.standard_normal(1152).astype(np.float32) * rng.choice([0.002, 0.02])
+        rows.append(v / np.linalg.norm(v))
+    x = np.stack(rows).astype(np.float16)
+    ids = rng.permutation(40).astype(np.uint32)
+    keep = oracle.dedup_visited(x, ids, 0.95)
+    v = x[ids].astype(np.float32)
+    sim = v @ v.T
+    included = np.zeros(40, bool)
+    for i in range(40):
+        if not (included & (sim[i] > 0.95)).any():
+            included[i] = True
+    near = np.abs(sim - 0.95) < 1e-4                               # decisions may differ only within rounding of the threshold
+    assert not near.any()
+    assert np.array_equal(keep, included) and 1 < keep.sum() < 40
