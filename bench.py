@@ -234,7 +234,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     steps, warmup = args.steps, max(args.warmup, 0)
     wl = [w for w in args.workloads.split(",") if w]
-    tower_cfg = {"workload": "siglip_image_tower_b256", "model": "ViT-SO400M-14-SigLIP-384 image tower (random init)", "batch_per_gpu": args.batch,
+    tower_cfg = {"workload": "siglip_image_tower_b256", "tower": "ViT-SO400M-14-SigLIP-384 image tower (random init)", "batch_per_gpu": args.batch,
                  "image": "384x384x3 u8", "storage": "fp16", "accumulate": "fp32", "parallelism": f"dp{world}",
                  "l2_policy": "inputs larger than L2 (per-layer activations 430 MB - 1.6 GB >> 126 MB)"}
     flat_cfg = {"workload": "flat_top100", "queries": args.queries, "k": args.k, "index_rows": args.rows, "dim": D, "index_dtype": "fp16",
