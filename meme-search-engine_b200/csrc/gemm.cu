@@ -4,6 +4,7 @@
 #include "internal.h"
 #include "gemm_sm100.cuh"
 #include "gemm_epilogues.cuh"
+#include "gemm_skinny.cuh"
 #include <algorithm>
 #include <stdlib.h>
 
@@ -53,10 +54,32 @@ static int launch_gemm(int device, const void *dA, const void *dB, uint32_t M, u
 
 static int force_bn = 0;  // profiling only (mse_debug_gemm)
 
+// small M (text tower at small batches): stream the weights once through every SM (gemm_skinny.cuh)
+static constexpr uint32_t kSkinnyMaxM = 512;
+template <int BN>
+static int launch_skinny(const __half *dA, const __half *dB, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb, const GemmOut &out,
+                         cudaStream_t st) {
+    auto kern = skinny::k_gemm_skinny<BN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skinny::smem_bytes<BN>()));
+        attr_done = true;
+    }
+    kern<<<dim3((N + BN - 1) / BN, (M + skinny::kBM - 1) / skinny::kBM), skinny::kThreads, skinny::smem_bytes<BN>(), st>>>(dA, dB, M, N, K, lda, ldb, out);
+    MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
 int gemm_f16_tn_dev(int device, const __half *dA, const __half *dB, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb,
                     const GemmOut &out, cudaStream_t st) {
     MSE_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, MSE_ERR_UNSUPPORTED, "gemm: K, lda, ldb must be multiples of 8");
     MSE_REQUIRE(M > 0 && N > 0 && K > 0, MSE_ERR_INVALID, "gemm: empty shape");
+    if (M <= kSkinnyMaxM && force_bn == 0 && ((uintptr_t)dA & 15) == 0 && ((uintptr_t)dB & 15) == 0 && getenv("MSE_GEMM_NO_SKINNY") == nullptr) {
+        GemmOut o = out;
+        o.res_in_place = 0;
+        // 16-column slices when N is small, so that at least ~70 SMs pull on the weights
+        return N <= 2048 ? launch_skinny<16>(dA, dB, M, N, K, lda, ldb, o, st) : launch_skinny<32>(dA, dB, M, N, K, lda, ldb, o, st);
+    }
     // fp16 output with 16-byte aligned rows: 256-wide tiles, staged through shared memory and written by TMA
     // (in-place residual -> TMA reduce-add).  Measured (tools/gemm_ablation.py): direct per-thread stores cost 25-50 %.
     if (out.c16 && !out.c32 && out.ldc % 8 == 0 && ((uintptr_t)out.c16 & 15) == 0 && !out.debug_no_store && force_bn != 128 && force_bn != 192 &&

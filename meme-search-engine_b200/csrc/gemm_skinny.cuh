@@ -1,0 +1,142 @@
+// Skinny GEMM for small batches:  C[M,N] = A[M,K] * B[N,K]^T  with M <= a few hundred rows (one text query is 64 tokens:
+// clip_server.py:98 at batch 1, BASELINE configs[0]).
+//
+// At M = 64 a linear layer is a pass over its weights: 7.96 MB (QKV), 9.9 MB (fc1 / fc2), 2.65 MB (out-proj) per block, 0.826 GB
+// per text tower -- HBM-bound (0.126 ms at the copy peak), 2 FLOP per weight byte per row.  The 128 x 256 tcgen05 tiles of
+// gemm_sm100.cuh give such a layer 5-17 tiles, i.e. 5-17 SMs pulling on HBM.  Here the N dimension is cut into 16- or 32-column
+// slices so that every SM streams its own slice of the weights exactly once (cp.async, 16-byte requests, 6 stages = ~80 KB in
+// flight per SM); the 64 x K activation panel is re-read by every CTA from L2.  Math: warp-level mma.sync m16n8k16
+// (fp16 x fp16 -> fp32) -- at 2 FLOP/B the tensor pipe idles either way; tcgen05 would add TMEM round trips for no gain.
+// Epilogue: GemmOut semantics of gemm_epilogues.cuh (bias, erf/tanh GELU, residual or position embedding, fp16 / fp32 stores).
+#pragma once
+#include "gemm_epilogues.cuh"
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace mse {
+namespace skinny {
+
+static constexpr int kBM = 64, kBK = 64, kThreads = 128, kStages = 6;
+static constexpr int kPitch = kBK + 8;   // halfs per shared-memory row (144 B): ldmatrix rows land in distinct banks
+
+template <int BN>
+constexpr uint32_t smem_bytes() { return (uint32_t)kStages * (kBM + BN) * kPitch * 2; }
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    const int n = valid ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void *smem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(s));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// grid (ceil(N / BN), ceil(M / 64)); warp w owns rows 16w .. 16w+15 of the CTA's 64 x BN tile
+template <int BN>
+__global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restrict__ A, const __half *__restrict__ B, uint32_t M, uint32_t N, uint32_t K,
+                                                          uint32_t lda, uint32_t ldb, GemmOut o) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __half *sA = (__half *)smem_raw;                                  // [stage][64][kPitch]
+    __half *sB = sA + (size_t)kStages * kBM * kPitch;                  // [stage][BN][kPitch]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t n0 = blockIdx.x * BN, m0 = blockIdx.y * kBM;
+    const uint32_t nk = (K + kBK - 1) / kBK;
+
+    auto load_stage = [&](uint32_t kt, int st) {
+        const uint32_t k0 = kt * kBK;
+        __half *a = sA + (size_t)st * kBM * kPitch;
+        __half *b = sB + (size_t)st * BN * kPitch;
+#pragma unroll
+        for (int i = 0; i < kBM * 8 / kThreads; i++) {                // 64 rows x 8 chunks of 16 B
+            const int c = tid + i * kThreads, r = c >> 3, kc = (c & 7) * 8;
+            const bool ok = m0 + r < M && k0 + kc < K;                // K % 8 == 0: a chunk is entirely inside or outside
+            cp_async16(a + r * kPitch + kc, A + (size_t)(ok ? m0 + r : 0) * lda + (ok ? k0 + kc : 0), ok);
+        }
+#pragma unroll
+        for (int i = 0; i < (BN * 8 + kThreads - 1) / kThreads; i++) {
+            const int c = tid + i * kThreads, r = c >> 3, kc = (c & 7) * 8;
+            if (c < BN * 8) {
+                const bool ok = n0 + r < N && k0 + kc < K;
+                cp_async16(b + r * kPitch + kc, B + (size_t)(ok ? n0 + r : 0) * ldb + (ok ? k0 + kc : 0), ok);
+            }
+        }
+    };
+
+    float acc[BN / 8][4];
+#pragma unroll
+    for (int j = 0; j < BN / 8; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < kStages - 1; s++) {
+        if ((uint32_t)s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (uint32_t kt = 0; kt < nk; kt++) {
+        cp_async_wait<kStages - 2>();
+        __syncthreads();                                              // stage kt has landed; stage kt-1 is free for the next load
+        const uint32_t nxt = kt + kStages - 1;
+        if (nxt < nk) load_stage(nxt, nxt % kStages);
+        cp_async_commit();
+        const __half *a = sA + (size_t)(kt % kStages) * kBM * kPitch + (warp * 16) * kPitch;
+        const __half *b = sB + (size_t)(kt % kStages) * BN * kPitch;
+#pragma unroll
+        for (int kk = 0; kk < kBK / 16; kk++) {
+            uint32_t af[4];
+            ldmatrix_x4(af, a + (lane & 15) * kPitch + kk * 16 + (lane >> 4) * 8);
+#pragma unroll
+            for (int j = 0; j < BN / 16; j++) {                        // two n8 tiles per ldmatrix.x4
+                uint32_t bf[4];
+                ldmatrix_x4(bf, b + (j * 16 + (lane & 7) + (lane >> 4) * 8) * kPitch + kk * 16 + ((lane >> 3) & 1) * 8);
+                mma_16816(acc[2 * j], af, bf[0], bf[1]);
+                mma_16816(acc[2 * j + 1], af, bf[2], bf[3]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: thread holds rows g and g + 8 (g = lane / 4), columns 2 (lane % 4) + {0, 1} of every n8 tile
+    const uint32_t g = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+    for (int j = 0; j < BN / 8; j++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t row = m0 + warp * 16 + g + h * 8, col = n0 + j * 8 + t2;
+            if (row >= M || col >= N) continue;
+            float v0 = acc[j][2 * h], v1 = acc[j][2 * h + 1];
+            const bool two = col + 1 < N;
+            if (o.bias) { v0 += o.bias[col]; if (two) v1 += o.bias[col + 1]; }
+            if (o.act == ACT_GELU_ERF) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
+            else if (o.act == ACT_GELU_TANH) { v0 = gelu_tanh(v0); v1 = gelu_tanh(v1); }
+            if (o.res) {
+                const uint32_t rr = o.res_mod ? row % o.res_mod : row;
+                const __half *rp = o.res + (size_t)rr * o.ldc + col;
+                v0 += __half2float(rp[0]);
+                if (two) v1 += __half2float(rp[1]);
+            }
+            if (o.debug_no_store) continue;
+            if (o.c16) {
+                __half *cp = o.c16 + (size_t)row * o.ldc + col;
+                if (two && ((o.ldc | col) & 1) == 0) *(__half2 *)cp = __floats2half2_rn(v0, v1);
+                else { cp[0] = __float2half_rn(v0); if (two) cp[1] = __float2half_rn(v1); }
+            }
+            if (o.c32) {
+                float *cp = o.c32 + (size_t)row * o.ldc + col;
+                cp[0] = v0;
+                if (two) cp[1] = v1;
+            }
+        }
+    }
+}
+
+}  // namespace skinny
+}  // namespace mse
