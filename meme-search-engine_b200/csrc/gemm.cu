@@ -55,7 +55,7 @@ static int launch_gemm(int device, const void *dA, const void *dB, uint32_t M, u
 static int force_bn = 0;  // profiling only (mse_debug_gemm)
 
 // small M (text tower at small batches): stream the weights once through every SM (gemm_skinny.cuh)
-static constexpr uint32_t kSkinnyMaxM = 512;
+static constexpr uint32_t kSkinnyMaxM = 128;   // measured (tools/text_latency.py): 2.80 -> 2.14 ms at 64 rows, 2.85 -> 2.25 ms at 128; slower than the tcgen05 tiles at 512
 template <int BN>
 static int launch_skinny(const __half *dA, const __half *dB, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb, const GemmOut &out,
                          cudaStream_t st) {
