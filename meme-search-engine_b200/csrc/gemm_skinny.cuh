@@ -16,7 +16,7 @@
 namespace mse {
 namespace skinny {
 
-static constexpr int kBM = 64, kBK = 64, kThreads = 128, kStages = 6;
+static constexpr int kBM = 64, kBK = 64, kThreads = 512, kStages = 6;   // 16 warps: 4 row groups x the 4 k16 steps of a 64-wide k tile
 static constexpr int kPitch = kBK + 8;   // halfs per shared-memory row (144 B): ldmatrix rows land in distinct banks
 
 template <int BN>
@@ -41,14 +41,17 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// grid (ceil(N / BN), ceil(M / 64)); warp w owns rows 16w .. 16w+15 of the CTA's 64 x BN tile
+// grid (ceil(N / BN), ceil(M / 64)).  Warp w = 4 * kq + wr: rows 16 wr .. 16 wr + 15 of the CTA's 64 x BN tile, k16 step kq of every
+// 64-wide k tile.  One CTA per SM means the only latency hiding is across the CTA's own warps: with 4 warps (one per scheduler)
+// the ldmatrix -> mma chains ran bare at ~650 ns per k tile (ncu: 12-17 us per layer); 16 warps give each scheduler four
+// independent chains.  The four partial sums of a row group are added in a fixed order through shared memory at the end.
 template <int BN>
 __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restrict__ A, const __half *__restrict__ B, uint32_t M, uint32_t N, uint32_t K,
                                                           uint32_t lda, uint32_t ldb, GemmOut o) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __half *sA = (__half *)smem_raw;                                  // [stage][64][kPitch]
     __half *sB = sA + (size_t)kStages * kBM * kPitch;                  // [stage][BN][kPitch]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = (tid >> 5) & 3, kq = tid >> 7, lane = tid & 31;
     const uint32_t n0 = blockIdx.x * BN, m0 = blockIdx.y * kBM;
     const uint32_t nk = (K + kBK - 1) / kBK;
 
@@ -56,19 +59,15 @@ __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restri
         const uint32_t k0 = kt * kBK;
         __half *a = sA + (size_t)st * kBM * kPitch;
         __half *b = sB + (size_t)st * BN * kPitch;
-#pragma unroll
-        for (int i = 0; i < kBM * 8 / kThreads; i++) {                // 64 rows x 8 chunks of 16 B
-            const int c = tid + i * kThreads, r = c >> 3, kc = (c & 7) * 8;
+        {                                                              // A: 64 rows x 8 chunks of 16 B = one chunk per thread
+            const int r = tid >> 3, kc = (tid & 7) * 8;
             const bool ok = m0 + r < M && k0 + kc < K;                // K % 8 == 0: a chunk is entirely inside or outside
             cp_async16(a + r * kPitch + kc, A + (size_t)(ok ? m0 + r : 0) * lda + (ok ? k0 + kc : 0), ok);
         }
-#pragma unroll
-        for (int i = 0; i < (BN * 8 + kThreads - 1) / kThreads; i++) {
-            const int c = tid + i * kThreads, r = c >> 3, kc = (c & 7) * 8;
-            if (c < BN * 8) {
-                const bool ok = n0 + r < N && k0 + kc < K;
-                cp_async16(b + r * kPitch + kc, B + (size_t)(ok ? n0 + r : 0) * ldb + (ok ? k0 + kc : 0), ok);
-            }
+        if (tid < BN * 8) {                                            // B: BN rows x 8 chunks
+            const int r = tid >> 3, kc = (tid & 7) * 8;
+            const bool ok = n0 + r < N && k0 + kc < K;
+            cp_async16(b + r * kPitch + kc, B + (size_t)(ok ? n0 + r : 0) * ldb + (ok ? k0 + kc : 0), ok);
         }
     };
 
@@ -89,8 +88,8 @@ __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restri
         cp_async_commit();
         const __half *a = sA + (size_t)(kt % kStages) * kBM * kPitch + (warp * 16) * kPitch;
         const __half *b = sB + (size_t)(kt % kStages) * BN * kPitch;
-#pragma unroll
-        for (int kk = 0; kk < kBK / 16; kk++) {
+        {
+            const int kk = kq;
             uint32_t af[4];
             ldmatrix_x4(af, a + (lane & 15) * kPitch + kk * 16 + (lane >> 4) * 8);
 #pragma unroll
@@ -103,6 +102,22 @@ __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restri
         }
     }
     cp_async_wait<0>();
+    __syncthreads();                                                  // the pipeline buffers are free: reuse them for the reduction
+    float *red = (float *)smem_raw;                                   // [3][4 warps][32 lanes][BN / 8 * 4]
+    if (kq > 0) {
+#pragma unroll
+        for (int j = 0; j < BN / 8; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) red[(((kq - 1) * 4 + warp) * 32 + lane) * (BN / 2) + j * 4 + e] = acc[j][e];
+    }
+    __syncthreads();
+    if (kq > 0) return;
+#pragma unroll
+    for (int q = 0; q < 3; q++)                                       // fixed order: k16 steps 0, 1, 2, 3
+#pragma unroll
+        for (int j = 0; j < BN / 8; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[j][e] += red[((q * 4 + warp) * 32 + lane) * (BN / 2) + j * 4 + e];
 
     // epilogue: thread holds rows g and g + 8 (g = lane / 4), columns 2 (lane % 4) + {0, 1} of every n8 tile
     const uint32_t g = lane >> 2, t2 = (lane & 3) * 2;
