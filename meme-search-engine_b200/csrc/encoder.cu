@@ -297,6 +297,9 @@ struct mse_encoder {
            *hh = nullptr, *z = nullptr, *outb = nullptr;
     uint8_t *img_dev = nullptr;
     int32_t *ids_dev = nullptr;
+    float *splitk_ws = nullptr;       // skinny GEMM scratch (gemm_skinny.cuh): partial tiles + arrival counters
+    uint32_t *splitk_cnt = nullptr;
+    static constexpr size_t kSplitkFloats = (size_t)2 << 20;
     cudaStream_t stream = nullptr;
     size_t max_tokens = 0;
     // profiling (bench.py roofline): CUDA-event brackets around GEMM (class 0) and attention (class 1) launches
@@ -427,6 +430,9 @@ int gemm(mse_encoder *e, const __half *A, const __half *W, uint32_t M, uint32_t 
     o.act = act;
     o.res = res;
     o.res_mod = res_mod;
+    o.splitk_ws = e->splitk_ws;
+    o.splitk_cnt = e->splitk_cnt;
+    o.splitk_ws_floats = mse_encoder::kSplitkFloats;
     return gemm_f16_tn_dev(e->device, A, W, M, N, K, K, K, o, st);
 }
 
@@ -631,6 +637,9 @@ MSE_API int mse_encoder_create(const char *weights_path, int device, int max_bat
         if ((rc = dev_alloc(e, (void **)&e->outb, Bm * D * 2))) break;
         if (has_v && (rc = dev_alloc(e, (void **)&e->img_dev, Bm * img * img * 3))) break;
         if (has_t && (rc = dev_alloc(e, (void **)&e->ids_dev, Bm * ctx * 4))) break;
+        if ((rc = dev_alloc(e, (void **)&e->splitk_ws, mse_encoder::kSplitkFloats * 4))) break;
+        if ((rc = dev_alloc(e, (void **)&e->splitk_cnt, 256 * 4))) break;
+        if (cudaMemset(e->splitk_cnt, 0, 256 * 4) != cudaSuccess) { set_error("encoder_create: cudaMemset failed"); rc = MSE_ERR_CUDA; break; }
     } while (0);
     if (rc != MSE_OK) return fail(rc);
     *out = e;

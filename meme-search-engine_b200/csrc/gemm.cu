@@ -56,8 +56,9 @@ static int force_bn = 0;  // profiling only (mse_debug_gemm)
 
 // small M (text tower at small batches): stream the weights once through every SM (gemm_skinny.cuh)
 static constexpr uint32_t kSkinnyMaxM = 128;   // measured (tools/text_latency.py): 2.80 -> 2.14 ms at 64 rows, 2.85 -> 2.25 ms at 128; slower than the tcgen05 tiles at 512
+static constexpr uint32_t kSkinnyMaxTiles = 256;   // arrival counters a caller provides (GemmOut::splitk_cnt)
 template <int BN>
-static int launch_skinny(const __half *dA, const __half *dB, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb, const GemmOut &out,
+static int launch_skinny(int out_device, const __half *dA, const __half *dB, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb, const GemmOut &out,
                          cudaStream_t st) {
     auto kern = skinny::k_gemm_skinny<BN>;
     static bool attr_done = false;
@@ -65,7 +66,13 @@ static int launch_skinny(const __half *dA, const __half *dB, uint32_t M, uint32_
         MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skinny::smem_bytes<BN>()));
         attr_done = true;
     }
-    kern<<<dim3((N + BN - 1) / BN, (M + skinny::kBM - 1) / skinny::kBM), skinny::kThreads, skinny::smem_bytes<BN>(), st>>>(dA, dB, M, N, K, lda, ldb, out);
+    const uint32_t slices = (N + BN - 1) / BN, mt = (M + skinny::kBM - 1) / skinny::kBM, nk = (K + skinny::kBK - 1) / skinny::kBK;
+    uint32_t splits = 1;
+    if (out.splitk_ws && out.splitk_cnt && slices * mt <= kSkinnyMaxTiles) {
+        splits = std::max<uint32_t>(1, std::min<uint32_t>(nk, (uint32_t)sm_count(out_device) / (slices * mt)));
+        while (splits > 1 && (size_t)splits * mt * skinny::kBM * slices * BN > out.splitk_ws_floats) splits--;
+    }
+    kern<<<dim3(slices, mt, splits), skinny::kThreads, skinny::smem_bytes<BN>(), st>>>(dA, dB, M, N, K, lda, ldb, out);
     MSE_LAUNCH_OK();
     return MSE_OK;
 }
@@ -77,8 +84,14 @@ int gemm_f16_tn_dev(int device, const __half *dA, const __half *dB, uint32_t M, 
     if (M <= kSkinnyMaxM && force_bn == 0 && ((uintptr_t)dA & 15) == 0 && ((uintptr_t)dB & 15) == 0 && getenv("MSE_GEMM_NO_SKINNY") == nullptr) {
         GemmOut o = out;
         o.res_in_place = 0;
-        // 16-column slices when N is small, so that at least ~70 SMs pull on the weights
-        return N <= 2048 ? launch_skinny<16>(dA, dB, M, N, K, lda, ldb, o, st) : launch_skinny<32>(dA, dB, M, N, K, lda, ldb, o, st);
+        if (o.splitk_ws && o.splitk_cnt && getenv("MSE_GEMM_NO_SPLITK") == nullptr) {
+            // wide slices + split over K: few readers of the activation panel, every SM busy (gemm_skinny.cuh)
+            return (N >= 2048 || K > 2048) ? launch_skinny<128>(device, dA, dB, M, N, K, lda, ldb, o, st)
+                                           : launch_skinny<64>(device, dA, dB, M, N, K, lda, ldb, o, st);
+        }
+        o.splitk_ws = nullptr;
+        // no scratch from the caller: 16-column slices when N is small, so that at least ~70 SMs pull on the weights
+        return N <= 2048 ? launch_skinny<16>(device, dA, dB, M, N, K, lda, ldb, o, st) : launch_skinny<32>(device, dA, dB, M, N, K, lda, ldb, o, st);
     }
     // fp16 output with 16-byte aligned rows: 256-wide tiles, staged through shared memory and written by TMA
     // (in-place residual -> TMA reduce-add).  Measured (tools/gemm_ablation.py): direct per-thread stores cost 25-50 %.

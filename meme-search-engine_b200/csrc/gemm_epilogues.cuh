@@ -18,6 +18,11 @@ struct GemmOut {
     int act;
     int debug_no_store;    // profiling only: run the epilogue math but skip the global stores
     int res_in_place;      // TMA-store path: residual == output buffer -> TMA reduce-add instead of a register add
+    // skinny split-K path (gemm_skinny.cuh): per-caller scratch for the partial sums and the tile arrival counters (zeroed once;
+    // the kernel leaves the counters at zero).  NULL: no split over K.
+    float *splitk_ws;      // [splits][rows rounded to 64][ldws] fp32
+    uint32_t *splitk_cnt;  // [n-slices x m-tiles]
+    size_t splitk_ws_floats;
 };
 
 // erf-GELU x * Phi(x) with Phi(x) - 1/2 = x * P(x^2): degree-13 Chebyshev fit on |x| <= 5.6 evaluated by Horner in fp32 (x is clamped;

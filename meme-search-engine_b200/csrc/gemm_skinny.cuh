@@ -41,22 +41,30 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// grid (ceil(N / BN), ceil(M / 64)).  Warp w = 4 * kq + wr: rows 16 wr .. 16 wr + 15 of the CTA's 64 x BN tile, k16 step kq of every
-// 64-wide k tile.  One CTA per SM means the only latency hiding is across the CTA's own warps: with 4 warps (one per scheduler)
-// the ldmatrix -> mma chains ran bare at ~650 ns per k tile (ncu: 12-17 us per layer); 16 warps give each scheduler four
-// independent chains.  The four partial sums of a row group are added in a fixed order through shared memory at the end.
+// grid (ceil(N / BN), ceil(M / 64), splits).  Warp w = 4 * kq + wr: rows 16 wr .. 16 wr + 15 of the CTA's 64 x BN tile, k16 step kq of
+// every 64-wide k tile; the four partial sums of a row group are added in a fixed order through shared memory at the end.
+//
+// Split over K (grid.z > 1): what limits these kernels is bytes moved per CTA over load latency, and with one N slice per CTA two
+// thirds of those bytes are the 64-row activation panel every CTA re-reads from L2 (ncu: profiles/r01p_skinny_gemm_ncu_full.md).
+// Wider slices (BN = 64 / 128) cut the number of panel readers, and the K range is split across CTAs to keep every SM busy: a CTA
+// then moves ~40-110 KB instead of 220-690 KB.  Partial tiles go to an fp32 scratch; the LAST CTA to arrive for a tile (atomic
+// counter) adds the partials in split order -- a fixed order, so results do not depend on which CTA came last -- and runs the
+// epilogue.
 template <int BN>
 __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restrict__ A, const __half *__restrict__ B, uint32_t M, uint32_t N, uint32_t K,
                                                           uint32_t lda, uint32_t ldb, GemmOut o) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ uint32_t s_last;
     __half *sA = (__half *)smem_raw;                                  // [stage][64][kPitch]
     __half *sB = sA + (size_t)kStages * kBM * kPitch;                  // [stage][BN][kPitch]
     const int tid = threadIdx.x, warp = (tid >> 5) & 3, kq = tid >> 7, lane = tid & 31;
     const uint32_t n0 = blockIdx.x * BN, m0 = blockIdx.y * kBM;
-    const uint32_t nk = (K + kBK - 1) / kBK;
+    const uint32_t nk_all = (K + kBK - 1) / kBK, splits = gridDim.z;
+    const uint32_t kt0 = (uint32_t)((uint64_t)nk_all * blockIdx.z / splits), kt1 = (uint32_t)((uint64_t)nk_all * (blockIdx.z + 1) / splits);
+    const uint32_t nk = kt1 - kt0;
 
     auto load_stage = [&](uint32_t kt, int st) {
-        const uint32_t k0 = kt * kBK;
+        const uint32_t k0 = (kt0 + kt) * kBK;
         __half *a = sA + (size_t)st * kBM * kPitch;
         __half *b = sB + (size_t)st * BN * kPitch;
         {                                                              // A: 64 rows x 8 chunks of 16 B = one chunk per thread
@@ -64,10 +72,13 @@ __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restri
             const bool ok = m0 + r < M && k0 + kc < K;                // K % 8 == 0: a chunk is entirely inside or outside
             cp_async16(a + r * kPitch + kc, A + (size_t)(ok ? m0 + r : 0) * lda + (ok ? k0 + kc : 0), ok);
         }
-        if (tid < BN * 8) {                                            // B: BN rows x 8 chunks
-            const int r = tid >> 3, kc = (tid & 7) * 8;
-            const bool ok = n0 + r < N && k0 + kc < K;
-            cp_async16(b + r * kPitch + kc, B + (size_t)(ok ? n0 + r : 0) * ldb + (ok ? k0 + kc : 0), ok);
+#pragma unroll
+        for (int i = 0; i < (BN * 8 + kThreads - 1) / kThreads; i++) {  // B: BN rows x 8 chunks
+            const int c = tid + i * kThreads, r = c >> 3, kc = (c & 7) * 8;
+            if (c < BN * 8) {
+                const bool ok = n0 + r < N && k0 + kc < K;
+                cp_async16(b + r * kPitch + kc, B + (size_t)(ok ? n0 + r : 0) * ldb + (ok ? k0 + kc : 0), ok);
+            }
         }
     };
 
@@ -88,22 +99,19 @@ __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restri
         cp_async_commit();
         const __half *a = sA + (size_t)(kt % kStages) * kBM * kPitch + (warp * 16) * kPitch;
         const __half *b = sB + (size_t)(kt % kStages) * BN * kPitch;
-        {
-            const int kk = kq;
-            uint32_t af[4];
-            ldmatrix_x4(af, a + (lane & 15) * kPitch + kk * 16 + (lane >> 4) * 8);
+        uint32_t af[4];
+        ldmatrix_x4(af, a + (lane & 15) * kPitch + kq * 16 + (lane >> 4) * 8);
 #pragma unroll
-            for (int j = 0; j < BN / 16; j++) {                        // two n8 tiles per ldmatrix.x4
-                uint32_t bf[4];
-                ldmatrix_x4(bf, b + (j * 16 + (lane & 7) + (lane >> 4) * 8) * kPitch + kk * 16 + ((lane >> 3) & 1) * 8);
-                mma_16816(acc[2 * j], af, bf[0], bf[1]);
-                mma_16816(acc[2 * j + 1], af, bf[2], bf[3]);
-            }
+        for (int j = 0; j < BN / 16; j++) {                            // two n8 tiles per ldmatrix.x4
+            uint32_t bf[4];
+            ldmatrix_x4(bf, b + (j * 16 + (lane & 7) + (lane >> 4) * 8) * kPitch + kq * 16 + ((lane >> 3) & 1) * 8);
+            mma_16816(acc[2 * j], af, bf[0], bf[1]);
+            mma_16816(acc[2 * j + 1], af, bf[2], bf[3]);
         }
     }
     cp_async_wait<0>();
     __syncthreads();                                                  // the pipeline buffers are free: reuse them for the reduction
-    float *red = (float *)smem_raw;                                   // [3][4 warps][32 lanes][BN / 8 * 4]
+    float *red = (float *)smem_raw;                                   // [3][4 warps][32 lanes][BN / 2]
     if (kq > 0) {
 #pragma unroll
         for (int j = 0; j < BN / 8; j++)
@@ -111,16 +119,50 @@ __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restri
             for (int e = 0; e < 4; e++) red[(((kq - 1) * 4 + warp) * 32 + lane) * (BN / 2) + j * 4 + e] = acc[j][e];
     }
     __syncthreads();
-    if (kq > 0) return;
+    if (kq == 0) {
 #pragma unroll
-    for (int q = 0; q < 3; q++)                                       // fixed order: k16 steps 0, 1, 2, 3
+        for (int q = 0; q < 3; q++)                                   // fixed order: k16 steps 0, 1, 2, 3
 #pragma unroll
-        for (int j = 0; j < BN / 8; j++)
+            for (int j = 0; j < BN / 8; j++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) acc[j][e] += red[((q * 4 + warp) * 32 + lane) * (BN / 2) + j * 4 + e];
-
-    // epilogue: thread holds rows g and g + 8 (g = lane / 4), columns 2 (lane % 4) + {0, 1} of every n8 tile
+                for (int e = 0; e < 4; e++) acc[j][e] += red[((q * 4 + warp) * 32 + lane) * (BN / 2) + j * 4 + e];
+    }
+    // thread (kq == 0) holds rows g and g + 8 (g = lane / 4), columns 2 (lane % 4) + {0, 1} of every n8 tile
     const uint32_t g = lane >> 2, t2 = (lane & 3) * 2;
+    if (splits > 1) {
+        const uint32_t ldws = gridDim.x * BN, rows_ws = gridDim.y * kBM;
+        if (kq == 0) {
+            float *w = o.splitk_ws + ((size_t)blockIdx.z * rows_ws + m0 + warp * 16 + g) * ldws + n0 + t2;
+#pragma unroll
+            for (int j = 0; j < BN / 8; j++) {
+                *(float2 *)(w + j * 8) = make_float2(acc[j][0], acc[j][1]);
+                *(float2 *)(w + (size_t)8 * ldws + j * 8) = make_float2(acc[j][2], acc[j][3]);
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t prev = atomicAdd(&o.splitk_cnt[blockIdx.y * gridDim.x + blockIdx.x], 1u);
+            s_last = prev == splits - 1;
+            if (prev == splits - 1) o.splitk_cnt[blockIdx.y * gridDim.x + blockIdx.x] = 0;   // ready for the next launch
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        if (kq == 0) {
+#pragma unroll
+            for (int j = 0; j < BN / 8; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+            for (uint32_t p = 0; p < splits; p++) {                   // split order, whoever arrived last
+                const float *w = o.splitk_ws + ((size_t)p * rows_ws + m0 + warp * 16 + g) * ldws + n0 + t2;
+#pragma unroll
+                for (int j = 0; j < BN / 8; j++) {
+                    const float2 u0 = __ldcg((const float2 *)(w + j * 8)), u1 = __ldcg((const float2 *)(w + (size_t)8 * ldws + j * 8));
+                    acc[j][0] += u0.x; acc[j][1] += u0.y; acc[j][2] += u1.x; acc[j][3] += u1.y;
+                }
+            }
+        }
+    }
+    if (kq != 0) return;
 #pragma unroll
     for (int j = 0; j < BN / 8; j++) {
 #pragma unroll
