@@ -111,12 +111,12 @@ __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restri
     }
     cp_async_wait<0>();
     __syncthreads();                                                  // the pipeline buffers are free: reuse them for the reduction
-    float *red = (float *)smem_raw;                                   // [3][4 warps][32 lanes][BN / 2]
+    float *red = (float *)smem_raw;                                   // [3][4 warps][BN / 2][32 lanes]
     if (kq > 0) {
 #pragma unroll
         for (int j = 0; j < BN / 8; j++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) red[(((kq - 1) * 4 + warp) * 32 + lane) * (BN / 2) + j * 4 + e] = acc[j][e];
+            for (int e = 0; e < 4; e++) red[(((kq - 1) * 4 + warp) * (BN / 2) + j * 4 + e) * 32 + lane] = acc[j][e];   // lane fastest: conflict-free
     }
     __syncthreads();
     if (kq == 0) {
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restri
 #pragma unroll
             for (int j = 0; j < BN / 8; j++)
 #pragma unroll
-                for (int e = 0; e < 4; e++) acc[j][e] += red[((q * 4 + warp) * 32 + lane) * (BN / 2) + j * 4 + e];
+                for (int e = 0; e < 4; e++) acc[j][e] += red[((q * 4 + warp) * (BN / 2) + j * 4 + e) * 32 + lane];
     }
     // thread (kq == 0) holds rows g and g + 8 (g = lane / 4), columns 2 (lane % 4) + {0, 1} of every n8 tile
     const uint32_t g = lane >> 2, t2 = (lane & 3) * 2;
