@@ -84,8 +84,10 @@ int gemm_f16_tn_dev(int device, const __half *dA, const __half *dB, uint32_t M, 
     if (M <= kSkinnyMaxM && force_bn == 0 && ((uintptr_t)dA & 15) == 0 && ((uintptr_t)dB & 15) == 0 && getenv("MSE_GEMM_NO_SKINNY") == nullptr) {
         GemmOut o = out;
         o.res_in_place = 0;
-        if (o.splitk_ws && o.splitk_cnt && getenv("MSE_GEMM_NO_SPLITK") == nullptr) {
-            // wide slices + split over K: few readers of the activation panel, every SM busy (gemm_skinny.cuh)
+        // Wide slices + split over K (few readers of the activation panel, every SM busy) -- measured SLOWER than one narrow slice per
+        // CTA (text tower at batch 1: 4.0 ms vs 2.12 ms, profiles/r01p_skinny_gemm_ncu_full.md): the last CTA of a tile serialises the
+        // fixed-order reduction of up to 16 partial tiles behind a device-wide fence.  Kept for experiments only.
+        if (o.splitk_ws && o.splitk_cnt && getenv("MSE_GEMM_SPLITK") != nullptr) {
             return (N >= 2048 || K > 2048) ? launch_skinny<128>(device, dA, dB, M, N, K, lda, ldb, o, st)
                                            : launch_skinny<64>(device, dA, dB, M, N, K, lda, ldb, o, st);
         }
