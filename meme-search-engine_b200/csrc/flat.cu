@@ -465,7 +465,10 @@ static int flat_search_device(mse_index *ix, const float *d_q, uint32_t nq, uint
     if (nq == 0) return MSE_OK;
     FlatWork &w = ix->fw;
 
-    bool tensor = ix->flat_mode == 2 || (ix->flat_mode == 0 && nq > 2);
+    // 1-2 queries over a small index: the exact fp64 scan has the lower latency.  Over a large index the scan is bound by its fp64 /
+    // conversion instruction stream (5.9 ms for one query over 23 GB, 0.60 of the HBM copy rate; tools/flat_latency.py) while the
+    // tensor pass runs at the HBM rate (3.6 ms, 0.97), so any batch takes the tensor pass there.
+    bool tensor = ix->flat_mode == 2 || (ix->flat_mode == 0 && (nq > 2 || ix->n >= (1u << 18)));
     if (tensor && !flat_tc_supported(ix)) {
         MSE_REQUIRE(ix->flat_mode != 2, MSE_ERR_UNSUPPORTED, "search_flat: tensor path needs d %% 64 == 0 (d=%u)", ix->d);
         tensor = false;
