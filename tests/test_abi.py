@@ -56,3 +56,21 @@ def test_argument_validation_without_device(mse):
     assert l.mse_search_flat(None, None, 1, 1, None, None) == -1
     assert b"NULL" in l.mse_last_error()
     assert l.mse_index_ntotal(None) == 0
+
+
+def test_graph_entries_validate_arguments_without_device(mse):
+    """Every graph / codec entry added behind the diskann boundary rejects NULL handles and buffers before touching a device
+    (error code -1 = MSE_ERR_INVALID, message through mse_last_error) -- no crash, no silent success."""
+    l = mse.lib()
+    assert l.mse_search_graph_dev(None, None, 1, 8, None, 0, 0, 0, None, None, None, None, None) == -1
+    assert l.mse_search_graph_check(None, 1) == -1
+    assert l.mse_search_graph_set_mode(7) == -1 and b"mode" in l.mse_last_error()
+    assert l.mse_search_graph_set_mode(0) == 0
+    assert l.mse_search_beam_dev(None, None, None, None, 0, 0, None, 1, 8, 1, None, 0, 256, 10, None, None, None, None, None, None) == -1
+    assert l.mse_search_beam_scaled(None, None, None, None, None, 1, 8, 1, None, 0, 256, None, None, None, 1, None, None) == -1
+    assert l.mse_dedup_topk_dev(None, 1, 0.95, 10, None, None, None, None, None) == -1
+    assert l.mse_index_set_code_scales(None, None) == -1
+    assert l.mse_index_encode_rabitq(None, None, 0) == -1
+    assert l.mse_index_robust_stitch(None, None, None, 0) == -1
+    assert l.mse_rabitq_preprocess_query(None, None, 1, None, None) == -1
+    assert l.mse_rabitq_query_dev(None, None, 1, None, None) == -1
