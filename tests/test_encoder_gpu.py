@@ -96,3 +96,21 @@ def test_full_depth_image_tower(tmp_path_factory, mse):
     ref = T.encode_image(v, imgs)
     out = enc.encode_image(imgs)
     assert _cos(out, ref).min() >= 1 - TOL, float(_cos(out, ref).min())
+
+
+def test_full_depth_text_tower(tmp_path_factory, mse):
+    """All 27 blocks of the text tower at SO400M size, batch 1 and 3 (64 and 192 rows: the skinny GEMM path with K = 1152 and
+    K = 4304, and the tcgen05 path) against the fp32 oracle."""
+    from oracle import towers as T
+    t = T.build_text(depth=27, seed=43)
+    sd = T.export_openclip(text=t)
+    path = str(tmp_path_factory.mktemp("t27") / "text27.msew")
+    mse.weights.save_weights(path, sd, mse.weights.config_for(sd))
+    enc = mse.Encoder(path, max_batch=3)
+    ids = T.synthetic_token_ids(9, 3)
+    ref = T.encode_text(t, ids)
+    out3 = enc.encode_text(ids)
+    out1 = enc.encode_text(ids[:1])
+    assert _cos(out3, ref).min() >= 1 - TOL, float(_cos(out3, ref).min())
+    assert _cos(out1, ref[:1]).min() >= 1 - TOL, float(_cos(out1, ref[:1]).min())
+    assert np.array_equal(out1, enc.encode_text(ids[:1]))          # deterministic
