@@ -54,6 +54,16 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
     } while (0)
 
 int use_device(int device);   // cudaSetDevice + verifies compute capability 10.x
+
+// cudaFuncSetAttribute applies to the current device only: a call site remembers which devices it has configured
+// (handles are independent across devices, so one process may drive several)
+struct PerDeviceOnce {
+    std::atomic<uint64_t> mask{0};
+    bool first(int device) {
+        const uint64_t bit = 1ull << (device & 63);
+        return !(mask.fetch_or(bit, std::memory_order_relaxed) & bit);
+    }
+};
 int sm_count(int device);
 
 // growable device buffer owned by a handle

@@ -447,22 +447,16 @@ int layernorm(const __half *x, __half *y, const float *g, const float *b, uint32
 int run_blocks(mse_encoder *e, const TowerW &tw, int depth, uint32_t B, uint32_t S, cudaStream_t st) {
     const uint32_t D = e->cfg[2], F = e->cfg[5], H = e->cfg[4], T = B * S;
     const int act = e->cfg[8];
-    static bool attr_done = false;
-    if (!attr_done) {
-        MSE_CUDA(cudaFuncSetAttribute(attn::k_mha_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::Smem)));
-        attr_done = true;
-    }
+    static PerDeviceOnce attr_once;
+    if (attr_once.first(e->device)) MSE_CUDA(cudaFuncSetAttribute(attn::k_mha_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::Smem)));
     const float scale_log2e = (1.0f / sqrtf((float)attn::kDH)) * 1.4426950408889634f;
     // S >= 128: tcgen05 kernel (attention_tc.cuh); the 64-token text tower keeps the warp-level kernel (a 128-row tile would be half empty)
     const bool use_tc = S >= 128 && getenv("MSE_ATTN_MMA_SYNC") == nullptr;
     CUtensorMap tm64, tm16;
     attn_tc::Params ap{};
     if (use_tc) {
-        static bool tc_attr_done = false;
-        if (!tc_attr_done) {
-            MSE_CUDA(cudaFuncSetAttribute(attn_tc::k_mha_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc::kSmemBytes));
-            tc_attr_done = true;
-        }
+        static PerDeviceOnce tc_once;
+        if (tc_once.first(e->device)) MSE_CUDA(cudaFuncSetAttribute(attn_tc::k_mha_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc::kSmemBytes));
         MSE_CHECK(encode_tmap_3d(&tm64, e->qkv, attn::kDH, 3 * H, (uint64_t)T, attn::kDH * 2, (uint64_t)3 * D * 2, 64, attn_tc::kBM, 128));
         MSE_CHECK(encode_tmap_3d(&tm16, e->qkv, attn::kDH, 3 * H, (uint64_t)T, attn::kDH * 2, (uint64_t)3 * D * 2, 16, attn_tc::kBM, 32));
         ap.S = (int)S; ap.H = (int)H; ap.B = (int)B;

@@ -347,13 +347,12 @@ __global__ void __launch_bounds__(256) k_merge_topk(const uint32_t *__restrict__
 
 // ================================================================== host side
 
-static int ensure_select_smem() {
-    static bool done = false;
-    if (done) return MSE_OK;
+static int ensure_select_smem(int device) {
+    static PerDeviceOnce once;
+    if (!once.first(device)) return MSE_OK;
     MSE_CUDA(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortMax * 8)));
     MSE_CUDA(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortMax * 8)));
     MSE_CUDA(cudaFuncSetAttribute(k_merge_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortMax * 8)));
-    done = true;
     return MSE_OK;
 }
 
@@ -456,7 +455,7 @@ static int read_flags(mse_index *ix, cudaStream_t st, uint32_t out[4]) {
 static int flat_search_device(mse_index *ix, const float *d_q, uint32_t nq, uint32_t k, uint32_t *d_ids, float *d_scores,
                               cudaStream_t st) {
     MSE_CHECK(use_device(ix->device));
-    MSE_CHECK(ensure_select_smem());
+    MSE_CHECK(ensure_select_smem(ix->device));
     MSE_REQUIRE(k >= 1, MSE_ERR_INVALID, "search_flat: k must be >= 1");
     MSE_REQUIRE(ix->d % 8 == 0 && ix->d <= 2048, MSE_ERR_UNSUPPORTED, "search_flat: d=%u unsupported", ix->d);
     memset(ix->stats, 0, sizeof(ix->stats));
@@ -768,7 +767,7 @@ MSE_API int mse_search_flat_set_mode(mse_index *ix, int mode) {
 MSE_API int mse_merge_topk_dev(int device, const uint32_t *d_ids, const float *d_scores, uint32_t n_shards, uint32_t nq,
                                uint32_t k, uint32_t *d_out_ids, float *d_out_scores, void *stream) {
     MSE_CHECK(use_device(device));
-    MSE_CHECK(ensure_select_smem());
+    MSE_CHECK(ensure_select_smem(device));
     MSE_REQUIRE(k >= 1 && n_shards >= 1, MSE_ERR_INVALID, "merge_topk: bad shape");
     MSE_REQUIRE((uint64_t)n_shards * k <= kSortMax, MSE_ERR_UNSUPPORTED, "merge_topk: n_shards*k=%llu exceeds %u",
                 (unsigned long long)n_shards * k, kSortMax);

@@ -55,12 +55,9 @@ int flat_tc_supported(const mse_index *ix) { return ix->d % 8 == 0 && ix->d >= 6
 
 int flat_tc_score_chunk(mse_index *ix, uint32_t nq, uint64_t row0, uint64_t nrows, uint32_t cap, cudaStream_t st) {
     using Cfg = GemmCfg<kFlatBN>;
-    static bool attr_done = false;
+    static PerDeviceOnce once;
     auto kern = k_gemm_tn<kFlatBN, 0, FlatEpilogue>;
-    if (!attr_done) {
-        MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
-        attr_done = true;
-    }
+    if (once.first(ix->device)) MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     FlatWork &w = ix->fw;
     const uint32_t nq_pad = (nq + 127) / 128 * 128;
     if (!ix->tmap_valid) {

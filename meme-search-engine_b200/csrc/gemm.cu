@@ -15,11 +15,8 @@ static int launch_gemm(int device, const void *dA, const void *dB, uint32_t M, u
                        Epi epi, cudaStream_t st) {
     constexpr uint32_t kSmem = gemm_smem_bytes<BN, Epi, CG>();
     auto kern = k_gemm_tn<BN, 0, Epi, CG>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-        attr_done = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first(device)) MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     CUtensorMap tmA, tmB, tmC;
     MSE_CHECK(encode_tmap_2d(&tmA, dA, M, K, lda, kGemmBM));
     MSE_CHECK(encode_tmap_2d(&tmB, dB, N, K, ldb, BN / CG));
@@ -61,11 +58,8 @@ template <int BN>
 static int launch_skinny(int out_device, const __half *dA, const __half *dB, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb, const GemmOut &out,
                          cudaStream_t st) {
     auto kern = skinny::k_gemm_skinny<BN>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skinny::smem_bytes<BN>()));
-        attr_done = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first(out_device)) MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skinny::smem_bytes<BN>()));
     const uint32_t slices = (N + BN - 1) / BN, mt = (M + skinny::kBM - 1) / skinny::kBM, nk = (K + skinny::kBK - 1) / skinny::kBK;
     uint32_t splits = 1;
     if (out.splitk_ws && out.splitk_cnt && slices * mt <= kSkinnyMaxTiles) {
