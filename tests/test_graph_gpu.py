@@ -551,3 +551,34 @@ def test_dedup_topk_dev(mse, oracle, graph_mode):
         assert (ti[i, m:] == 0xFFFFFFFF).all()
     assert dropped > nq                                            # the planted duplicates were actually met and dropped
     vl.close()
+
+
+def test_load_packed_index_files(mse, oracle, world, tmp_path):
+    """index.msgpack + index.pq-codes.bin + index.descriptor-codes.bin as the serving side loads them (query_disk_index.rs:664-705):
+    the codec rebuilt from the header and the attached codes must drive the same beam search as the in-memory objects."""
+    from mse_b200 import index_io
+    w = world
+    x, vl = w["x"], w["vl"]
+    po, pg, cent, T = _pq_setup(oracle, mse, x)
+    codes = po.quantize_batch(x.astype(np.float32))
+    rng = np.random.default_rng(13)
+    desc = rng.integers(0, 256, (w["n"], 4)).astype(np.uint8)
+    hdr = index_io.IndexHeader([(x[:50].astype(np.float32).mean(axis=0), w["med"])], w["n"], 0, 4096,
+                               {"centroids": cent.reshape(-1), "transform": T.reshape(-1), "n_dims_per_code": 18, "n_dims": 1152},
+                               [np.linspace(0, 1, 8).astype(np.float32)] * 4)
+    index_io.write_index_header(str(tmp_path / "index.msgpack"), hdr)
+    codes.tofile(str(tmp_path / "index.pq-codes.bin"))
+    desc.tofile(str(tmp_path / "index.descriptor-codes.bin"))
+    h2, pq2 = index_io.load_packed_index(str(tmp_path), vl)
+    assert h2.pq_code_size == 64 and h2.n_descriptors == 4 and h2.shards[0][1] == w["med"]
+    q = clustered_f16(67, 6, n_clusters=24)
+    luts = pq2.preprocess_query(q.astype(np.float32))
+    scales = (rng.standard_normal((6, 4)) / 512).astype(np.float32)
+    res, cmps, pqc = mse.diskann.beam_search(vl, q, luts, w["med"], 40, 3, desc_scales=scales)
+    adj, off = w["g"].to_csr()
+    for i in range(6):
+        lo = po.preprocess_query(q[i].astype(np.float32))
+        assert np.array_equal(luts[i], lo)
+        ids, sc, (c, pc) = oracle.beam_search(x, adj, off, codes, lo, w["med"], q[i], 40, 3, descriptors=desc, desc_scales=scales[i])
+        assert np.array_equal(res[i][0], ids) and np.array_equal(res[i][1], sc) and int(cmps[i]) == c and int(pqc[i]) == pc
+    vl.set_descriptors(None, None)
