@@ -12,7 +12,8 @@
  *   - one in-flight call per handle (the reference has one inference thread / one &mut Scratch per thread);
  *     handles on different devices are independent
  *   - fixed-point scores are i64 = trunc(f32 * 2^32) exactly as diskann/src/vector.rs:46,249-250,408-416
- *   - "_dev" variants take device pointers and a cudaStream_t (as void*) and do not synchronise
+ *   - "_dev" variants take device pointers and a cudaStream_t (as void*); they return with the work queued on that stream.
+ *     Exceptions are stated per entry (mse_search_flat_dev reads one status word back before returning; *_check synchronise)
  *   - there is NO CPU fallback: every compute entry fails with MSE_ERR_CUDA when no sm_100 device is usable
  */
 #ifndef MSE_B200_H
@@ -144,7 +145,11 @@ int mse_search_graph_check(mse_index *ix, uint32_t nq);
 int mse_search_graph_set_mode(int mode);
 /* greedy_search of query_disk_index.rs:144-212 (beam W, PQ ADC for candidates, exact score + descriptor bias for expanded
  * nodes).  luts [nq][M*n_centroids] from mse_pq_preprocess_query; desc_scales [nq][n_desc] or NULL.  out_* [nq][out_cap]:
- * expanded nodes in visit order with their exact scores (the caller sorts, :529); cmps / pq_cmps as :148-149. */
+ * expanded nodes in visit order with their exact scores (the caller sorts, :529); cmps as :148.  pq_cmps counts every candidate
+ * once; the reference clears its pre-buffer per beam iteration (:157), not per expanded node, and so re-scores (and counts, :149)
+ * the earlier nodes' candidates again when W > 1 -- same results, larger counter.  A query that expands more than out_cap nodes
+ * fails the call (MSE_ERR_UNSUPPORTED) instead of returning a truncated list.  start / starts[] are LOCAL row numbers of this
+ * shard (IndexHeader.shards[i].medioid is global: subtract the shard's id_base); out-of-range values are MSE_ERR_INVALID. */
 int mse_search_beam(mse_index *ix, const uint16_t *q_f16, const float *luts, const float *desc_scales, uint32_t nq, uint32_t L,
                     uint32_t W, const uint32_t *starts, uint32_t start, int disable_pq, uint32_t n_centroids, uint32_t *out_ids,
                     int64_t *out_scores, uint32_t *out_len, uint32_t out_cap, uint64_t *cmps, uint64_t *pq_cmps);
@@ -184,7 +189,9 @@ int mse_index_medioid(mse_index *ix, uint32_t *out);
  * query_order: the query node ids in the order of the reference's shuffled loop (:333-334), or NULL for a seeded shuffle. */
 int mse_index_robust_stitch(mse_index *ix, const mse_build_config *cfg, const uint32_t *query_order, uint64_t seed);
 /* build_graph (lib.rs:287-324), batch-synchronous (see csrc/build.cu).  max_batch 0 = default.
- * stats (optional, 4 values): batches, point searches, back-edge merges, distance evaluations of the searches */
+ * stats (optional, 6 values): batches, point searches, back-edge merges, distance evaluations of the searches, searches whose
+ * visited_list (lib.rs:205, unbounded there) was cut at max(8192, 48 l) entries, searches stopped by a visited-set overflow
+ * (any of those fails the build with MSE_ERR_UNSUPPORTED) */
 int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_build_config *cfg, uint64_t seed, uint32_t max_batch,
                            uint64_t *stats);
 

@@ -454,7 +454,7 @@ static PruneCfg to_prune_cfg(const mse_build_config &c) {
 }
 
 static int ensure_graph_storage(mse_index *ix, uint32_t stride) {
-    if (ix->adj && ix->graph_stride == stride) return MSE_OK;
+    if (ix->adj && ix->graph_stride == stride && ix->side_n == ix->n) return MSE_OK;
     if (ix->adj) cudaFree(ix->adj);
     if (ix->deg) cudaFree(ix->deg);
     ix->adj = nullptr; ix->deg = nullptr;
@@ -463,6 +463,7 @@ static int ensure_graph_storage(mse_index *ix, uint32_t stride) {
     MSE_CUDA(cudaMemset(ix->adj, 0, std::max<size_t>(ix->n * stride * 4, 16)));
     MSE_CUDA(cudaMemset(ix->deg, 0, std::max<size_t>(ix->n * 4, 16)));
     ix->graph_stride = stride;
+    ix->side_n = ix->n;
     return MSE_OK;
 }
 
@@ -550,7 +551,8 @@ MSE_API int mse_index_medioid(mse_index *ix, uint32_t *out) {
 }
 
 // build_graph (lib.rs:287-324), batch-synchronous.  The graph must hold a starting graph (mse_index_random_fill_graph or
-// mse_index_set_graph); stats (optional, 4 values): batches, searches, back-edge merges, total distance evaluations.
+// mse_index_set_graph); stats (optional, 6 values): batches, searches, back-edge merges, total distance evaluations,
+// searches whose visited list was cut at its capacity, searches aborted on a visited-set overflow (the build then fails).
 MSE_API int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_build_config *cfg, uint64_t seed, uint32_t max_batch, uint64_t *stats) {
     MSE_REQUIRE(ix != nullptr, MSE_ERR_INVALID, "build_vamana: NULL handle");
     MSE_CHECK(check_cfg(cfg, "build_vamana"));
@@ -561,7 +563,9 @@ MSE_API int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_bu
     const uint64_t n = ix->n;
     if (max_batch == 0) max_batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(n / 50, 64), 16384);
     const uint32_t L = (uint32_t)cfg->l, stride = ix->graph_stride;
-    const uint32_t vl_cap = 8192;
+    // visited_list (lib.rs:205) is unbounded in the reference; a search evaluates ~25 x L rows at R = 64, so 48 x L (>= 8192) entries
+    // hold it with a wide margin, and a search that still exceeds them is counted in stats[4] (its list keeps the first vl_cap entries)
+    const uint32_t vl_cap = std::max<uint32_t>(8192, 48 * L);
     // sigma: host-side shuffle (lib.rs:291-292; the reference's fastrand stream need not be matched)
     std::vector<uint32_t> sigma(n);
     for (uint64_t i = 0; i < n; i++) sigma[i] = (uint32_t)i;
@@ -579,7 +583,7 @@ MSE_API int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_bu
     MSE_CUDA(cudaFuncSetAttribute(merge_backedges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     DevBuf b_sigma, b_ids, b_sc, b_len, b_dist, b_st, b_h, b_vi, b_vs, b_vl, b_na, b_nd, b_in, b_ic, b_t, b_nt;
     int rc = MSE_OK;
-    uint64_t st_batches = 0, st_search = 0, st_merge = 0, st_dist = 0;
+    uint64_t st_batches = 0, st_search = 0, st_merge = 0, st_dist = 0, st_trunc = 0, st_ovf = 0;
     do {
         if ((rc = b_sigma.ensure(n * 4)) || (rc = b_ids.ensure((size_t)max_batch * L * 4)) || (rc = b_sc.ensure((size_t)max_batch * L * 8)) ||
             (rc = b_len.ensure((size_t)max_batch * 4)) || (rc = b_dist.ensure((size_t)max_batch * 8)) || (rc = b_st.ensure((size_t)max_batch * 4)) ||
@@ -595,6 +599,7 @@ MSE_API int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_bu
         uint64_t done = 0;
         uint32_t bs = 1;
         std::vector<unsigned long long> hdist(max_batch);
+        std::vector<uint32_t> hst(max_batch), hvl(max_batch);
         while (done < n && rc == MSE_OK) {
             const uint32_t nb = (uint32_t)std::min<uint64_t>(bs, n - done);
             const uint32_t *pts = b_sigma.as<uint32_t>() + done;
@@ -619,7 +624,18 @@ MSE_API int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_bu
                 count_launch();
             }
             cudaMemcpy(hdist.data(), b_dist.p, (size_t)nb * 8, cudaMemcpyDeviceToHost);
-            for (uint32_t i = 0; i < nb; i++) st_dist += hdist[i];
+            cudaMemcpy(hst.data(), b_st.p, (size_t)nb * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(hvl.data(), b_vl.p, (size_t)nb * 4, cudaMemcpyDeviceToHost);
+            for (uint32_t i = 0; i < nb; i++) {
+                st_dist += hdist[i];
+                st_trunc += hvl[i] > vl_cap;
+                st_ovf += hst[i] != 0;
+            }
+            if (st_ovf) {   // the search stopped early: the point would be pruned over a partial candidate set
+                set_error("build_vamana: the visited-set table overflowed in %llu searches (l=%u, stride=%u)", (unsigned long long)st_ovf, L, stride);
+                rc = MSE_ERR_UNSUPPORTED;
+                break;
+            }
             st_batches++; st_search += nb; st_merge += nt;
             done += nb;
             bs = std::min<uint32_t>(bs * 2, max_batch);
@@ -631,7 +647,7 @@ MSE_API int mse_index_build_vamana(mse_index *ix, uint32_t medioid, const mse_bu
     } while (0);
     b_sigma.release(); b_ids.release(); b_sc.release(); b_len.release(); b_dist.release(); b_st.release(); b_h.release(); b_vi.release();
     b_vs.release(); b_vl.release(); b_na.release(); b_nd.release(); b_in.release(); b_ic.release(); b_t.release(); b_nt.release();
-    if (stats) { stats[0] = st_batches; stats[1] = st_search; stats[2] = st_merge; stats[3] = st_dist; }
+    if (stats) { stats[0] = st_batches; stats[1] = st_search; stats[2] = st_merge; stats[3] = st_dist; stats[4] = st_trunc; stats[5] = st_ovf; }
     return rc;
 }
 

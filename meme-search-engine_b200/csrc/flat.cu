@@ -594,6 +594,28 @@ static int index_reserve(mse_index *ix, uint64_t rows, bool exact = false) {
     return MSE_OK;
 }
 
+namespace mse {
+void index_drop_side_arrays(mse_index *ix) {
+    if (ix->adj) cudaFree(ix->adj);
+    if (ix->deg) cudaFree(ix->deg);
+    if (ix->pq_codes) cudaFree(ix->pq_codes);
+    if (ix->code_scale) cudaFree(ix->code_scale);
+    if (ix->desc) cudaFree(ix->desc);
+    if (ix->has_url) cudaFree(ix->has_url);
+    ix->adj = ix->deg = nullptr;
+    ix->pq_codes = ix->desc = ix->has_url = nullptr;
+    ix->code_scale = nullptr;
+    ix->graph_stride = ix->code_size = ix->n_desc = 0;
+    ix->side_n = 0;
+}
+}  // namespace mse
+
+// VectorList::push after IndexGraph::empty(n, r) has no counterpart in the reference (the graph is sized from the final
+// vector count, generate_index_shard.rs:102); here growing the row store invalidates every per-row side array
+static void index_rows_grew(mse_index *ix) {
+    if (ix->adj || ix->deg || ix->pq_codes || ix->code_scale || ix->desc || ix->has_url) index_drop_side_arrays(ix);
+}
+
 static int index_note_rows(mse_index *ix, uint64_t first, uint64_t n, cudaStream_t st) {
     if (n == 0) return MSE_OK;
     uint32_t blocks = (uint32_t)std::min<uint64_t>((n + 7) / 8, (uint64_t)sm_count(ix->device) * 8);
@@ -642,6 +664,7 @@ MSE_API int mse_index_add_f16(mse_index *ix, const uint16_t *x_f16, uint64_t n) 
     MSE_CHECK(index_note_rows(ix, ix->n, n, ix->stream));
     MSE_CUDA(cudaStreamSynchronize(ix->stream));
     ix->n += n;
+    index_rows_grew(ix);
     return MSE_OK;
 }
 
@@ -658,6 +681,7 @@ MSE_API int mse_index_add_f16_dev(mse_index *ix, const uint16_t *d_x_f16, uint64
     MSE_CHECK(index_note_rows(ix, ix->n, n, st));
     MSE_CUDA(cudaStreamSynchronize(st));
     ix->n += n;
+    index_rows_grew(ix);
     return MSE_OK;
 }
 
@@ -682,7 +706,10 @@ MSE_API int mse_index_add(mse_index *ix, const float *x_f32, uint64_t n) {
         if (cudaStreamSynchronize(ix->stream) != cudaSuccess) { rc = MSE_ERR_CUDA; set_error("index_add: sync failed"); break; }
     } while (0);
     cudaFree(stage);
-    if (rc == MSE_OK) ix->n += n;
+    if (rc == MSE_OK) {
+        ix->n += n;
+        index_rows_grew(ix);
+    }
     return rc;
 }
 

@@ -175,6 +175,11 @@ __global__ void __launch_bounds__(kGsThreads) k_greedy_search(GraphArgs g, const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (uint32_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
+        if ((starts ? starts[qi] : start_all) >= g.n) {                              // not a row of this shard: empty result, status bit 2
+            for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) { out.ids[(size_t)qi * L + i] = kEmpty; out.scores[(size_t)qi * L + i] = 0; }
+            if (threadIdx.x == 0) { out.len[qi] = 0; out.distances[qi] = 0; if (out.vl_len) out.vl_len[qi] = 0; out.status[qi] = 4u; }
+            continue;
+        }
         for (uint32_t i = threadIdx.x; i < hcap; i += blockDim.x) htab[i] = kEmpty;
         const size_t qrow = q_rows ? q_rows[qi] : qi;
         // base_vectors_only (lib.rs:196-199) applies to the searches of query nodes only (build_graph :297-298)
@@ -293,6 +298,11 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_greedy_search_wq(GraphArgs
     const unsigned full = 0xffffffffu;
 
     for (uint32_t qi = gw; qi < nq; qi += nw) {
+        if ((starts ? starts[qi] : start_all) >= g.n) {                              // not a row of this shard: empty result, status bit 2
+            for (uint32_t i = lane; i < L; i += 32) { out.ids[(size_t)qi * L + i] = kEmpty; out.scores[(size_t)qi * L + i] = 0; }
+            if (lane == 0) { out.len[qi] = 0; out.distances[qi] = 0; if (out.vl_len) out.vl_len[qi] = 0; out.status[qi] = 4u; }
+            continue;
+        }
         {
             uint4 *t4 = (uint4 *)htab;
             const uint4 e4 = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
@@ -446,6 +456,11 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
     const uint32_t lut_n = ba.M * ba.C;
 
     for (uint32_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
+        if ((starts ? starts[qi] : start_all) >= g.n) {                              // not a row of this shard: empty result, status bit 2
+            for (uint32_t i = threadIdx.x; i < out.topk; i += blockDim.x) { out.top_ids[(size_t)qi * out.topk + i] = kEmpty; out.top_scores[(size_t)qi * out.topk + i] = 0; }
+            if (threadIdx.x == 0) { out.len[qi] = 0; out.cmps[qi] = 0; out.pq_cmps[qi] = 0; out.status[qi] = 4u; if (out.topk) out.top_len[qi] = 0; }
+            continue;
+        }
         for (uint32_t i = threadIdx.x; i < hcap + vcap; i += blockDim.x) hadj[i] = kEmpty;
         for (uint32_t i = threadIdx.x; i < g.d; i += blockDim.x) s.q[i] = __half2float(queries[(size_t)qi * g.d + i]);
         float qt[kRqPerLane];
@@ -611,6 +626,11 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
     const unsigned full = 0xffffffffu;
 
     for (uint32_t qi = gw; qi < nq; qi += nw) {
+        if ((starts ? starts[qi] : start_all) >= g.n) {                              // not a row of this shard: empty result, status bit 2
+            for (uint32_t i = lane; i < out.topk; i += 32) { out.top_ids[(size_t)qi * out.topk + i] = kEmpty; out.top_scores[(size_t)qi * out.topk + i] = 0; }
+            if (lane == 0) { out.len[qi] = 0; out.cmps[qi] = 0; out.pq_cmps[qi] = 0; out.status[qi] = 4u; if (out.topk) out.top_len[qi] = 0; }
+            continue;
+        }
         {
             uint4 *t4 = (uint4 *)hadj;
             const uint4 e4 = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
@@ -803,6 +823,16 @@ __global__ void __launch_bounds__(256) k_scores_i64(const __half *__restrict__ x
     }
 }
 
+// adjacency ids must address rows of this shard (local ids): flags the first offender
+__global__ void k_check_adjacency(const uint32_t *__restrict__ adj, const uint32_t *__restrict__ deg, uint64_t n, uint32_t stride, uint32_t *bad) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * stride) return;
+    const uint64_t node = i / stride;
+    const uint32_t j = (uint32_t)(i % stride);
+    if (j == 0 && deg[node] > stride) atomicMin(bad, (uint32_t)node);
+    if (j < min(deg[node], stride) && adj[i] >= n) atomicMin(bad, (uint32_t)node);
+}
+
 // visited-set capacity: a search evaluates ~25 x L rows at R = 64 (1.6 k at L = 64, 4-5 k at L = 192); 4 x L x R slots keep the
 // table under ~15 % full, and the kernels stop with an overflow status at 75 % rather than degrade (the tables are cleared per
 // query, so their size is HBM write traffic)
@@ -869,6 +899,26 @@ static int require_graph(const mse_index *ix, const char *who) {
     return MSE_OK;
 }
 
+// entry points are local row numbers of this shard (IndexHeader.shards[i].medioid is a global id: subtract the shard's id_base)
+static int check_host_starts(const mse_index *ix, const uint32_t *starts, uint32_t start, uint32_t nq, const char *who) {
+    if (!starts) {
+        MSE_REQUIRE(start < ix->n, MSE_ERR_INVALID, "%s: start=%u is not a row of this shard (n=%llu; ids are local)", who, start, (unsigned long long)ix->n);
+        return MSE_OK;
+    }
+    for (uint32_t i = 0; i < nq; i++)
+        MSE_REQUIRE(starts[i] < ix->n, MSE_ERR_INVALID, "%s: starts[%u]=%u is not a row of this shard (n=%llu; ids are local)", who, i, starts[i],
+                    (unsigned long long)ix->n);
+    return MSE_OK;
+}
+
+// device-pointer variant: a scalar start is checked here; entries of a device array are checked by the search kernels, which
+// skip the query and set status bit 2 (mse_search_graph_check reports it)
+static int check_dev_start(const mse_index *ix, const uint32_t *d_starts, uint32_t start, const char *who) {
+    MSE_REQUIRE(d_starts || start < ix->n, MSE_ERR_INVALID, "%s: start=%u is not a row of this shard (n=%llu; ids are local)", who, start,
+                (unsigned long long)ix->n);
+    return MSE_OK;
+}
+
 static uint32_t pow2_at_least(uint64_t v) {
     uint32_t p = 1024;
     while (p < v && p < (1u << 30)) p <<= 1;
@@ -887,6 +937,25 @@ MSE_API int mse_index_set_graph(mse_index *ix, const uint32_t *adj, const uint32
     MSE_CUDA(cudaMemcpy(ix->adj, adj, ix->n * stride * 4, cudaMemcpyHostToDevice));
     MSE_CUDA(cudaMemcpy(ix->deg, deg, ix->n * 4, cudaMemcpyHostToDevice));
     ix->graph_stride = stride;
+    ix->side_n = ix->n;
+    if (ix->n) {   // neighbour ids are local row numbers; a global id (e.g. from a merged index) would be an out-of-bounds gather
+        DevBuf bad;
+        MSE_CHECK(bad.ensure(4));
+        uint32_t h = 0xFFFFFFFFu;
+        cudaMemcpy(bad.p, &h, 4, cudaMemcpyHostToDevice);
+        const uint64_t total = ix->n * stride;
+        k_check_adjacency<<<(uint32_t)((total + 255) / 256), 256>>>(ix->adj, ix->deg, ix->n, stride, bad.as<uint32_t>());
+        count_launch();
+        cudaError_t e = cudaMemcpy(&h, bad.p, 4, cudaMemcpyDeviceToHost);
+        bad.release();
+        if (e != cudaSuccess) { set_error("index_set_graph: %s", cudaGetErrorString(e)); return MSE_ERR_CUDA; }
+        if (h != 0xFFFFFFFFu) {
+            index_drop_side_arrays(ix);
+            set_error("index_set_graph: node %u has a degree above the stride or a neighbour id >= n=%llu (ids are local to the shard)", h,
+                      (unsigned long long)ix->n);
+            return MSE_ERR_INVALID;
+        }
+    }
     return MSE_OK;
 }
 
@@ -939,6 +1008,7 @@ MSE_API int mse_search_graph(mse_index *ix, const uint16_t *q_f16, uint32_t nq, 
     MSE_REQUIRE(q_f16 && ids && scores && len && distances, MSE_ERR_INVALID, "search_graph: NULL buffer");
     MSE_REQUIRE(L >= 1 && L <= 4096, MSE_ERR_UNSUPPORTED, "search_graph: L=%u out of range [1,4096]", L);
     if (nq == 0) return MSE_OK;
+    MSE_CHECK(check_host_starts(ix, starts, start, nq, "search_graph"));
     MSE_CHECK(use_device(ix->device));
     const uint32_t grid = greedy_grid(ix, nq);
     const uint32_t hcap = greedy_hash_capacity(L, ix->graph_stride);
@@ -998,6 +1068,7 @@ MSE_API int mse_search_graph_dev(mse_index *ix, const uint16_t *d_q_f16, uint32_
     MSE_REQUIRE(d_q_f16 && d_ids && d_scores && d_len && d_distances, MSE_ERR_INVALID, "search_graph_dev: NULL buffer");
     MSE_REQUIRE(L >= 1 && L <= 4096, MSE_ERR_UNSUPPORTED, "search_graph_dev: L=%u out of range [1,4096]", L);
     if (nq == 0) return MSE_OK;
+    MSE_CHECK(check_dev_start(ix, d_starts, start, "search_graph_dev"));
     MSE_CHECK(use_device(ix->device));
     const uint32_t workers = greedy_grid(ix, nq);
     const uint32_t hcap = greedy_hash_capacity(L, ix->graph_stride);
@@ -1020,6 +1091,7 @@ MSE_API int mse_search_graph_check(mse_index *ix, uint32_t nq) {
     for (uint32_t i = 0; i < nq; i++) {
         MSE_REQUIRE(!(status[i] & 1u), MSE_ERR_UNSUPPORTED, "search_graph: visited-set table overflowed for query %u", i);
         MSE_REQUIRE(!(status[i] & 2u), MSE_ERR_UNSUPPORTED, "search_beam_dev: query %u expanded more nodes than the visit list holds", i);
+        MSE_REQUIRE(!(status[i] & 4u), MSE_ERR_INVALID, "search_*_dev: the entry point of query %u is not a row of this shard (ids are local)", i);
     }
     return MSE_OK;
 }
@@ -1037,6 +1109,7 @@ static int search_beam_impl(mse_index *ix, const uint16_t *q_f16, const float *l
     MSE_REQUIRE(L >= 1 && L <= 4096 && W >= 1 && W <= 64, MSE_ERR_UNSUPPORTED, "search_beam: L=%u W=%u out of range", L, W);
     MSE_REQUIRE(!ix->n_desc || desc_scales, MSE_ERR_INVALID, "search_beam: the index has descriptors but desc_scales is NULL");
     if (nq == 0) return MSE_OK;
+    MSE_CHECK(check_host_starts(ix, starts, start, nq, "search_beam"));
     MSE_CHECK(use_device(ix->device));
     const uint32_t M = ix->code_size, C = n_centroids;
     const size_t lut_bytes = disable_pq ? 16 : (size_t)M * C * 4;
@@ -1080,6 +1153,7 @@ static int search_beam_impl(mse_index *ix, const uint16_t *q_f16, const float *l
         cudaMemcpy(status.data(), b_st.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
         for (uint32_t i = 0; i < nq; i++)
             if (status[i] & 1u) { set_error("search_beam: visited-set table overflowed for query %u", i); rc = MSE_ERR_UNSUPPORTED; break; }
+            else if (status[i] & 2u) { set_error("search_beam: query %u expanded more than out_cap=%u nodes (the list would be truncated)", i, out_cap); rc = MSE_ERR_UNSUPPORTED; break; }
     } while (0);
     b_q.release(); b_lut.release(); b_ds.release(); b_ids.release(); b_sc.release(); b_len.release(); b_c.release(); b_p.release();
     b_st.release(); b_h.release(); b_starts.release(); b_cb.release();
@@ -1120,6 +1194,7 @@ MSE_API int mse_search_beam_dev(mse_index *ix, const uint16_t *d_q_f16, const fl
     MSE_REQUIRE(L >= 1 && L <= 4096 && W >= 1 && W <= 64, MSE_ERR_UNSUPPORTED, "search_beam_dev: L=%u W=%u out of range", L, W);
     MSE_REQUIRE(!ix->n_desc || d_desc_scales, MSE_ERR_INVALID, "search_beam_dev: the index has descriptors but d_desc_scales is NULL");
     if (nq == 0) return MSE_OK;
+    MSE_CHECK(check_dev_start(ix, d_starts, start, "search_beam_dev"));
     MSE_CHECK(use_device(ix->device));
     const uint32_t M = ix->code_size, C = d_qtm ? 0u : n_centroids;
     MSE_REQUIRE(d_qtm || C >= 1, MSE_ERR_INVALID, "search_beam_dev: n_centroids is 0");

@@ -39,6 +39,7 @@ struct mse_index {
     // graph + packed-index side arrays (IndexGraph lib.rs:16-39; index.pq-codes.bin / index.descriptor-codes.bin)
     uint32_t *adj = nullptr, *deg = nullptr;   // fixed stride adjacency [n][graph_stride], degrees [n]
     uint32_t graph_stride = 0;
+    uint64_t side_n = 0;                       // row count the side arrays below (adj, deg, codes, scales, descriptors) were sized for
     uint8_t *pq_codes = nullptr;               // [n][code_size]
     uint32_t code_size = 0;
     float *code_scale = nullptr;               // [n] per-vector factor of scaled codes (RabitQ: |o| * <o_bar, o>)
@@ -59,6 +60,9 @@ struct mse_index {
 };
 
 namespace mse {
+// flat.cu: rows were appended -> the per-row side arrays (graph, codes, scales, descriptors) no longer cover the index;
+// they are released so that later graph / beam calls fail with MSE_ERR_STATE instead of reading past them
+void index_drop_side_arrays(mse_index *ix);
 // flat_tc.cu: tensor-core scoring pass over rows [row0, row0+nrows) for queries [0,nq) (q16 padded to 128 rows)
 int flat_tc_score_chunk(mse_index *ix, uint32_t nq, uint64_t row0, uint64_t nrows, uint32_t cap, cudaStream_t st);
 int flat_tc_supported(const mse_index *ix);

@@ -254,14 +254,18 @@ static int parse_codec_msgpack(const uint8_t *buf, size_t len, std::vector<std::
         uint64_t kl;
         const uint8_t kt = r.u8();
         if (!(r.read_len(kt, 0xa0, 0xbf, 0xda, 0xdb, kl) || (kt == 0xd9 && ((kl = r.be(1)), true)))) { set_error("codec msgpack: key is not a string"); return MSE_ERR_INVALID; }
-        MSE_REQUIRE(r.p + kl <= r.end, MSE_ERR_INVALID, "codec msgpack: truncated key");
+        MSE_REQUIRE(r.ok && kl <= (uint64_t)(r.end - r.p), MSE_ERR_INVALID, "codec msgpack: truncated key");
         std::string key((const char *)r.p, kl);
         r.p += kl;
+        MSE_REQUIRE(r.p < r.end, MSE_ERR_INVALID, "codec msgpack: no value after key '%s'", key.c_str());
         const uint8_t vt = *r.p;
         uint64_t al;
         if ((vt >= 0x90 && vt <= 0x9f) || vt == 0xdc || vt == 0xdd) {
             r.u8();
             r.read_len(vt, 0x90, 0x9f, 0xdc, 0xdd, al);
+            // every element takes at least one byte: a length beyond the remaining bytes is a corrupt (or hostile) header
+            MSE_REQUIRE(r.ok && al <= (uint64_t)(r.end - r.p), MSE_ERR_INVALID, "codec msgpack: array '%s' claims %llu elements, %llu bytes remain",
+                        key.c_str(), (unsigned long long)al, (unsigned long long)(r.end - r.p));
             std::vector<float> v;
             v.reserve(al);
             for (uint64_t j = 0; j < al; j++) {

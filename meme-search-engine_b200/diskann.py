@@ -102,9 +102,10 @@ def medioid(vecs: VectorList) -> int:
 
 
 def build_graph(vecs: VectorList, medioid_: int, config: IndexBuildConfig, seed: int = 0, max_batch: int = 0) -> dict:
-    stats = (C.c_uint64 * 4)()
+    stats = (C.c_uint64 * 6)()
     check(lib().mse_index_build_vamana(vecs._h, medioid_, C.byref(config), seed, max_batch, stats), "mse_index_build_vamana")
-    return {"batches": int(stats[0]), "searches": int(stats[1]), "backedge_merges": int(stats[2]), "distances": int(stats[3])}
+    return {"batches": int(stats[0]), "searches": int(stats[1]), "backedge_merges": int(stats[2]), "distances": int(stats[3]),
+            "truncated_visit_lists": int(stats[4])}
 
 
 def robust_stitch(vecs: VectorList, config: IndexBuildConfig, seed: int = 0, order=None):
