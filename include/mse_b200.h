@@ -86,8 +86,16 @@ void mse_index_destroy(mse_index *ix);
  * certified against the rounding bound of the fp16 pass; uncertified queries are re-run on the exact scan.
  * ===================================================================================== */
 int mse_search_flat(mse_index *ix, const float *q, uint32_t nq, uint32_t k, uint32_t *ids, float *scores);
+/* Device pointers; queues the whole search on `stream` and returns without synchronising.  The results in d_ids / d_scores
+ * are final once mse_search_flat_check has returned: it synchronises the stream, reads the search's status word and re-runs
+ * the (rare) queries whose cut could not be certified, or whose candidate buffer overflowed, on the exact scan.
+ * *repaired (optional) = number of queries it had to re-run. */
 int mse_search_flat_dev(mse_index *ix, const float *d_q, uint32_t nq, uint32_t k, uint32_t *d_ids, float *d_scores,
                         void *stream);
+int mse_search_flat_check(mse_index *ix, uint32_t *repaired);
+/* Query assembly on the device -- get_total_embedding (src/common.rs:215-274): d_q[i][:] += weight * f32(d_e_f16[i][:]) for nq rows of
+ * d values (`*total += *value * weight`, :270).  The query stays f32 and is NOT renormalised.  Zero d_q first. */
+int mse_query_accumulate_f16_dev(int device, const uint16_t *d_e_f16, float weight, float *d_q, uint32_t nq, uint32_t d, void *stream);
 /* statistics of the last mse_search_flat* call on this handle:
  * out[0]=tensor-path queries, out[1]=exact-scan queries, out[2]=queries escalated after a failed certificate,
  * out[3]=candidate-buffer overflows, out[4]=kernel launches, out[5]=chunks,
@@ -102,6 +110,50 @@ int mse_search_flat_set_mode(mse_index *ix, int mode);
  * [n_shards][nq][k] (ids, scores), output [nq][k] by (score desc, id asc). Device pointers. */
 int mse_merge_topk_dev(int device, const uint32_t *d_ids, const float *d_scores, uint32_t n_shards, uint32_t nq,
                        uint32_t k, uint32_t *d_out_ids, float *d_out_scores, void *stream);
+
+/* =====================================================================================
+ * Id-range sharding over the GPUs of one box (BASELINE north_star: "the index partitions by vector-id range across
+ * the 8 GPUs of one box with a single NCCL all-gather of per-shard top-k over NVLink").  One process (or thread) per GPU:
+ * every rank creates its shard with mse_index_create(..., device, id_base = first global id of the shard), joins the group,
+ * and calls the *_sharded_dev searches with the same replicated queries.  Each call queues, on the caller's stream:
+ * local search -> top-k written as packed (score, global id) entries straight into this rank's slot of the NCCL-registered
+ * gather buffer -> ONE ncclAllGather (in place) -> k-way merge by (score desc, id asc) on every rank.  Ids are global and
+ * the order is total, so the merged result is independent of the number of shards.  No host synchronisation.
+ * NCCL is bound at run time (the libnccl.so.2 already loaded in the process, else $MSE_NCCL_LIB, else the system's); a
+ * one-rank group needs no NCCL at all.  The reference has no counterpart (it shards on disk: dump_processor.rs:134,438-461).
+ * ===================================================================================== */
+#define MSE_SHARD_ID_BYTES 128
+typedef struct mse_shard_group mse_shard_group;
+
+/* [lo, hi) = the global ids of shard `rank` of `n_ranks` over n_total vectors */
+int mse_shard_range(uint64_t n_total, int n_ranks, int rank, uint64_t *lo, uint64_t *hi);
+/* rank 0 draws the group id (ncclGetUniqueId) and hands the bytes to the other ranks by any means (file, socket, MPI, ...) */
+int mse_shard_group_unique_id(uint8_t out[MSE_SHARD_ID_BYTES]);
+/* collective over the n_ranks callers (ncclCommInitRank).  unique_id may be NULL when n_ranks == 1. */
+int mse_shard_group_create(const uint8_t *unique_id, int n_ranks, int rank, int device, mse_shard_group **out);
+/* out = n_ranks, rank, device, NCCL version (0 for a one-rank group) */
+int mse_shard_group_info(const mse_shard_group *g, int32_t out[4]);
+/* number of all-gathers this group has issued (bench.py's collective count) */
+uint64_t mse_shard_group_gathers(const mse_shard_group *g);
+void mse_shard_group_destroy(mse_shard_group *g);
+
+/* mse_search_flat_dev over all shards: d_ids (global) / d_scores [nq][k], identical on every rank.  The certificate status
+ * of every shard travels with its list, so mse_search_sharded_check -- which every rank must call, like the search itself --
+ * decides without a further exchange whether a repair round (exact re-run on the flagged shards, second gather + merge) is needed. */
+int mse_search_flat_sharded_dev(mse_shard_group *g, mse_index *shard, const float *d_q, uint32_t nq, uint32_t k, uint32_t *d_ids,
+                                float *d_scores, void *stream);
+int mse_search_sharded_check(mse_shard_group *g, uint32_t *repaired);
+/* greedy_search (lib.rs:183-211) on every shard's own Vamana graph from its entry point `start` (a local row of this shard),
+ * best k of each shard's candidate list merged: d_ids (global) / d_scores (i64 fixed point) [nq][k].  d_distances (optional)
+ * [nq] = this shard's GreedySearchCounters.distances.  mse_search_graph_check(shard, nq) reports overflows as usual. */
+int mse_search_graph_sharded_dev(mse_shard_group *g, mse_index *shard, const uint16_t *d_q_f16, uint32_t nq, uint32_t L, uint32_t start,
+                                 uint32_t k, uint32_t *d_ids, int64_t *d_scores, uint64_t *d_distances, void *stream);
+/* mse_search_beam_dev (query_disk_index.rs:144-212: compressed scores for the frontier, exact scores for expanded nodes)
+ * on every shard, best k expanded nodes of each shard merged.  d_cmps / d_pq_cmps (optional) [nq] = this shard's counters. */
+int mse_search_beam_sharded_dev(mse_shard_group *g, mse_index *shard, const uint16_t *d_q_f16, const float *d_luts, const float *d_qtm,
+                                uint32_t rabitq_output_dims, uint32_t rabitq_n_dims, const float *d_desc_scales, uint32_t nq, uint32_t L, uint32_t W,
+                                uint32_t start, uint32_t n_centroids, uint32_t k, uint32_t *d_ids, int64_t *d_scores, uint64_t *d_cmps,
+                                uint64_t *d_pq_cmps, void *stream);
 
 /* =====================================================================================
  * Graph index -- the diskann crate's build/search entry points (diskann/src/lib.rs) and the packed-index search of

@@ -18,3 +18,5 @@ from .flat import FlatIndex, merge_topk  # noqa: F401
 from .encoder import Encoder  # noqa: F401
 from . import diskann  # noqa: F401
 from . import weights  # noqa: F401
+from . import sharding  # noqa: F401
+from .sharding import ShardGroup  # noqa: F401

@@ -55,7 +55,19 @@ _SIGS = {
     "mse_index_destroy": (None, [_vp]),
     "mse_search_flat": (_i32, [_vp, _vp, _u32, _u32, _vp, _vp]),
     "mse_search_flat_dev": (_i32, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
+    "mse_search_flat_check": (_i32, [_vp, _vp]),
+    "mse_query_accumulate_f16_dev": (_i32, [_i32, _vp, C.c_float, _vp, _u32, _u32, _vp]),
     "mse_search_flat_stats": (_i32, [_vp, _vp]),
+    "mse_shard_range": (_i32, [_u64, _i32, _i32, _vp, _vp]),
+    "mse_shard_group_unique_id": (_i32, [_vp]),
+    "mse_shard_group_create": (_i32, [_vp, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "mse_shard_group_info": (_i32, [_vp, _vp]),
+    "mse_shard_group_gathers": (_u64, [_vp]),
+    "mse_shard_group_destroy": (None, [_vp]),
+    "mse_search_flat_sharded_dev": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
+    "mse_search_sharded_check": (_i32, [_vp, _vp]),
+    "mse_search_graph_sharded_dev": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
+    "mse_search_beam_sharded_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "mse_search_flat_set_mode": (_i32, [_vp, _i32]),
     "mse_search_flat_profile": (_i32, [_vp, _i32]),
     "mse_merge_topk_dev": (_i32, [_i32, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),

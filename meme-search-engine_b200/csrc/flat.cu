@@ -101,6 +101,12 @@ __global__ void k_reset_state(uint32_t *ntop, float *thr, uint32_t *count, uint3
     if (clear_global && i < 4) flags[i] = 0;
 }
 
+// get_total_embedding (src/common.rs:215-274): q += weight * e, e an fp16 embedding row, q the f32 query (never renormalised)
+__global__ void k_query_axpy_f16(const __half *__restrict__ e, float w, float *__restrict__ q, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) q[i] += __half2float(e[i]) * w;                 // common.rs:270 `*total += *value * weight` (f32 multiply, f32 add)
+}
+
 __global__ void k_iota(uint32_t *p, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;
@@ -273,7 +279,7 @@ __global__ void __launch_bounds__(512) k_finalize(const uint64_t *__restrict__ t
                                                   const uint32_t *__restrict__ ntop, const float *__restrict__ thr,
                                                   const float *__restrict__ qstat, uint32_t k, uint32_t id_base, int rerank,
                                                   uint32_t *__restrict__ out_ids, float *__restrict__ out_scores,
-                                                  uint32_t out_stride, uint32_t *__restrict__ flags,
+                                                  uint64_t *__restrict__ out_keys, uint32_t out_stride, uint32_t *__restrict__ flags,
                                                   const uint32_t *__restrict__ qsel) {
     extern __shared__ uint64_t s_keys[];
     const uint32_t q = qsel ? qsel[blockIdx.x] : blockIdx.x;
@@ -299,13 +305,13 @@ __global__ void __launch_bounds__(512) k_finalize(const uint64_t *__restrict__ t
         }
     }
     for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
-        if (i < n) {
-            uint64_t key = src[i];
-            out_ids[(size_t)q * out_stride + i] = key_id(key) + id_base;
-            out_scores[(size_t)q * out_stride + i] = key_score(key);
-        } else {
-            out_ids[(size_t)q * out_stride + i] = MSE_ID_NONE;
-            out_scores[(size_t)q * out_stride + i] = -INFINITY;
+        const bool have = i < n;
+        const uint64_t key = have ? src[i] : 0ull;
+        if (out_keys)   // sharded search: the rank key with the GLOBAL id, written straight into the all-gather send slot (0 = no entry)
+            out_keys[(size_t)q * out_stride + i] = have ? rank_key(key_score(key), key_id(key) + id_base) : 0ull;
+        if (out_ids) {
+            out_ids[(size_t)q * out_stride + i] = have ? key_id(key) + id_base : MSE_ID_NONE;
+            out_scores[(size_t)q * out_stride + i] = have ? key_score(key) : -INFINITY;
         }
     }
 }
@@ -345,6 +351,26 @@ __global__ void __launch_bounds__(256) k_merge_topk(const uint32_t *__restrict__
     }
 }
 
+// merge of all-gathered rank-key slots (sharded search epilogue): slots[r] holds [nq][k] keys of rank r at stride slot_stride
+__global__ void __launch_bounds__(256) k_merge_keys(const uint64_t *__restrict__ slots, uint32_t n_shards, size_t slot_stride, uint32_t nq,
+                                                    uint32_t k, uint32_t *__restrict__ out_ids, float *__restrict__ out_scores) {
+    extern __shared__ uint64_t s_keys[];
+    const uint32_t q = blockIdx.x;
+    const uint32_t n = n_shards * k;
+    const uint32_t np2 = next_pow2_min64(n);
+    for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = i < n ? slots[(size_t)(i / k) * slot_stride + (size_t)q * k + i % k] : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(s_keys, np2);
+    for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
+        const uint64_t key = s_keys[i];
+        out_ids[(size_t)q * k + i] = key ? key_id(key) : MSE_ID_NONE;
+        out_scores[(size_t)q * k + i] = key ? key_score(key) : -INFINITY;
+    }
+}
+
+// [0] = overflow seen, [1] = uncertified queries -> one status word behind the keys of the slot
+__global__ void k_publish_status(const uint32_t *flags, uint64_t *word) { *word = (uint64_t)flags[0] | ((uint64_t)flags[1] << 32); }
+
 // ================================================================== host side
 
 static int ensure_select_smem(int device) {
@@ -353,6 +379,7 @@ static int ensure_select_smem(int device) {
     MSE_CUDA(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortMax * 8)));
     MSE_CUDA(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortMax * 8)));
     MSE_CUDA(cudaFuncSetAttribute(k_merge_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortMax * 8)));
+    MSE_CUDA(cudaFuncSetAttribute(k_merge_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortMax * 8)));
     return MSE_OK;
 }
 
@@ -397,15 +424,20 @@ static void prof_collect(mse_index *ix) {
     ix->stats[7] = ix->prof_used / 2;
 }
 
+// Chunk schedule.  After N rows the threshold is the kp-th best of those N, so under exchangeable row order a further chunk of
+// g*N rows contributes ~g*kp candidates per query; g is chosen so that this stays at a third of the candidate buffer
+// (g = 1, i.e. doubling, for the largest kp; up to 15 for small k: 10 M rows are 5 launches instead of 13).  Row orders that
+// defeat the estimate overflow the buffer, which is detected and repaired by the exact re-run (fixed chunks).
 struct ChunkPlan {
     std::vector<std::pair<uint64_t, uint64_t>> chunks;  // (row0, nrows)
-    ChunkPlan(uint64_t n, uint64_t fixed) {
-        uint64_t row0 = 0, sz = fixed ? fixed : kChunk0;
+    ChunkPlan(uint64_t n, uint64_t fixed, uint32_t kp, uint32_t cap) {
+        const uint64_t g = std::min<uint64_t>(15, std::max<uint64_t>(1, cap / (3ull * std::max(kp, 1u))));
+        uint64_t row0 = 0;
         while (row0 < n) {
-            uint64_t m = std::min(sz, n - row0);
+            const uint64_t sz = fixed ? fixed : (row0 == 0 ? kChunk0 : g * row0);
+            const uint64_t m = std::min(sz, n - row0);
             chunks.push_back({row0, m});
             row0 += m;
-            if (!fixed && row0 >= 2 * sz) sz *= 2;
         }
     }
 };
@@ -416,7 +448,7 @@ static int run_exact(mse_index *ix, const float *d_q, const uint32_t *d_sel, uin
     FlatWork &w = ix->fw;
     const int sms = sm_count(ix->device);
     const int vpl = (int)((ix->d / 8 + 31) / 32);
-    ChunkPlan plan(ix->n, fixed_chunk);
+    ChunkPlan plan(ix->n, fixed_chunk, kp, cap);
     k_reset_state<<<(nsel + 255) / 256, 256, 0, st>>>(w.ntop.as<uint32_t>(), w.thr.as<float>(), w.count.as<uint32_t>(),
                                                      w.flags.as<uint32_t>(), d_sel, nsel, 0);
     MSE_LAUNCH_OK();
@@ -452,14 +484,25 @@ static int read_flags(mse_index *ix, cudaStream_t st, uint32_t out[4]) {
     return MSE_OK;
 }
 
-static int flat_search_device(mse_index *ix, const float *d_q, uint32_t nq, uint32_t k, uint32_t *d_ids, float *d_scores,
-                              cudaStream_t st) {
+static int launch_finalize(mse_index *ix, uint32_t n_ctas, uint32_t k, uint32_t cap, int rerank, const FlatOut &o, const uint32_t *d_sel, cudaStream_t st) {
+    FlatWork &w = ix->fw;
+    k_finalize<<<n_ctas, 512, kSortMax * 8, st>>>(w.top.as<uint64_t>(), kKpMax, w.cand.as<uint64_t>(), cap, w.ntop.as<uint32_t>(), w.thr.as<float>(),
+                                                  w.qstat.as<float>(), k, ix->id_base, rerank, o.ids, o.scores, o.keys, k, w.flags.as<uint32_t>(), d_sel);
+    MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
+// Queues one search on `st` and returns without synchronising.  What is left on the device afterwards: the results, and the
+// status word flags[0..1] (candidate-buffer overflow seen / number of queries whose cut could not be certified).
+// flat_search_settle reads it and repairs the flagged queries.
+int flat_search_queue(mse_index *ix, const float *d_q, uint32_t nq, uint32_t k, const FlatOut &out, cudaStream_t st) {
     MSE_CHECK(use_device(ix->device));
     MSE_CHECK(ensure_select_smem(ix->device));
     MSE_REQUIRE(k >= 1, MSE_ERR_INVALID, "search_flat: k must be >= 1");
     MSE_REQUIRE(ix->d % 8 == 0 && ix->d <= 2048, MSE_ERR_UNSUPPORTED, "search_flat: d=%u unsupported", ix->d);
     memset(ix->stats, 0, sizeof(ix->stats));
     ix->prof_used = 0;
+    ix->pending = FlatPending{};
     const uint64_t launches0 = g_launches.load();
     if (nq == 0) return MSE_OK;
     FlatWork &w = ix->fw;
@@ -498,26 +541,17 @@ static int flat_search_device(mse_index *ix, const float *d_q, uint32_t nq, uint
     MSE_LAUNCH_OK();
 
     if (ix->n == 0) {
-        k_finalize<<<nq, 512, kSortMax * 8, st>>>(w.top.as<uint64_t>(), kKpMax, w.cand.as<uint64_t>(), cap, w.ntop.as<uint32_t>(),
-                                                  w.thr.as<float>(), w.qstat.as<float>(), k, ix->id_base, 0, d_ids, d_scores, k,
-                                                  w.flags.as<uint32_t>(), nullptr);
-        MSE_LAUNCH_OK();
-        return MSE_OK;
-    }
-
-    if (!tensor) {
+        MSE_CHECK(launch_finalize(ix, nq, k, cap, 0, out, nullptr, st));
+    } else if (!tensor) {
         ix->stats[1] = nq;
         MSE_CHECK(run_exact(ix, d_q, w.sel.as<uint32_t>(), nq, kp, cap, 0, st));
-        k_finalize<<<nq, 512, kSortMax * 8, st>>>(w.top.as<uint64_t>(), kKpMax, w.cand.as<uint64_t>(), cap, w.ntop.as<uint32_t>(),
-                                                  w.thr.as<float>(), w.qstat.as<float>(), k, ix->id_base, 0, d_ids, d_scores, k,
-                                                  w.flags.as<uint32_t>(), nullptr);
-        MSE_LAUNCH_OK();
+        MSE_CHECK(launch_finalize(ix, nq, k, cap, 0, out, nullptr, st));
     } else {
         ix->stats[0] = nq;
         k_prepare_queries<<<(nq_pad * 32 + 255) / 256, 256, 0, st>>>(d_q, nq, nq_pad, ix->d, w.q16.as<__half>(), w.qstat.as<float>(),
                                                                      ix->max_norm);
         MSE_LAUNCH_OK();
-        ChunkPlan plan(ix->n, 0);
+        ChunkPlan plan(ix->n, 0, kp, cap);
         for (auto &c : plan.chunks) {
             prof_mark(ix, st);
             MSE_CHECK(flat_tc_score_chunk(ix, nq, c.first, c.second, cap, st));
@@ -531,20 +565,33 @@ static int flat_search_device(mse_index *ix, const float *d_q, uint32_t nq, uint
         k_rerank<<<dim3((kp * 32 + 255) / 256, nq), 256, 0, st>>>(ix->x, ix->d, d_q, w.top.as<uint64_t>(), kKpMax, w.ntop.as<uint32_t>(),
                                                                  w.cand.as<uint64_t>(), cap, nq);
         MSE_LAUNCH_OK();
-        k_finalize<<<nq, 512, kSortMax * 8, st>>>(w.top.as<uint64_t>(), kKpMax, w.cand.as<uint64_t>(), cap, w.ntop.as<uint32_t>(),
-                                                  w.thr.as<float>(), w.qstat.as<float>(), k, ix->id_base, 1, d_ids, d_scores, k,
-                                                  w.flags.as<uint32_t>(), nullptr);
-        MSE_LAUNCH_OK();
+        MSE_CHECK(launch_finalize(ix, nq, k, cap, 1, out, nullptr, st));
     }
+    ix->stats[4] = g_launches.load() - launches0;
+    ix->pending = FlatPending{d_q, nq, k, out, st, ix->n != 0};
+    return MSE_OK;
+}
 
-    // status word: [0] overflow seen, [1] number of uncertified queries
+// Synchronises `st`, reads the status word of the last queued search and re-runs flagged queries on the exact scan; if that
+// overflowed too (adversarial row order), once more with fixed chunks no larger than the candidate buffer, which cannot overflow.
+// *repaired (optional) = number of queries that were re-run.
+int flat_search_settle(mse_index *ix, uint32_t *repaired) {
+    if (repaired) *repaired = 0;
+    FlatPending p = ix->pending;
+    if (!p.live) {
+        if (p.st_valid()) MSE_CUDA(cudaStreamSynchronize(p.st));
+        return MSE_OK;
+    }
+    MSE_CHECK(use_device(ix->device));
+    FlatWork &w = ix->fw;
+    cudaStream_t st = p.st;
+    const uint32_t nq = p.nq, k = p.k, cap = kSortMax - kKpMax;
+    const uint64_t launches0 = g_launches.load();
     uint32_t fl[4];
     MSE_CHECK(read_flags(ix, st, fl));
     int guard = 0;
     uint64_t fixed = 0;
     while (fl[0] != 0 || fl[1] != 0) {
-        // re-run the flagged queries on the exact scan; if that overflowed too (adversarial row order),
-        // fall back to fixed chunks no larger than the candidate buffer, which cannot overflow
         MSE_REQUIRE(++guard <= 2, MSE_ERR_CUDA, "search_flat: exact re-run did not converge");
         ix->stats[2] += fl[1];
         ix->stats[3] += fl[0];
@@ -556,16 +603,32 @@ static int flat_search_device(mse_index *ix, const float *d_q, uint32_t nq, uint
         const uint32_t nsel = fl[2];
         MSE_CUDA(cudaMemsetAsync(w.flags.p, 0, 16, st));
         ix->stats[1] += nsel;
-        MSE_CHECK(run_exact(ix, d_q, w.sel.as<uint32_t>(), nsel, k, cap, fixed, st));
-        k_finalize<<<nsel, 512, kSortMax * 8, st>>>(w.top.as<uint64_t>(), kKpMax, w.cand.as<uint64_t>(), cap, w.ntop.as<uint32_t>(),
-                                                    w.thr.as<float>(), w.qstat.as<float>(), k, ix->id_base, 0, d_ids, d_scores, k,
-                                                    w.flags.as<uint32_t>(), w.sel.as<uint32_t>());
-        MSE_LAUNCH_OK();
+        if (repaired) *repaired += nsel;
+        MSE_CHECK(run_exact(ix, p.d_q, w.sel.as<uint32_t>(), nsel, k, cap, fixed, st));
+        MSE_CHECK(launch_finalize(ix, nsel, k, cap, 0, p.out, w.sel.as<uint32_t>(), st));
         MSE_CHECK(read_flags(ix, st, fl));
         fixed = cap;
     }
-    ix->stats[4] = g_launches.load() - launches0;
+    ix->stats[4] += g_launches.load() - launches0;
+    ix->pending.live = false;
     prof_collect(ix);
+    return MSE_OK;
+}
+
+int flat_publish_status(mse_index *ix, uint64_t *d_word, cudaStream_t st) {
+    if (!ix->fw.flags.p) { MSE_CUDA(cudaMemsetAsync(d_word, 0, 8, st)); return MSE_OK; }
+    k_publish_status<<<1, 1, 0, st>>>(ix->fw.flags.as<uint32_t>(), d_word);
+    MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
+int flat_merge_keys(int device, const uint64_t *d_slots, uint32_t n_shards, size_t slot_stride, uint32_t nq, uint32_t k, uint32_t *d_ids,
+                    float *d_scores, cudaStream_t st) {
+    MSE_CHECK(ensure_select_smem(device));
+    MSE_REQUIRE((uint64_t)n_shards * k <= kSortMax, MSE_ERR_UNSUPPORTED, "sharded search: n_shards*k=%llu exceeds %u", (unsigned long long)n_shards * k, kSortMax);
+    if (nq == 0) return MSE_OK;
+    k_merge_keys<<<nq, 256, kSortMax * 8, st>>>(d_slots, n_shards, slot_stride, nq, k, d_ids, d_scores);
+    MSE_LAUNCH_OK();
     return MSE_OK;
 }
 
@@ -752,7 +815,12 @@ MSE_API int mse_search_flat_dev(mse_index *ix, const float *d_q, uint32_t nq, ui
                                 void *stream) {
     MSE_REQUIRE(ix != nullptr, MSE_ERR_INVALID, "search_flat_dev: NULL handle");
     MSE_REQUIRE(nq == 0 || (d_q && d_ids && d_scores), MSE_ERR_INVALID, "search_flat_dev: NULL buffer");
-    return flat_search_device(ix, d_q, nq, k, d_ids, d_scores, (cudaStream_t)stream);
+    return flat_search_queue(ix, d_q, nq, k, FlatOut{d_ids, d_scores, nullptr}, (cudaStream_t)stream);
+}
+
+MSE_API int mse_search_flat_check(mse_index *ix, uint32_t *repaired) {
+    MSE_REQUIRE(ix != nullptr, MSE_ERR_INVALID, "search_flat_check: NULL handle");
+    return flat_search_settle(ix, repaired);
 }
 
 MSE_API int mse_search_flat(mse_index *ix, const float *q, uint32_t nq, uint32_t k, uint32_t *ids, float *scores) {
@@ -766,15 +834,31 @@ MSE_API int mse_search_flat(mse_index *ix, const float *q, uint32_t nq, uint32_t
     MSE_CHECK(w.out_ids.ensure((size_t)nq * k * 4));
     MSE_CHECK(w.out_sc.ensure((size_t)nq * k * 4));
     MSE_CUDA(cudaMemcpyAsync(w.q.p, q, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, ix->stream));
-    MSE_CHECK(flat_search_device(ix, w.q.as<float>(), nq, k, w.out_ids.as<uint32_t>(), w.out_sc.as<float>(), ix->stream));
+    MSE_CHECK(flat_search_queue(ix, w.q.as<float>(), nq, k, FlatOut{w.out_ids.as<uint32_t>(), w.out_sc.as<float>(), nullptr}, ix->stream));
+    MSE_CHECK(flat_search_settle(ix, nullptr));
     MSE_CUDA(cudaMemcpyAsync(ids, w.out_ids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
     MSE_CUDA(cudaMemcpyAsync(scores, w.out_sc.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
     MSE_CUDA(cudaStreamSynchronize(ix->stream));
     return MSE_OK;
 }
 
+MSE_API int mse_query_accumulate_f16_dev(int device, const uint16_t *d_e_f16, float weight, float *d_q, uint32_t nq, uint32_t d, void *stream) {
+    MSE_REQUIRE(nq == 0 || (d_e_f16 && d_q), MSE_ERR_INVALID, "query_accumulate_f16_dev: NULL buffer");
+    if (nq == 0 || d == 0) return MSE_OK;
+    MSE_CHECK(use_device(device));
+    const uint64_t n = (uint64_t)nq * d;
+    k_query_axpy_f16<<<(uint32_t)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half *)d_e_f16, weight, d_q, n);
+    MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
 MSE_API int mse_search_flat_stats(const mse_index *ix, uint64_t out[8]) {
     MSE_REQUIRE(ix != nullptr && out != nullptr, MSE_ERR_INVALID, "search_flat_stats: NULL argument");
+    if (ix->profile && ix->prof_used) {   // event times need the launches to have finished
+        mse_index *m = const_cast<mse_index *>(ix);
+        if (ix->pending.st_valid()) cudaStreamSynchronize(ix->pending.st);
+        prof_collect(m);
+    }
     memcpy(out, ix->stats, sizeof(ix->stats));
     return MSE_OK;
 }

@@ -26,6 +26,25 @@ struct FlatWork {
     }
 };
 
+// where a flat search leaves its results: ids + scores ([nq][k]), and/or rank keys with global ids ([nq][k] u64, 0 = no entry)
+struct FlatOut {
+    uint32_t *ids = nullptr;
+    float *scores = nullptr;
+    uint64_t *keys = nullptr;
+};
+// the last queued flat search of a handle, kept for flat_search_settle
+struct FlatPending {
+    const float *d_q = nullptr;
+    uint32_t nq = 0, k = 0;
+    FlatOut out;
+    cudaStream_t st = nullptr;
+    bool live = false;       // results still need their status word read
+    bool queued = false;
+    bool st_valid() const { return queued; }
+    FlatPending() {}
+    FlatPending(const float *q, uint32_t nq_, uint32_t k_, const FlatOut &o, cudaStream_t s, bool live_) : d_q(q), nq(nq_), k(k_), out(o), st(s), live(live_), queued(true) {}
+};
+
 }  // namespace mse
 
 struct mse_index {
@@ -51,6 +70,7 @@ struct mse_index {
     size_t prof_used = 0;
     uint64_t stats[8] = {0};
     mse::FlatWork fw;
+    mse::FlatPending pending;
     mse::DevBuf gw_htabs, gw_status, gw_vis_ids, gw_vis_sc, gw_vis_len;
     uint32_t gw_vis_cap = 0;          // entries per query of the visit lists the last mse_search_beam_dev call wrote  // graph search workspace of the device-pointer API (visited-set tables, per-query status)
     cudaStream_t stream = nullptr;  // handle-owned stream for the host-pointer API
@@ -66,4 +86,10 @@ void index_drop_side_arrays(mse_index *ix);
 // flat_tc.cu: tensor-core scoring pass over rows [row0, row0+nrows) for queries [0,nq) (q16 padded to 128 rows)
 int flat_tc_score_chunk(mse_index *ix, uint32_t nq, uint64_t row0, uint64_t nrows, uint32_t cap, cudaStream_t st);
 int flat_tc_supported(const mse_index *ix);
+// flat.cu: queue a search without synchronising / read its status word and repair flagged queries (synchronises)
+int flat_search_queue(mse_index *ix, const float *d_q, uint32_t nq, uint32_t k, const FlatOut &out, cudaStream_t st);
+int flat_search_settle(mse_index *ix, uint32_t *repaired);
+int flat_publish_status(mse_index *ix, uint64_t *d_word, cudaStream_t st);
+int flat_merge_keys(int device, const uint64_t *d_slots, uint32_t n_shards, size_t slot_stride, uint32_t nq, uint32_t k, uint32_t *d_ids,
+                    float *d_scores, cudaStream_t st);
 }  // namespace mse

@@ -44,8 +44,8 @@ class VectorList(FlatIndex):
     """diskann/src/vector.rs:118-186: flat row-major fp16 store (+ the graph and packed-index arrays attached to it)."""
 
     @classmethod
-    def from_f16s(cls, x16: np.ndarray, device: int = 0) -> "VectorList":
-        return cls.from_f16(x16, device)
+    def from_f16s(cls, x16: np.ndarray, device: int = 0, id_base: int = 0) -> "VectorList":
+        return cls.from_f16(x16, device, id_base)
 
     def __len__(self):
         return self.ntotal

@@ -77,9 +77,16 @@ class FlatIndex:
         return sc, labels
 
     def search_dev(self, q_ptr: int, nq: int, k: int, ids_ptr: int, scores_ptr: int, stream: int = 0):
-        """Device-pointer variant (queries and results stay in HBM)."""
+        """Device-pointer variant (queries and results stay in HBM): queues the search on `stream` and returns; the results are
+        final after check()."""
         check(lib().mse_search_flat_dev(self._h, C.c_void_p(q_ptr), nq, k, C.c_void_p(ids_ptr), C.c_void_p(scores_ptr),
                                         C.c_void_p(stream)), "mse_search_flat_dev")
+
+    def check(self) -> int:
+        """Synchronises the last search_dev, re-runs the (rare) queries whose cut could not be certified; returns how many."""
+        rep = C.c_uint32()
+        check(lib().mse_search_flat_check(self._h, C.byref(rep)), "mse_search_flat_check")
+        return int(rep.value)
 
     # -- diagnostics -------------------------------------------------------------------------
     def set_mode(self, mode: int):
