@@ -321,7 +321,7 @@ def main():
     ap.add_argument("--graph-rows-per-gpu", type=int, default=12_500_000, help="graph: index rows per rank (C4: 12.5M x 8 GPUs = 1e8)")
     ap.add_argument("--graph-queries", type=int, default=4096)
     ap.add_argument("--graph-L", type=int, default=64, help="search list size of the exact greedy_search (C4 'beam 64')")
-    ap.add_argument("--graph-sweep", default="64:4,128:4,256:4", help="L:W variants of the RabitQ beam traversal, cheapest first; the headline is the first with recall@10 >= --recall-target")
+    ap.add_argument("--graph-sweep", default="64:4,128:4,256:4,512:4", help="L:W variants of the RabitQ beam traversal, cheapest first; the headline is the first with recall@10 >= --recall-target")
     ap.add_argument("--recall-target", type=float, default=0.9)
     ap.add_argument("--graph-data", default="families", choices=sorted(GRAPH_DATA_NOTE))
     ap.add_argument("--cpu-sample-graph-rows", type=int, default=1_000_000, help="rows of the separate index the CPU graph baseline runs on")
