@@ -1,7 +1,7 @@
 """numpy restatement of diskann/rabitq.py:8-48 -- TEST INFRASTRUCTURE ONLY (tests/ and bench.py's cpu_baseline).
 
-PARITY UNPINNED: the script is an experiment that was never wired into the Rust binaries and ships no expected outputs
-(its inputs embeddings.bin / query.bin are git-ignored).  It is the only RabitQ definition in the tree, so it is restated
+PINNED TO AN EXECUTION OF THE REFERENCE: tests/golden/make_rabitq_golden.py runs the unmodified script (runpy) on seeded inputs and
+tests/test_rabitq_reference.py holds this restatement to what it printed (sign bits exact, floats to 2e-6).  It is restated
 line for line: centre by the dataset mean (:14-16), normalise and keep the norm (:17), P = first `output_dims` rows of a
 random orthogonal matrix (:22-28), code = sign(P o_hat) (:30-33), dots = <o_bar, P o_hat> with o_bar = +-1/sqrt(n_dims)
 (:34-35), estimate = |o| * <o_bar, P q> * dots + <mean, q> (:42-48).
