@@ -405,17 +405,82 @@ struct BeamArgs {
     float rq_scale;           // 1 / sqrt(n_dims), rounded to f32 on the host
 };
 
-// RabitQ estimate straight from the sign code, no tables (diskann/rabitq.py:42-48): lane l holds (P q)[16l .. 16l+15] and the
-// 16 sign bits of outputs 16l .. 16l+15 (bit i of byte b = output 8b + i); the signed sum runs in bit order per lane, then
-// an xor butterfly (16, 8, 4, 2, 1) -- every lane ends with the same f32.  One 64-byte coalesced request per candidate.
-static constexpr int kRqPerLane = 16;   // output_dims = 512
-__device__ __forceinline__ float rabitq_signed_sum(const float (&qt)[kRqPerLane], uint32_t bits16) {
-    float t = 0.f;
+// RabitQ estimate for the traversal, straight from the 64-byte sign code (diskann/rabitq.py:42-48) in the integer form of the
+// RabitQ paper (arXiv 2405.12497, the paper rabitq.py cites, section 3.3): the query side P q is quantised once per query to
+// B_q = 8 bit unsigned integers  qu_i = rint((Pq_i - vmin) / delta),  delta = (vmax - vmin) / 255,  and kept as 8 bit planes of
+// 512 bits; then  sum_i (+-) Pq_i  ~  vmin * (2 popc(code) - 512) + delta * (2 S1 - sum_i qu_i),  S1 = sum_b 2^b popc(code & plane_b).
+// One LANE scores one candidate (16 code words x 8 planes of AND + POPC), 32 candidates per pass, no shuffles, and the sum is an
+// exact integer -- independent of any summation order, so the CPU oracle restates it trivially (oracle/mse_oracle.c::rabitq_int_sum).
+// The quantisation adds ~1e-4 absolute to an estimate whose own noise is ~5e-2 (tests/test_rabitq_reference.py bounds it at 1e-3
+// against the script's f64 result); mse_rabitq_estimate, the codec entry point, stays the script's float formula.
+static constexpr int kRqBits = 8;       // B_q
+static constexpr int kRqWords = 16;     // output_dims = 512 sign bits = 16 words
+static constexpr int kRqPlaneWords = kRqWords * kRqBits;   // u32 [word][plane]
+
+struct RqQuery {
+    float vmin, delta;
+    int qsum;
+};
+
+// whole warp: quantise (P q)[0..512) and write the planes to shared memory (planes[w * 8 + b], bit j = bit b of qu[32 w + j])
+__device__ __forceinline__ RqQuery rq_quantize_query(const float *__restrict__ qt, uint32_t *planes, int lane) {
+    const unsigned full = 0xffffffffu;
+    float v[kRqWords];
+    float lo = INFINITY, hi = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < kRqPerLane; j++) t += ((bits16 >> j) & 1u) ? qt[j] : -qt[j];
+    for (int w = 0; w < kRqWords; w++) {
+        v[w] = qt[32 * w + lane];
+        lo = fminf(lo, v[w]);
+        hi = fmaxf(hi, v[w]);
+    }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    return t;
+    for (int o = 16; o; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(full, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(full, hi, o));
+    }
+    const float range = hi - lo;
+    const float inv = range > 0.f ? 255.0f / range : 0.f;
+    int sum = 0;
+#pragma unroll
+    for (int w = 0; w < kRqWords; w++) {
+        int u = __float2int_rn((v[w] - lo) * inv);
+        u = min(max(u, 0), 255);
+        sum += u;
+#pragma unroll
+        for (int b = 0; b < kRqBits; b++) {
+            const uint32_t word = __ballot_sync(full, (u >> b) & 1);
+            if (lane == 0) planes[w * kRqBits + b] = word;
+        }
+    }
+    sum = __reduce_add_sync(full, sum);
+    __syncwarp();
+    return RqQuery{lo, range / 255.0f, sum};
+}
+
+// one thread: the signed sum  sum_i (+-)(P q)_i  of one 64-byte code against the planes in shared memory
+__device__ __forceinline__ float rq_signed_sum(const uint32_t *planes, const uint4 *__restrict__ code, const RqQuery &rq) {
+    uint32_t acc[kRqBits];
+#pragma unroll
+    for (int b = 0; b < kRqBits; b++) acc[b] = 0;
+    uint32_t pc = 0;
+#pragma unroll
+    for (int v4 = 0; v4 < kRqWords / 4; v4++) {
+        const uint4 c = __ldg(code + v4);
+        const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const uint4 p0 = *reinterpret_cast<const uint4 *>(planes + (v4 * 4 + t) * kRqBits);
+            const uint4 p1 = *reinterpret_cast<const uint4 *>(planes + (v4 * 4 + t) * kRqBits + 4);
+            acc[0] += __popc(cw[t] & p0.x); acc[1] += __popc(cw[t] & p0.y); acc[2] += __popc(cw[t] & p0.z); acc[3] += __popc(cw[t] & p0.w);
+            acc[4] += __popc(cw[t] & p1.x); acc[5] += __popc(cw[t] & p1.y); acc[6] += __popc(cw[t] & p1.z); acc[7] += __popc(cw[t] & p1.w);
+            pc += __popc(cw[t]);
+        }
+    }
+    uint32_t s1 = 0;
+#pragma unroll
+    for (int b = 0; b < kRqBits; b++) s1 += acc[b] << b;
+    const int isum = 2 * (int)s1 - rq.qsum, csum = 2 * (int)pc - 32 * kRqWords;
+    return fmaf(rq.delta, (float)isum, rq.vmin * (float)csum);
 }
 __device__ __forceinline__ long long rabitq_score(float signed_sum, float rq_scale, float code_scale, float bias) {
     return fast_dot_fix(fmaf(rq_scale * signed_sum, code_scale, bias));
@@ -452,6 +517,8 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
     const uint32_t hmask = hcap - 1, vmask = vcap - 1;
     __shared__ uint32_t fill_adj, fill_vis;
     __shared__ uint32_t pts[64];
+    __shared__ __align__(16) uint32_t rq_planes[kRqPlaneWords];
+    __shared__ RqQuery rq_shared;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lut_n = ba.M * ba.C;
 
@@ -463,10 +530,11 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
         }
         for (uint32_t i = threadIdx.x; i < hcap + vcap; i += blockDim.x) hadj[i] = kEmpty;
         for (uint32_t i = threadIdx.x; i < g.d; i += blockDim.x) s.q[i] = __half2float(queries[(size_t)qi * g.d + i]);
-        float qt[kRqPerLane];
         if (ba.qtm) {
-#pragma unroll
-            for (int j = 0; j < kRqPerLane; j++) qt[j] = ba.qtm[(size_t)qi * (ba.rq_O + 1) + kRqPerLane * lane + j];
+            if (warp == 0) {
+                const RqQuery r = rq_quantize_query(ba.qtm + (size_t)qi * (ba.rq_O + 1), rq_planes, lane);
+                if (lane == 0) rq_shared = r;
+            }
         } else if (!ba.disable_pq) {
             for (uint32_t i = threadIdx.x; i < lut_n; i += blockDim.x) lut[i] = luts[(size_t)qi * lut_n + i];
         }
@@ -524,10 +592,11 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
                         if (lane == 0) s.pre_scores[i] = sc;
                     }
                 } else if (ba.qtm) {
-                    for (int i = warp; i < n_pre; i += kGsWarps) {                   // one warp per candidate code
+                    const RqQuery rq = rq_shared;
+                    for (int i = threadIdx.x; i < n_pre; i += blockDim.x) {         // one thread per candidate code
                         const uint32_t id = s.pre[i];
-                        const float t = rabitq_signed_sum(qt, ((const uint16_t *)(ba.codes + (size_t)id * ba.M))[lane]);
-                        if (lane == 0) s.pre_scores[i] = rabitq_score(t, ba.rq_scale, ba.code_scale[id], code_bias_q);
+                        const float t = rq_signed_sum(rq_planes, (const uint4 *)(ba.codes + (size_t)id * ba.M), rq);
+                        s.pre_scores[i] = rabitq_score(t, ba.rq_scale, ba.code_scale[id], code_bias_q);
                     }
                 } else {
                     for (int i = threadIdx.x; i < n_pre; i += blockDim.x) {        // asymmetric_dot_product vector.rs:387-405
@@ -593,14 +662,27 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
 
 // ------------------------------------------------------------------ beam search over RabitQ codes, one WARP per query
 //
-// Same traversal as k_beam_search (query_disk_index.rs:144-212) in the warp-per-query schedule of k_greedy_search_wq: the W
-// expanded nodes of an iteration are scored exactly two rows per pass (their scores do not depend on the inserts in between),
-// candidates are ranked by the RabitQ estimate computed straight from their 64-byte sign codes with (P q) in registers.
-// No per-query table exists anywhere, so a warp's state is ~7 KB of shared memory and 24-32 queries run per SM.
+// Same traversal as k_beam_search (query_disk_index.rs:144-212) in the warp-per-query schedule of k_greedy_search_wq.  One beam
+// iteration = the W popped nodes:
+//   1. their exact scores, two rows per pass (they do not depend on anything below);
+//   2. node by node (the order fixes which duplicate wins): adjacency list -> visited_adjacent set -> the fresh ids are appended
+//      to ONE candidate array for the whole iteration (ids of node a, then node b, ...);
+//   3. the candidates are scored 32 at a time, one LANE per candidate (rq_signed_sum: 64-byte code, AND + POPC against the
+//      query's bit planes), all code gathers of a pass in flight together; the score stays in the lane's registers;
+//   4. a ballot drops the candidates a full list would reject (lib.rs:118) and the survivors are inserted in candidate order --
+//      exactly the sequence of NeighbourBuffer::insert calls the reference makes.
+// No per-query table exists in any memory, so a warp's state is ~8 KB of shared memory.
 
 __host__ __device__ static size_t bq_warp_bytes(uint32_t L, uint32_t stride, uint32_t d, uint32_t W) {
-    size_t o = (size_t)(L + 1) * 8 + (size_t)stride * 8 + (size_t)W * 8 + (size_t)d * 4 + (size_t)(L + 1) * 4 + (size_t)stride * 4 + (size_t)W * 4 + (L + 1);
+    size_t o = (size_t)(L + 1) * 8 + (size_t)W * 8 + (size_t)d * 4 + (size_t)kRqPlaneWords * 4 + (size_t)(L + 1) * 4 + (size_t)W * stride * 4 +
+               (size_t)W * 4 + (L + 1);
     return (o + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ long long shfl_ll(long long v, int src) {
+    const unsigned full = 0xffffffffu;
+    const int lo = __shfl_sync(full, (int)(unsigned long long)v, src), hi = __shfl_sync(full, (int)((unsigned long long)v >> 32), src);
+    return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo);
 }
 
 template <int NC2>
@@ -612,13 +694,13 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t S = g.stride;
     uint8_t *base = smem_raw + (size_t)warp * bq_warp_bytes(L, S, g.d, W);
-    long long *nb_scores = (long long *)base;
-    long long *pre_scores = nb_scores + (L + 1);
-    long long *pt_scores = pre_scores + S;
-    float *qs = (float *)(pt_scores + W);
+    uint32_t *planes = (uint32_t *)base;                       // first: read as uint4
+    long long *nb_scores = (long long *)(planes + kRqPlaneWords);
+    long long *pt_scores = nb_scores + (L + 1);
+    float *qs = (float *)(pt_scores + W);                      // 8-byte aligned: read as float2
     uint32_t *nb_ids = (uint32_t *)(qs + g.d);
     uint32_t *pre = nb_ids + (L + 1);
-    uint32_t *pts = pre + S;
+    uint32_t *pts = pre + (size_t)W * S;
     uint8_t *nb_vis = (uint8_t *)(pts + W);
     const uint32_t gw = blockIdx.x * kWqWarps + warp, nw = gridDim.x * kWqWarps;
     uint32_t *hadj = htabs + (size_t)gw * (hcap + vcap), *hvis = hadj + hcap;
@@ -637,9 +719,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
             for (uint32_t i = lane; i < (hcap + vcap) / 4; i += 32) t4[i] = e4;   // both tables
         }
         for (uint32_t c = lane; c < g.d; c += 32) qs[c] = __half2float(queries[(size_t)qi * g.d + c]);
-        float qt[kRqPerLane];
-#pragma unroll
-        for (int j = 0; j < kRqPerLane; j++) qt[j] = ba.qtm[(size_t)qi * (ba.rq_O + 1) + kRqPerLane * lane + j];
+        const RqQuery rq = rq_quantize_query(ba.qtm + (size_t)qi * (ba.rq_O + 1), planes, lane);
         const float bias = ba.qtm[(size_t)qi * (ba.rq_O + 1) + ba.rq_O];
         const float *scales = desc_scales ? desc_scales + (size_t)qi * ba.n_desc : nullptr;
         __syncwarp();
@@ -667,6 +747,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
                 if (lane == 0) { pt_scores[i] = s0; pt_scores[j] = s1; }
             }
             __syncwarp();
+            int n_pre = 0;
             for (uint32_t b = 0; b < np; b++) {
                 const uint32_t id = pts[b];
                 long long sc = pt_scores[b];
@@ -687,7 +768,6 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
                 // out-neighbours not seen as a neighbour before, first occurrence first
                 const uint32_t dgl = g.deg[id];
                 const uint32_t *nbrs = g.adj + (size_t)id * S;
-                int n_pre = 0;
                 for (uint32_t b0 = 0; b0 < S; b0 += 32) {
                     const uint32_t i = b0 + lane;
                     const uint32_t rawid = i < S ? nbrs[i] : kEmpty;                  // issued before the degree is known
@@ -701,39 +781,32 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
                     const unsigned m = __ballot_sync(full, ins);
                     if (ins) pre[n_pre + __popc(m & ((1u << lane) - 1))] = nid;
                     n_pre += __popc(m);
-                    __syncwarp();
                 }
-                fill_adj += n_pre;
-                // RabitQ estimates, four codes in flight
-                for (int i = 0; i < n_pre; i += 4) {
-                    uint32_t bits[4], cid[4];
-                    float csc[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        cid[u] = pre[min(i + u, n_pre - 1)];
-                        bits[u] = ((const uint16_t *)(ba.codes + (size_t)cid[u] * ba.M))[lane];
-                        csc[u] = ba.code_scale[cid[u]];
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const float t = rabitq_signed_sum(qt, bits[u]);
-                        if (lane == 0 && i + u < n_pre) pre_scores[i + u] = rabitq_score(t, ba.rq_scale, csc[u], bias);
-                    }
-                }
-                __syncwarp();
-                if (ba.n_desc) {
-                    for (int i = lane; i < n_pre; i += 32) pre_scores[i] += descriptor_product(ba, scales, pre[i]);   // :202
-                    __syncwarp();
+            }
+            fill_adj += n_pre;
+            pq_cmps += n_pre;
+            __syncwarp();
+            // candidates of the whole iteration, 32 per pass: estimate in the lane, filter, ordered inserts
+            for (int c0 = 0; c0 < n_pre; c0 += 32) {
+                const int i = c0 + lane;
+                const bool have = i < n_pre;
+                const uint32_t cid = have ? pre[i] : 0u;
+                long long cs = 0;
+                if (have) {
+                    const float t = rq_signed_sum(planes, (const uint4 *)(ba.codes + (size_t)cid * ba.M), rq);
+                    cs = rabitq_score(t, ba.rq_scale, ba.code_scale[cid], bias);
+                    if (ba.n_desc) cs += descriptor_product(ba, scales, cid);        // :202
                 }
                 const bool full0 = nb.len == nb.cap;
                 const long long last0 = full0 ? nb.scores[nb.len - 1] : 0;
-                for (int i = 0; i < n_pre; i++) {
-                    const long long cs = pre_scores[i];
-                    if (!(full0 && last0 > cs)) nb_insert(nb, pre[i], cs, lane);
+                unsigned m = __ballot_sync(full, have && !(full0 && last0 > cs));    // lib.rs:118 against the tail as it is now (it only grows)
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    nb_insert(nb, __shfl_sync(full, cid, src), shfl_ll(cs, src), lane);
                 }
-                pq_cmps += n_pre;
-                __syncwarp();
             }
+            __syncwarp();
         }
         const uint32_t m = min(n_out, out.cap);
         if (lane == 0) {
@@ -744,16 +817,33 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
         }
         __syncwarp();
         if (out.topk) {
+            // best topk of the visit list under (score desc, visit order asc) -- the stable sort of :303 -- by repeated selection:
+            // round r picks the largest element strictly below the previous pick
             const uint32_t *vi = out.ids + (size_t)qi * out.cap;
             const long long *vs = out.scores + (size_t)qi * out.cap;
-            for (uint32_t i = lane; i < m; i += 32) {
-                const long long si = vs[i];
-                uint32_t rank = 0;
-                for (uint32_t j = 0; j < m; j++) { const long long sj = vs[j]; rank += (sj > si) || (sj == si && j < i); }
-                if (rank < out.topk) { out.top_ids[(size_t)qi * out.topk + rank] = vi[i]; out.top_scores[(size_t)qi * out.topk + rank] = si; }
+            long long prev_s = 0;
+            uint32_t prev_i = 0;
+            const uint32_t rounds = min(m, out.topk);
+            for (uint32_t r = 0; r < rounds; r++) {
+                long long best_s = 0;
+                uint32_t best_i = 0xFFFFFFFFu;
+                for (uint32_t i = lane; i < m; i += 32) {
+                    const long long si = vs[i];
+                    const bool below = r == 0 || si < prev_s || (si == prev_s && i > prev_i);
+                    if (below && (best_i == 0xFFFFFFFFu || si > best_s)) { best_s = si; best_i = i; }   // ascending i: the first maximum stays
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const long long os = shfl_ll(best_s, lane ^ o);
+                    const uint32_t oi = __shfl_xor_sync(full, best_i, o);
+                    if (oi != 0xFFFFFFFFu && (best_i == 0xFFFFFFFFu || os > best_s || (os == best_s && oi < best_i))) { best_s = os; best_i = oi; }
+                }
+                if (lane == 0) { out.top_ids[(size_t)qi * out.topk + r] = vi[best_i]; out.top_scores[(size_t)qi * out.topk + r] = best_s; }
+                prev_s = best_s;
+                prev_i = best_i;
             }
-            for (uint32_t i = m + lane; i < out.topk; i += 32) { out.top_ids[(size_t)qi * out.topk + i] = kEmpty; out.top_scores[(size_t)qi * out.topk + i] = 0; }
-            if (lane == 0) out.top_len[qi] = min(m, out.topk);
+            for (uint32_t i = rounds + lane; i < out.topk; i += 32) { out.top_ids[(size_t)qi * out.topk + i] = kEmpty; out.top_scores[(size_t)qi * out.topk + i] = 0; }
+            if (lane == 0) out.top_len[qi] = rounds;
         }
         __syncwarp();
     }
@@ -1198,7 +1288,7 @@ MSE_API int mse_search_beam_dev(mse_index *ix, const uint16_t *d_q_f16, const fl
     MSE_CHECK(use_device(ix->device));
     const uint32_t M = ix->code_size, C = d_qtm ? 0u : n_centroids;
     MSE_REQUIRE(d_qtm || C >= 1, MSE_ERR_INVALID, "search_beam_dev: n_centroids is 0");
-    MSE_REQUIRE(!d_qtm || rabitq_output_dims == 32 * kRqPerLane, MSE_ERR_UNSUPPORTED, "search_beam_dev: RabitQ traversal supports output_dims = %d", 32 * kRqPerLane);
+    MSE_REQUIRE(!d_qtm || rabitq_output_dims == 32 * kRqWords, MSE_ERR_UNSUPPORTED, "search_beam_dev: RabitQ traversal supports output_dims = %d", 32 * kRqWords);
     const uint32_t hcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * ix->graph_stride * 4);
     const uint32_t vcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * 16);
     const uint32_t cap = std::max<uint32_t>(8 * L + 64, topk);

@@ -960,22 +960,48 @@ static int64_t descriptor_product(const orc_disk_index *ix, const float *scales,
  * faithful_prebuffer != 0 reproduces :157 (the pre-buffer is cleared once per beam iteration, so later nodes
  * of a beam re-score earlier nodes' neighbours); 0 clears it per expanded node.
  */
-/* RabitQ signed sum straight from a 512-bit sign code, in the summation order of the GPU's warp: "lane" l adds its 16 terms
- * (outputs 16l .. 16l+15, bit i of byte b = output 8b + i) in bit order, then an xor butterfly over the 32 lane sums
- * (offsets 16, 8, 4, 2, 1).  f32 throughout; the order is part of the definition because f32 addition is not associative. */
-static float rabitq_direct_sum(const float *qt, const uint8_t *code) {
-    float s[32], t[32];
-    for (int l = 0; l < 32; l++) {
-        uint32_t bits = (uint32_t)code[2 * l] | ((uint32_t)code[2 * l + 1] << 8);
-        float a = 0.0f;
-        for (int j = 0; j < 16; j++) a += ((bits >> j) & 1u) ? qt[16 * l + j] : -qt[16 * l + j];
-        s[l] = a;
+/* RabitQ signed sum  sum_i (+-)(P q)_i  straight from a 512-bit sign code (bit i of byte b = output 8b + i), in the integer form the
+ * GPU traversal uses (csrc/graph.cu::rq_quantize_query / rq_signed_sum, after the RabitQ paper's query quantisation, arXiv
+ * 2405.12497 section 3.3): P q is quantised once per query to 8-bit unsigned integers qu_i = rint((Pq_i - vmin) / delta),
+ * delta = (vmax - vmin) / 255; then the sum is  vmin * (2 popc(code) - 512) + delta * (2 S1 - sum_i qu_i),  S1 = sum over set bits
+ * of qu_i.  S1 is an exact integer, so no summation order is involved; the three f32 operations below are the definition. */
+typedef struct {
+    float vmin, delta;
+    int qsum;
+    uint8_t qu[512];
+} rq_query;
+
+static void rabitq_quantize_query(const float *qt, rq_query *o) {
+    float lo = qt[0], hi = qt[0];
+    for (int i = 1; i < 512; i++) {
+        lo = fminf(lo, qt[i]);
+        hi = fmaxf(hi, qt[i]);
     }
-    for (int o = 16; o; o >>= 1) {
-        for (int l = 0; l < 32; l++) t[l] = s[l] + s[l ^ o];
-        memcpy(s, t, sizeof(s));
+    const float range = hi - lo;
+    const float inv = range > 0.0f ? 255.0f / range : 0.0f;
+    o->vmin = lo;
+    o->delta = range / 255.0f;
+    o->qsum = 0;
+    for (int i = 0; i < 512; i++) {
+        const float scaled = (qt[i] - lo) * inv;
+        long u = lrintf(scaled); /* round to nearest even, as cvt.rni */
+        if (u < 0) u = 0;
+        if (u > 255) u = 255;
+        o->qu[i] = (uint8_t)u;
+        o->qsum += (int)u;
     }
-    return s[0];
+}
+
+static float rabitq_int_sum(const rq_query *q, const uint8_t *code) {
+    int s1 = 0, pc = 0;
+    for (int i = 0; i < 512; i++)
+        if ((code[i >> 3] >> (i & 7)) & 1) {
+            s1 += q->qu[i];
+            pc++;
+        }
+    const int isum = 2 * s1 - q->qsum, csum = 2 * pc - 512;
+    const float vc = q->vmin * (float)csum;
+    return fmaf(q->delta, (float)isum, vc);
 }
 
 static size_t beam_search_impl(const orc_disk_index *ix, uint32_t start, const uint16_t *query, const float *lut,
@@ -992,6 +1018,8 @@ static size_t beam_search_impl(const orc_disk_index *ix, uint32_t start, const u
     uint64_t cmps = 0, pq_cmps = 0;
     size_t nout = 0;
     size_t M = ix->code_size;
+    rq_query rqq;
+    if (rq_qt) rabitq_quantize_query(rq_qt, &rqq);
 
     orc_nb_insert(nb, start, 0); /* :153 seeds with score 0 */
     vadj[start] = 1;
@@ -1034,7 +1062,7 @@ static size_t beam_search_impl(const orc_disk_index *ix, uint32_t start, const u
                 } else {
                     float s = 0.0f;
                     const uint8_t *code = ix->pq_codes + (size_t)t * M;
-                    if (rq_qt) s = rq_scale * rabitq_direct_sum(rq_qt, code);
+                    if (rq_qt) s = rq_scale * rabitq_int_sum(&rqq, code);
                     else for (size_t m = 0; m < M; m++) s += lut[m * ix->n_centroids + code[m]];
                     if (code_scale) s = fmaf(s, code_scale[t], code_bias); /* RabitQ estimate, rabitq.py:47-48 */
                     sc = sat_trunc_f32(s * 4294967296.0f);
@@ -1067,7 +1095,8 @@ ORC_API size_t orc_beam_search_scaled(const orc_disk_index *ix, uint32_t start, 
 }
 
 /* candidates ranked by the RabitQ estimate computed straight from the sign codes: qtm = (P q)[512] followed by <mean, q>;
- * estimate = fma(rq_scale * signed_sum, code_scale[id], <mean, q>)  (the device-pointer entry mse_search_beam_dev) */
+ * estimate = fma(rq_scale * signed_sum, code_scale[id], <mean, q>) with the integer signed sum above (the device-pointer entry
+ * mse_search_beam_dev) */
 ORC_API size_t orc_beam_search_rabitq(const orc_disk_index *ix, uint32_t start, const uint16_t *query, const float *qtm, float rq_scale,
                                       const float *code_scale, const float *desc_scales, size_t L, size_t beamwidth,
                                       uint32_t *out_ids, int64_t *out_scores, size_t out_cap, uint64_t *counts) {
@@ -1075,10 +1104,12 @@ ORC_API size_t orc_beam_search_rabitq(const orc_disk_index *ix, uint32_t start, 
                             qtm, rq_scale);
 }
 
-/* the direct RabitQ estimate for n codes (test hook: lets the CPU suite compare the summation-order-pinned f32 value with
- * the numpy restatement of rabitq.py:42-48) */
+/* the traversal's RabitQ estimate for n codes (test hook: lets the CPU suite bound the query-quantised value against the numpy
+ * restatement of rabitq.py:42-48) */
 ORC_API void orc_rabitq_direct_estimates(const float *qtm, float rq_scale, const uint8_t *codes, size_t n, const float *code_scale, float *out) {
-    for (size_t i = 0; i < n; i++) out[i] = fmaf(rq_scale * rabitq_direct_sum(qtm, codes + i * 64), code_scale[i], qtm[512]);
+    rq_query rqq;
+    rabitq_quantize_query(qtm, &rqq);
+    for (size_t i = 0; i < n; i++) out[i] = fmaf(rq_scale * rabitq_int_sum(&rqq, codes + i * 64), code_scale[i], qtm[512]);
 }
 
 /* ------------------------------------------------------------------ runtime de-duplication (src/query_disk_index.rs:99,486-529)

@@ -287,8 +287,9 @@ def test_greedy_search_batch_equals_single(oracle):
 
 
 def test_rabitq_direct_estimate_matches_numpy(oracle):
-    """The table-free RabitQ estimate the GPU traversal uses (lane-ordered f32 sums) against the numpy restatement of
-    diskann/rabitq.py:42-48 (f64): |difference| < 2e-5 for unit vectors."""
+    """The table-free RabitQ estimate the GPU traversal uses (query side quantised to 8-bit planes, integer popcount sum -- the
+    RabitQ paper's form) against the numpy restatement of diskann/rabitq.py:42-48 (f64): the quantisation costs < 5e-4 absolute
+    for unit vectors (measured: max 1.8e-4, mean 3e-5), two orders below the estimator's own noise."""
     from oracle.rabitq_np import RabitQ as NpRabitQ
     x = clustered_f16(41, 600, n_clusters=8)
     ref = NpRabitQ.train(x[:300].astype(np.float32), output_dims=512, seed=2)
@@ -301,7 +302,7 @@ def test_rabitq_direct_estimate_matches_numpy(oracle):
         qtm = np.concatenate([qt, [mq]]).astype(np.float32)
         got = oracle.rabitq_direct_estimates(qtm, np.float32(1.0 / np.sqrt(1152.0)), codes, (norms * dots).astype(np.float32))
         want = ref.approx_dot(bits, norms, dots, q[i])
-        assert np.abs(got - want).max() < 2e-5
+        assert np.abs(got - want).max() < 5e-4 and np.abs(got - want).mean() < 1e-4
 
 
 def test_robust_stitch_vs_python_model(oracle):

@@ -41,12 +41,13 @@ def test_msgpack_layout_matches_the_script():
 
 
 def test_c_oracle_direct_estimate_matches_the_script(oracle):
-    """the summation order the GPU traversal uses (oracle/mse_oracle.c::rabitq_direct_sum) against the script's f64 result"""
+    """the estimate the GPU traversal ranks candidates by (oracle/mse_oracle.c::rabitq_int_sum: query side quantised to 8 bits, exact
+    integer popcount sum) against the script's f64 result: the quantisation costs < 5e-4 absolute"""
     p64, q = G["p"].astype(np.float64), G["query0_f16"].astype(np.float64)
     qtm = np.concatenate([p64 @ q, [G["mean"].astype(np.float64) @ q]]).astype(np.float32)
     scale = (G["norms"] * G["dots"]).astype(np.float32)
     got = oracle.rabitq_direct_estimates(qtm, np.float32(1.0 / np.sqrt(1152.0)), G["qsample"], scale)
-    assert np.abs(got - G["approx_results"]).max() < 2e-5
+    assert np.abs(got - G["approx_results"]).max() < 5e-4
 
 
 @pytest.mark.gpu
@@ -78,5 +79,5 @@ def test_cuda_query_side_and_traversal_estimate_match_the_script(mse, oracle):
     want = np.concatenate([G["p"].astype(np.float64) @ G["query0_f16"].astype(np.float64), [G["mean"].astype(np.float64) @ G["query0_f16"].astype(np.float64)]])
     assert np.abs(qtm - want).max() < 2e-5
     est = oracle.rabitq_direct_estimates(qtm, np.float32(1.0 / np.sqrt(1152.0)), G["qsample"], (G["norms"] * G["dots"]).astype(np.float32))
-    assert np.abs(est - G["approx_results"]).max() < 5e-5
+    assert np.abs(est - G["approx_results"]).max() < 5e-4
     rq.close()
