@@ -302,9 +302,9 @@ class RabitQ:
         if getattr(self, "_h", None) and self._h.value:
             try:
                 lib().mse_rabitq_destroy(self._h)
-            except Exception:
+                self._h = C.c_void_p()
+            except Exception:  # interpreter shutdown
                 pass
-            self._h = C.c_void_p()
 
     __del__ = close
 
