@@ -33,52 +33,28 @@ struct NbView {
 // ---- NeighbourBuffer (lib.rs:73-155), executed by ONE warp; state scalars are kept uniform across the warp
 
 __device__ __forceinline__ void nb_insert(NbView &b, uint32_t id, long long score, int lane) {
-    const unsigned full = 0xffffffffu;
     if (b.cap == 0) return;
     if (b.len == b.cap && b.scores[b.len - 1] > score) return;                     // :118
-    // binary_search_by on the descending list: g = #entries > score, e = #entries == score
-    int g = 0, e = 0, c = 0;
-    const int nch = (b.len + 31) >> 5;
-    if (nch > 1 && nch <= 32) {
-        // lane k looks at the head of chunk k; the chunks whose head is above `score` form a prefix, and all of them but the last
-        // lie entirely above it (every entry of chunk k is >= the head of chunk k+1), so the scan starts at the last of them
-        const bool hin = lane < nch;
-        const long long h = hin ? b.scores[lane << 5] : 0;
-        const int G = __popc(__ballot_sync(full, hin && h > score));
-        c = G > 0 ? G - 1 : 0;
-        g = c << 5;
-    }
-    for (int i0 = c << 5; i0 < b.len; i0 += 32) {
+    int g = 0, e = 0;                                                              // binary_search_by on the descending list:
+    for (int i0 = 0; i0 < b.len; i0 += 32) {                                       // g = #entries > score, e = #entries == score
         const int i = i0 + lane;
         const bool in = i < b.len;
         const long long s = in ? b.scores[i] : 0;
-        const unsigned mg = __ballot_sync(full, in && s > score), me = __ballot_sync(full, in && s == score);
+        const unsigned mg = __ballot_sync(0xffffffffu, in && s > score), me = __ballot_sync(0xffffffffu, in && s == score);
         g += __popc(mg);
         e += __popc(me);
-        if ((mg | me) != full) break;                                              // sorted: everything further down is smaller
+        if ((mg | me) != 0xffffffffu) break;                                       // sorted: everything further down is smaller
     }
     const int loc = e > 0 ? g + e - 1 : g;                                         // Ok(last equal) / Err(insertion point)
     if (loc < b.len && b.ids[loc] == id) return;                                   // :127
-    // insert at loc, truncate to cap (:132-137): shift [loc, len) right by one -- groups of four chunks from the top down, all
-    // loads of a group before its stores
-    const int c_lo = loc >> 5;
-    for (int ct = (b.len - 1) >> 5; b.len > 0 && ct >= c_lo; ct -= 4) {
-        uint32_t ti[4];
-        long long ts[4];
-        uint8_t tv[4];
-        bool mv[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int i = ((ct - k) << 5) + lane;
-            mv[k] = ct - k >= c_lo && i >= loc && i < b.len && i + 1 < b.cap;
-            if (mv[k]) { ti[k] = b.ids[i]; ts[k] = b.scores[i]; tv[k] = b.vis[i]; }
-        }
+    // insert at loc, truncate to cap (:132-137): shift [loc, len) right by one, chunks from the top down
+    for (int c = (b.len - 1) >> 5; b.len > 0 && c >= (loc >> 5); c--) {
+        const int i = (c << 5) + lane;
+        const bool mv = i >= loc && i < b.len && i + 1 < b.cap;
+        uint32_t ti = 0; long long ts = 0; uint8_t tv = 0;
+        if (mv) { ti = b.ids[i]; ts = b.scores[i]; tv = b.vis[i]; }
         __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int i = ((ct - k) << 5) + lane;
-            if (mv[k]) { b.ids[i + 1] = ti[k]; b.scores[i + 1] = ts[k]; b.vis[i + 1] = tv[k]; }
-        }
+        if (mv) { b.ids[i + 1] = ti; b.scores[i + 1] = ts; b.vis[i + 1] = tv; }
         __syncwarp();
     }
     if (lane == 0) { b.ids[loc] = id; b.scores[loc] = score; b.vis[loc] = 0; }
@@ -709,8 +685,7 @@ __device__ __forceinline__ long long shfl_ll(long long v, int src) {
     return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo);
 }
 
-// kNodeGroup: expanded nodes whose adjacency lists are fetched together
-template <int NC2, int kNodeGroup>
+template <int NC2>
 __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g, BeamArgs ba, const __half *__restrict__ queries,
                                                                      const float *__restrict__ desc_scales, uint32_t nq,
                                                                      const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L, uint32_t W,
@@ -773,72 +748,39 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
             }
             __syncwarp();
             int n_pre = 0;
-            for (uint32_t b0 = 0; b0 < np; b0 += kNodeGroup) {
-                const uint32_t ng = min((uint32_t)kNodeGroup, np - b0);
-                // the group's expanded-set inserts in parallel (lane k <-> node k); a repeated id is fresh only at its first position
-                unsigned fresh_mask;
-                {
-                    const bool act = (uint32_t)lane < ng;
-                    const uint32_t pid = act ? pts[b0 + lane] : 0u;
-                    const unsigned same = __match_any_sync(full, pid) & ((1u << ng) - 1u);
-                    bool f = false;
-                    if (act && (same & ((1u << lane) - 1)) == 0) f = hs_insert_nc(hvis, vmask, pid);
-                    fresh_mask = __ballot_sync(full, f);
+            for (uint32_t b = 0; b < np; b++) {
+                const uint32_t id = pts[b];
+                long long sc = pt_scores[b];
+                if (ba.n_desc) sc += descriptor_product(ba, scales, id);             // :170
+                cmps++;
+                bool fresh_v = false;
+                if (lane == 0) fresh_v = hs_insert_nc(hvis, vmask, id);
+                fresh_v = __shfl_sync(full, fresh_v, 0);
+                fill_vis += fresh_v;
+                const bool rec = fresh_v && (!ba.has_url || ba.has_url[id]);              // :172
+                if (rec) {
+                    if (lane == 0 && n_out < out.cap) {
+                        out.ids[(size_t)qi * out.cap + n_out] = id;
+                        out.scores[(size_t)qi * out.cap + n_out] = sc;
+                    }
+                    n_out++;
                 }
-                // adjacency lists of the whole group, then the home slot of every neighbour in the visited_adjacent table: two rounds
-                // of loads for the group instead of a dependent chain per node.  A neighbour found at its home slot was seen in an
-                // earlier iteration (the snapshot predates this group's inserts); everything else takes the ordered CAS path below.
-                uint32_t raw[kNodeGroup][2], seen[kNodeGroup][2], dgs[kNodeGroup];
-                const bool pre_ok = S <= 64;
-                if (pre_ok) {
-#pragma unroll
-                    for (int k = 0; k < kNodeGroup; k++) {
-                        const uint32_t id = pts[min(b0 + k, np - 1)];
-                        dgs[k] = g.deg[id];
-                        const uint32_t *nbrs = g.adj + (size_t)id * S;
-                        raw[k][0] = (uint32_t)lane < S ? nbrs[lane] : kEmpty;
-                        raw[k][1] = 32u + lane < S ? nbrs[32 + lane] : kEmpty;
-                    }
-#pragma unroll
-                    for (int k = 0; k < kNodeGroup; k++) {
-                        seen[k][0] = __ldcg(hadj + ((raw[k][0] * 2654435761u) & hmask));
-                        seen[k][1] = __ldcg(hadj + ((raw[k][1] * 2654435761u) & hmask));
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < kNodeGroup; k++) {
-                    if ((uint32_t)k >= ng) break;
-                    const uint32_t id = pts[b0 + k];
-                    long long sc = pt_scores[b0 + k];
-                    if (ba.n_desc) sc += descriptor_product(ba, scales, id);         // :170
-                    cmps++;
-                    const bool fresh_v = (fresh_mask >> k) & 1u;
-                    fill_vis += fresh_v;
-                    const bool rec = fresh_v && (!ba.has_url || ba.has_url[id]);          // :172
-                    if (rec) {
-                        if (lane == 0 && n_out < out.cap) {
-                            out.ids[(size_t)qi * out.cap + n_out] = id;
-                            out.scores[(size_t)qi * out.cap + n_out] = sc;
-                        }
-                        n_out++;
-                    }
-                    // out-neighbours not seen as a neighbour before, first occurrence first
-                    const uint32_t dg = min(pre_ok ? dgs[k] : g.deg[id], S);
-                    const uint32_t *nbrs = g.adj + (size_t)id * S;
-                    for (uint32_t r0 = 0; r0 < dg; r0 += 32) {
-                        const uint32_t i = r0 + lane;
-                        const bool have = i < dg;
-                        uint32_t nid, home;
-                        if (pre_ok) { nid = r0 == 0 ? raw[k][0] : raw[k][1]; home = r0 == 0 ? seen[k][0] : seen[k][1]; }
-                        else { nid = have ? nbrs[i] : kEmpty; home = kEmpty; }
-                        if (!have) nid = kEmpty;
-                        const unsigned same = __match_any_sync(full, nid);
-                        bool ins = false;
-                        if (have && (same & ((1u << lane) - 1)) == 0 && !(pre_ok && home == nid)) ins = hs_insert_nc(hadj, hmask, nid);
-                        const unsigned m = __ballot_sync(full, ins);
-                        if (ins) pre[n_pre + __popc(m & ((1u << lane) - 1))] = nid;
-                        n_pre += __popc(m);
-                    }
+                // out-neighbours not seen as a neighbour before, first occurrence first
+                const uint32_t dgl = g.deg[id];
+                const uint32_t *nbrs = g.adj + (size_t)id * S;
+                for (uint32_t b0 = 0; b0 < S; b0 += 32) {
+                    const uint32_t i = b0 + lane;
+                    const uint32_t rawid = i < S ? nbrs[i] : kEmpty;                  // issued before the degree is known
+                    const uint32_t dg = min(dgl, S);
+                    if (b0 >= dg) break;
+                    const bool have = i < dg;
+                    const uint32_t nid = have ? rawid : kEmpty;
+                    const unsigned same = __match_any_sync(full, nid);
+                    bool ins = false;
+                    if (have && (same & ((1u << lane) - 1)) == 0) ins = hs_insert_nc(hadj, hmask, nid);
+                    const unsigned m = __ballot_sync(full, ins);
+                    if (ins) pre[n_pre + __popc(m & ((1u << lane) - 1))] = nid;
+                    n_pre += __popc(m);
                 }
             }
             fill_adj += n_pre;
@@ -1366,11 +1308,15 @@ MSE_API int mse_search_beam_dev(mse_index *ix, const uint16_t *d_q_f16, const fl
         // one warp per query
         const uint32_t grid = std::min<uint32_t>((nq + kWqWarps - 1) / kWqWarps, sms * 8);
         MSE_CHECK(ix->gw_htabs.ensure((size_t)grid * kWqWarps * (hcap + vcap) * 4));
-        static const int ng_env = getenv("MSE_BEAM_NODE_GROUP") ? atoi(getenv("MSE_BEAM_NODE_GROUP")) : 0;   // tuning aid
-        auto kern = ix->d == 1152 ? (ng_env == 2 ? k_beam_search_wq<18, 2> : ng_env == 1 ? k_beam_search_wq<18, 1> : k_beam_search_wq<18, 4>) : k_beam_search_wq<0, 4>;
-        MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-        kern<<<grid, kWqWarps * 32, wsmem, (cudaStream_t)stream>>>(g, ba, (const __half *)d_q_f16, ix->n_desc ? d_desc_scales : nullptr, nq, d_starts, start, L, W,
-                                                                   ix->gw_htabs.as<uint32_t>(), hcap, vcap, o);
+        if (ix->d == 1152) {
+            MSE_CUDA(cudaFuncSetAttribute(k_beam_search_wq<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            k_beam_search_wq<18><<<grid, kWqWarps * 32, wsmem, (cudaStream_t)stream>>>(g, ba, (const __half *)d_q_f16, ix->n_desc ? d_desc_scales : nullptr, nq,
+                                                                                       d_starts, start, L, W, ix->gw_htabs.as<uint32_t>(), hcap, vcap, o);
+        } else {
+            MSE_CUDA(cudaFuncSetAttribute(k_beam_search_wq<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            k_beam_search_wq<0><<<grid, kWqWarps * 32, wsmem, (cudaStream_t)stream>>>(g, ba, (const __half *)d_q_f16, ix->n_desc ? d_desc_scales : nullptr, nq,
+                                                                                      d_starts, start, L, W, ix->gw_htabs.as<uint32_t>(), hcap, vcap, o);
+        }
         MSE_LAUNCH_OK();
         return MSE_OK;
     }
