@@ -309,6 +309,12 @@ struct mse_encoder {
     size_t ev_used = 0;
     uint64_t stats[8] = {0};
     double gemm_flops = 0;
+    // CUDA graphs of the text tower's forward pass, one per small batch size: at batch 1 the ~200 launches of a forward are
+    // launch-latency bound (query traffic is batch 1: src/main.rs:899-934 embeds one text per search)
+    static constexpr int kGraphMaxBatch = 16;
+    cudaGraphExec_t text_graph[kGraphMaxBatch + 1] = {nullptr};
+    uint64_t text_graph_launches[kGraphMaxBatch + 1] = {0};
+    cudaStream_t cap_stream = nullptr;
 };
 
 namespace {
@@ -537,6 +543,9 @@ MSE_API void mse_encoder_destroy(mse_encoder *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void *p : e->allocs) cudaFree(p);
     for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
+    for (cudaGraphExec_t gx : e->text_graph)
+        if (gx) cudaGraphExecDestroy(gx);
+    if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -696,7 +705,36 @@ static int encode_text_impl(mse_encoder *e, const int32_t *ids, bool ids_on_devi
     prof_begin(e);
     const uint64_t l0 = g_launches.load();
     MSE_CUDA(cudaMemcpyAsync(e->ids_dev, ids, (size_t)batch * S * 4, ids_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-    MSE_CHECK(text_forward(e, (uint32_t)batch, layer_stop, st));
+    static const bool no_graph = getenv("MSE_NO_GRAPH") != nullptr;
+    if (layer_stop < 0 && !e->profile && batch <= mse_encoder::kGraphMaxBatch && !no_graph) {
+        // small batches: replay the whole forward pass as one CUDA graph.  The first call at a batch size runs eagerly (that also sets
+        // every kernel's attributes) and records the graph; buffers, shapes and tensor maps of a batch size never change.
+        if (!e->text_graph[batch]) {
+            MSE_CHECK(text_forward(e, (uint32_t)batch, -1, st));
+            MSE_CUDA(cudaStreamSynchronize(st));
+            if (!e->cap_stream) MSE_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+            cudaGraph_t graph = nullptr;
+            const uint64_t c0 = g_launches.load();
+            MSE_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = text_forward(e, (uint32_t)batch, -1, e->cap_stream);
+            const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+            if (rc != MSE_OK || ce != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                (void)cudaGetLastError();
+                if (rc == MSE_OK) set_error("encode_text: graph capture failed: %s", cudaGetErrorString(ce));
+                return rc != MSE_OK ? rc : MSE_ERR_CUDA;
+            }
+            e->text_graph_launches[batch] = g_launches.load() - c0;
+            const cudaError_t ie = cudaGraphInstantiate(&e->text_graph[batch], graph, 0);
+            cudaGraphDestroy(graph);
+            MSE_REQUIRE(ie == cudaSuccess, MSE_ERR_CUDA, "encode_text: cudaGraphInstantiate -> %s", cudaGetErrorString(ie));
+        } else {
+            MSE_CUDA(cudaGraphLaunch(e->text_graph[batch], st));
+            count_launch(e->text_graph_launches[batch]);      // the kernels inside the graph
+        }
+    } else {
+        MSE_CHECK(text_forward(e, (uint32_t)batch, layer_stop, st));
+    }
     e->stats[4] = g_launches.load() - l0;
     if (layer_stop >= 0)
         MSE_CUDA(cudaMemcpyAsync(out, e->x, (size_t)batch * S * D * 2, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));

@@ -104,6 +104,14 @@ int gemm_f16_tn_dev(int device, const __half *dA, const __half *dB, uint32_t M, 
         const char *bn_env = getenv("MSE_GEMM_BN");  // profiling only
         const bool allow192 = !(bn_env && atoi(bn_env) == 256);
         const char *cg_env = getenv("MSE_GEMM_CG");  // profiling only: 1 forces single-CTA tiles
+        // mid-size M (text tower at batch 3-32, MAP head): the 256 x 256 pair tiles leave most of the chip idle (M = 512, N = 1152 is 10
+        // pairs on 74); 128 x 128 single-CTA tiles give 4x the units
+        {
+            const uint32_t sms = (uint32_t)sm_count(device);
+            const uint32_t pairs = ((M + 255) / 256) * ((N + 255) / 256), t128 = ((M + 127) / 128) * ((N + 127) / 128);
+            if (pairs * 2 * 10 < sms * 6 && t128 > pairs * 2 && !(bn_env || cg_env) && force_bn == 0)
+                return launch_gemm<128, LinearEpilogueT<true>, 1>(device, dA, dB, M, N, K, lda, ldb, e2, st);
+        }
         if (!(cg_env && atoi(cg_env) == 1)) {
             // 256 x 256 pair tiles even where 192 would divide N exactly: measured 146.5 ms vs 157.4 ms of GEMM time per tower step
             if (bn_env && atoi(bn_env) == 192 && w192 < w256) return launch_gemm<192, LinearEpilogueT<true>, 2>(device, dA, dB, M, N, K, lda, ldb, e2, st);
