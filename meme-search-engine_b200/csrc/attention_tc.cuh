@@ -11,11 +11,15 @@
 //               in TMEM (double buffered).  O_j = P_j V_j: per 16 keys one N=64 (SW128, MN-major B) and one N=16 (SW32,
 //               MN-major B) tcgen05.mma into a per-block O buffer (double buffered) -- V is consumed exactly as it lies
 //               in memory ([key][dh]), no transpose.
-//   warps 2..5  softmax: thread = query row.  Reads S_j from TMEM (two passes: max, then exp2), writes P_j as fp16 into a
-//               SW128 K-major shared tile for the PV MMA, keeps the running max / sum, and folds each finished O_j into
-//               its 72 fp32 output registers with the usual rescale.  Normalises and stores fp16 at the end.
+//   softmax     FOUR warpgroups: a query tile's 128 x 128 score block is split by columns between two of them (thread = one
+//               query row x 64 keys).  Reads S_j from TMEM, exchanges the half-row maxima through shared memory, writes P_j as
+//               fp16 into a SW128 K-major shared tile for the PV MMA (each half owns one 64-key tile), keeps the running
+//               reference / its half of the row sum; O accumulates in TMEM.  Normalises and stores fp16 at the end.
 // S_{j+1} is issued before P_j V_j, so the tensor core works on the next score block while the softmax warps are busy.
-// Bound: the 128x128 exp2 per block (MUFU, 16/clk/SM) -- about 1.0 k cycles per block against 0.64 k cycles of MMA.
+// Bounds: TMEM read (64 B/clk/SM) and exp2 (MUFU, 16/clk/SM) are ~2.0 k cycles per block pair each; with two warpgroups (the
+// r01 kernel) the ~850 ALU instructions per warp and block issued at ~0.45 IPC per scheduler (2 softmax warps each) and set the
+// pace at ~4 k cycles (ablation r02: the kernel took the same time with the TMEM loads, ex2, MMAs and TMA all switched off).
+// Four warps per scheduler hide that latency.
 #pragma once
 #include "ptx.cuh"
 #include <cuda_fp16.h>
@@ -26,8 +30,9 @@ namespace attn_tc {
 static constexpr int kBM = 128;          // query rows per tile; a work item is TWO tiles (256 rows) sharing every K/V block
 static constexpr int kBN = 128;          // keys per block
 static constexpr int kDH = 72;
-static constexpr int kThreads = 384;     // warps 0-3: softmax group A, 4-7: softmax group B, 8: TMA, 9/10: MMA issuers (tile A/B), 11: idle
-static constexpr int kKVStages = 3;
+static constexpr int kThreads = 640;     // warps 0-7: softmax tile A (0-3 keys 0-63, 4-7 keys 64-127), 8-15: tile B, 16: TMA, 17/18: MMA issuers (A/B), 19: idle
+static constexpr int kSoftmaxWarps = 16;
+static constexpr int kKVStages = 2;
 static constexpr uint32_t kT64 = kBM * 128;   // [128 rows][64 halfs] SW128 tile bytes
 static constexpr uint32_t kT16 = kBM * 32;    // [128 rows][16 halfs] SW32 tile bytes
 static constexpr uint32_t kQBytes = 2 * (kT64 + kT16);      // both query tiles
@@ -37,7 +42,8 @@ static constexpr uint32_t kPBytes = 2 * kT64;               // 128 keys = two 64
 static constexpr uint32_t kOffQ = 0;
 static constexpr uint32_t kOffKV = kOffQ + kQBytes;                     // 40960
 static constexpr uint32_t kOffP = kOffKV + kKVStages * kKVBytes;        // + 122880
-static constexpr uint32_t kOffBar = kOffP + 2 * kPBytes;                // + 65536 = 229376
+static constexpr uint32_t kOffX = kOffP + 2 * kPBytes;                  // exchange: f32 [2 tiles][3 slots (max even / max odd / row sum)][2 halves][128 rows] = 6 KB
+static constexpr uint32_t kOffBar = kOffX + 6144;
 static constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;
 static constexpr uint32_t kTmemCols = 512;
 static constexpr uint32_t kTmS = 0, kTmO = 256;  // S_A @0, S_B @128, O_A @256, O_B @384
@@ -109,7 +115,7 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (warp == 8 && lane == 0) {
+    if (warp == kSoftmaxWarps && lane == 0) {
         ptx::prefetch_tensormap(&tm64);
         ptx::prefetch_tensormap(&tm16);
         ptx::mbar_init(q_full, 1);
@@ -117,14 +123,14 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
         for (int i = 0; i < kKVStages; i++) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 2); }
         for (int i = 0; i < 2; i++) {
             ptx::mbar_init(&s_full[i], 1);
-            ptx::mbar_init(&s_empty[i], 128);
-            ptx::mbar_init(&p_full[i], 128);
+            ptx::mbar_init(&s_empty[i], 256);
+            ptx::mbar_init(&p_full[i], 256);
             ptx::mbar_init(&o_full[i], 1);
-            ptx::mbar_init(&o_empty[i], 128);
+            ptx::mbar_init(&o_empty[i], 256);
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 9) {
+    if (warp == kSoftmaxWarps + 1) {
         ptx::tmem_alloc(tmem_slot, kTmemCols);
         ptx::tmem_relinquish();
     }
@@ -135,9 +141,9 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
     const int nb = p.n_blocks;
 
     // register budget: the two softmax groups need their 128-score row in registers; the TMA / MMA group needs almost none
-    if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == 8) {
+    if (warp >= kSoftmaxWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == kSoftmaxWarps) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t item_n = 0, kv_n = 0;
@@ -164,12 +170,12 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                 }
             }
         }
-    } else if (warp == 9 || warp == 10) {
+    } else if (warp == kSoftmaxWarps + 1 || warp == kSoftmaxWarps + 2) {
         // ------------------------------------------------------------ MMA issuers: warp 9 drives query tile A, warp 10 tile B.
         // The MMAs of this kernel are small (N = 128 / 64 / 16), so the instruction stream of the issuing thread -- not the
         // tensor pipe -- sets the pace: two issuers run in parallel and every descriptor is a precomputed base plus a constant.
         if (lane == 0) {
-            const uint32_t t = warp - 9;
+            const uint32_t t = warp - (kSoftmaxWarps + 1);
             constexpr uint32_t idesc_s = ptx::umma_idesc_f16(kBM, kBN, 0);
             constexpr uint32_t idesc_o64 = idesc_f16_bmn(kBM, 64);
             constexpr uint32_t idesc_o16 = idesc_f16_bmn(kBM, 16);
@@ -234,59 +240,65 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
         }
     }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-        // ------------------------------------------------------------ softmax / output groups (thread = query row)
-        // TMEM -> register bandwidth (64 B/clk/SM) is the scarce resource, so every score is read exactly once: the thread
-        // keeps its whole 128-key row in registers.  The output accumulates in TMEM across key blocks; it is rescaled in
-        // place only when the running max has grown by more than 2^8 since the reference the P tiles are expressed in
-        // (P <= 256 fits fp16 comfortably), which after the first block or two almost never happens.
-        const uint32_t t = warp >> 2;  // query tile owned by this group
-        const uint32_t quad = warp & 3;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // ------------------------------------------------------------ softmax / output groups (thread = query row x 64 keys)
+        // Every score is read from TMEM exactly once: the thread keeps its 64-key half row in registers.  The output accumulates in
+        // TMEM across key blocks; it is rescaled in place only when the running max has grown by more than 2^8 since the reference
+        // the P tiles are expressed in (P <= 256 fits fp16 comfortably), which after the first block or two almost never happens.
+        const uint32_t t = warp >> 3;          // query tile owned by this group of eight warps
+        const uint32_t hf = (warp >> 2) & 1;   // which 64 keys of a block (and which 40 output columns)
+        const uint32_t quad = warp & 3;        // TMEM lane quadrant = warp id % 4
         const uint32_t row = quad * 32 + lane;
         const uint32_t lane_base = (quad * 32) << 16;
         const float sc = p.scale_log2e;
-        const uint32_t ts = tmem_base + lane_base + kTmS + t * kBN;
-        const uint32_t to = tmem_base + lane_base + kTmO + t * 128;
-        uint8_t *pt = smem + kOffP + t * kPBytes + row * 128;
+        const uint32_t ts = tmem_base + lane_base + kTmS + t * kBN + hf * 64;
+        const uint32_t to = tmem_base + lane_base + kTmO + t * 128 + hf * 40;
+        uint8_t *pt = smem + kOffP + t * kPBytes + hf * kT64 + row * 128;      // this half's 64-key SW128 tile
+        float *xch = (float *)(smem + kOffX) + t * 768;                        // [slot][half][row]
+        const uint32_t bar_id = 1 + t;                                         // named barrier of the tile's 256 threads
         uint32_t blk_n = 0, item_n = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, item_n++) {
             const int qi = item % p.q_items, bh = item / p.q_items, h = bh % p.H, b = bh / p.H;
-            float m_ref = -INFINITY;  // reference max the P tiles / O / l are expressed against
-            float l_run = 0.f;
+            float m_ref = -INFINITY;  // reference max the P tiles / O / l are expressed against (identical in both halves)
+            float l_run = 0.f;        // this half's part of the row sum
             for (int j = 0; j < nb; j++) {
                 const uint32_t bn = blk_n + j;
                 ptx::mbar_wait(&s_full[t], bn & 1);
                 ptx::tc_fence_after();
-                uint32_t v[kBN];
-#pragma unroll
-                for (int c = 0; c < kBN / 32; c++) ptx::tmem_ld_32x32(ts + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+                uint32_t v[64];
+                ptx::tmem_ld_32x32(ts, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                ptx::tmem_ld_32x32(ts + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&s_empty[t]);  // the score buffer can take block j+1 while we work from registers
-                const int kvalid = p.S - j * kBN;   // keys of this block that exist (>= 1); only the last block is partial
-                if (kvalid < kBN) {                 // warp-uniform
+                const int kvalid = p.S - j * kBN - (int)hf * 64;   // keys of this half block that exist; only the last block is partial
+                if (kvalid < 64) {                  // warp-uniform
 #pragma unroll
-                    for (int i = 0; i < kBN; i++) v[i] = (i < kvalid) ? v[i] : 0xff800000u;  // -inf
+                    for (int i = 0; i < 64; i++) v[i] = (i < kvalid) ? v[i] : 0xff800000u;  // -inf
                 }
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < kBN; i += 4) {
+                for (int i = 0; i < 64; i += 4) {
                     mx0 = fmaxf(mx0, __uint_as_float(v[i]));
                     mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
                     mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
                     mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
                 }
-                const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+                const float m_half = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                float *xb = xch + (bn & 1) * 256;
+                xb[hf * 128 + row] = m_half;
+                ptx::named_bar_sync(bar_id, 256);
+                const float m_blk = fmaxf(m_half, xb[(hf ^ 1) * 128 + row]) * sc;   // both halves compute the same value
                 const bool grow = m_blk > m_ref + 8.0f;  // also true on the first block (m_ref = -inf)
                 const float f = grow ? ex2_approx(m_ref - m_blk) : 1.0f;  // rescale of O and l if the reference moves
                 if (grow) m_ref = m_blk;
                 const float neg_m = -m_ref;
-                // all 128 exponentials first, packed to fp16 in registers: none of this needs the P buffer or O, so it
-                // overlaps the P V MMAs of the previous block
-                uint32_t pk[kBN / 2];
+                // the 64 exponentials first, packed to fp16 in registers: none of this needs the P buffer or O, so it overlaps the
+                // P V MMAs of the previous block
+                uint32_t pk[32];
                 float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < kBN / 2; i++) {
+                for (int i = 0; i < 32; i++) {
                     float p0 = fmaf(__uint_as_float(v[2 * i]), sc, neg_m), p1 = fmaf(__uint_as_float(v[2 * i + 1]), sc, neg_m);
                     if (!(p.debug & 1)) { p0 = ex2_approx(p0); p1 = ex2_approx(p1); }
                     rs0 += p0;
@@ -298,55 +310,57 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                     // P V of block j-1 must be complete before O is touched or the P buffer is overwritten
                     ptx::mbar_wait(&o_full[t], (bn - 1) & 1);
                     ptx::tc_fence_after();
-                    if (__any_sync(0xffffffffu, grow)) {
-                        uint32_t a[32], c2[32], d2[8];
+                    if (__any_sync(0xffffffffu, grow)) {   // same rows, same decision in both halves; each rescales its 40 columns
+                        uint32_t a[32], d2[8];
                         ptx::tmem_ld_32x32(to, a);
-                        ptx::tmem_ld_32x32(to + 32, c2);
-                        tmem_ld_32x32_x8(to + 64, d2);
+                        tmem_ld_32x32_x8(to + 32, d2);
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; i++) a[i] = __float_as_uint(__uint_as_float(a[i]) * f);
 #pragma unroll
-                        for (int i = 0; i < 32; i++) c2[i] = __float_as_uint(__uint_as_float(c2[i]) * f);
-#pragma unroll
                         for (int i = 0; i < 8; i++) d2[i] = __float_as_uint(__uint_as_float(d2[i]) * f);
                         tmem_st_32x32(to, a);
-                        tmem_st_32x32(to + 32, c2);
-                        tmem_st_32x32_x8(to + 64, d2);
+                        tmem_st_32x32_x8(to + 32, d2);
                         tmem_st_wait();
                     }
                 }
                 l_run = fmaf(l_run, f, rs0 + rs1);
-                // 128 keys = 16 chunks of 8 halfs; chunk c8 lives in 64-key SW128 tile (c8 >> 3) at slot (c8 & 7) ^ (row & 7)
+                // 64 keys = 8 chunks of 8 halfs in this half's SW128 tile: chunk c8 lives at slot c8 ^ (row & 7)
                 if (!(p.debug & 2))
 #pragma unroll
-                for (int c8 = 0; c8 < kBN / 8; c8++) {
-                    const uint32_t chunk = (uint32_t)(c8 & 7) ^ (row & 7);
-                    *(uint4 *)(pt + (c8 >> 3) * kT64 + chunk * 16) = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+                for (int c8 = 0; c8 < 8; c8++) {
+                    const uint32_t chunk = (uint32_t)c8 ^ (row & 7);
+                    *(uint4 *)(pt + chunk * 16) = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
                 }
                 // P written: make the generic-proxy stores (and the TMEM rescale) visible to the tensor core
                 ptx::tc_fence_before();
                 ptx::fence_proxy_async();
                 ptx::mbar_arrive(&p_full[t]);
             }
-            // output: O / l for this row -> out[b*S + q][h*72 .. +72)
+            // output: O / l for this row -> out[b*S + q][h*72 + hf*40 .. ), 40 columns from half 0, 32 from half 1
             ptx::mbar_wait(&o_full[t], (blk_n + nb - 1) & 1);
             ptx::tc_fence_after();
             {
-                uint32_t a[32], c2[32], d2[8];
+                uint32_t a[32], d2[8];
                 ptx::tmem_ld_32x32(to, a);
-                ptx::tmem_ld_32x32(to + 32, c2);
-                tmem_ld_32x32_x8(to + 64, d2);
+                tmem_ld_32x32_x8(to + 32, d2);
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&o_empty[t]);
+                // row sum = both halves' parts (own exchange slot: a fast thread may already be in the next item's first block)
+                float *xb = xch + 2 * 256;
+                xb[hf * 128 + row] = l_run;
+                ptx::named_bar_sync(bar_id, 256);
+                const float l_tot = hf == 0 ? l_run + xb[128 + row] : xb[row] + l_run;   // same order in both halves
                 const int qrow = (qi * 2 + (int)t) * kBM + (int)row;
                 if (qrow < p.S) {
-                    const float inv = 1.f / l_run;
-                    __half *dst = out + ((size_t)(b * p.S + qrow) * p.H + h) * kDH;
+                    const float inv = 1.f / l_tot;
+                    __half *dst = out + ((size_t)(b * p.S + qrow) * p.H + h) * kDH + hf * 40;
+                    const int nchunk = hf == 0 ? 5 : 4;   // 40 columns, or the 32 that remain of the 72
 #pragma unroll
-                    for (int c = 0; c < 9; c++) {
-                        const uint32_t *src = c < 4 ? &a[c * 8] : (c < 8 ? &c2[(c - 4) * 8] : &d2[0]);
+                    for (int c = 0; c < 5; c++) {
+                        if (c >= nchunk) break;
+                        const uint32_t *src = c < 4 ? &a[c * 8] : &d2[0];
                         uint4 u;
                         __half2 *hh = (__half2 *)&u;
 #pragma unroll
@@ -361,7 +375,7 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == kSoftmaxWarps + 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
     }
