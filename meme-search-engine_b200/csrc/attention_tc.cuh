@@ -11,15 +11,11 @@
 //               in TMEM (double buffered).  O_j = P_j V_j: per 16 keys one N=64 (SW128, MN-major B) and one N=16 (SW32,
 //               MN-major B) tcgen05.mma into a per-block O buffer (double buffered) -- V is consumed exactly as it lies
 //               in memory ([key][dh]), no transpose.
-//   softmax     FOUR warpgroups: a query tile's 128 x 128 score block is split by columns between two of them (thread = one
-//               query row x 64 keys).  Reads S_j from TMEM, exchanges the half-row maxima through shared memory, writes P_j as
-//               fp16 into a SW128 K-major shared tile for the PV MMA (each half owns one 64-key tile), keeps the running
-//               reference / its half of the row sum; O accumulates in TMEM.  Normalises and stores fp16 at the end.
+//   warps 2..5  softmax: thread = query row.  Reads S_j from TMEM (two passes: max, then exp2), writes P_j as fp16 into a
+//               SW128 K-major shared tile for the PV MMA, keeps the running max / sum, and folds each finished O_j into
+//               its 72 fp32 output registers with the usual rescale.  Normalises and stores fp16 at the end.
 // S_{j+1} is issued before P_j V_j, so the tensor core works on the next score block while the softmax warps are busy.
-// Bounds: TMEM read (64 B/clk/SM) and exp2 (MUFU, 16/clk/SM) are ~2.0 k cycles per block pair each; with two warpgroups (the
-// r01 kernel) the ~850 ALU instructions per warp and block issued at ~0.45 IPC per scheduler (2 softmax warps each) and set the
-// pace at ~4 k cycles (ablation r02: the kernel took the same time with the TMEM loads, ex2, MMAs and TMA all switched off).
-// Four warps per scheduler hide that latency.
+// Bound: the 128x128 exp2 per block (MUFU, 16/clk/SM) -- about 1.0 k cycles per block against 0.64 k cycles of MMA.
 #pragma once
 #include "ptx.cuh"
 #include <cuda_fp16.h>
@@ -30,9 +26,8 @@ namespace attn_tc {
 static constexpr int kBM = 128;          // query rows per tile; a work item is TWO tiles (256 rows) sharing every K/V block
 static constexpr int kBN = 128;          // keys per block
 static constexpr int kDH = 72;
-static constexpr int kThreads = 640;     // warps 0-7: softmax tile A (0-3 keys 0-63, 4-7 keys 64-127), 8-15: tile B, 16: TMA, 17/18: MMA issuers (A/B), 19: idle
-static constexpr int kSoftmaxWarps = 16;
-static constexpr int kKVStages = 2;
+static constexpr int kThreads = 384;     // warps 0-3: softmax group A, 4-7: softmax group B, 8: TMA, 9/10: MMA issuers (tile A/B), 11: idle
+static constexpr int kKVStages = 3;
 static constexpr uint32_t kT64 = kBM * 128;   // [128 rows][64 halfs] SW128 tile bytes
 static constexpr uint32_t kT16 = kBM * 32;    // [128 rows][16 halfs] SW32 tile bytes
 static constexpr uint32_t kQBytes = 2 * (kT64 + kT16);      // both query tiles
@@ -42,8 +37,7 @@ static constexpr uint32_t kPBytes = 2 * kT64;               // 128 keys = two 64
 static constexpr uint32_t kOffQ = 0;
 static constexpr uint32_t kOffKV = kOffQ + kQBytes;                     // 40960
 static constexpr uint32_t kOffP = kOffKV + kKVStages * kKVBytes;        // + 122880
-static constexpr uint32_t kOffX = kOffP + 2 * kPBytes;                  // exchange: f32 [2 tiles][3 slots (max even / max odd / row sum)][2 halves][128 rows] = 6 KB
-static constexpr uint32_t kOffBar = kOffX + 6144;
+static constexpr uint32_t kOffBar = kOffP + 2 * kPBytes;                // + 65536 = 229376
 static constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;
 static constexpr uint32_t kTmemCols = 512;
 static constexpr uint32_t kTmS = 0, kTmO = 256;  // S_A @0, S_B @128, O_A @256, O_B @384
@@ -88,7 +82,8 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    // volatile: the exponentials must stay between the ping-pong barriers (pure arithmetic would be free to move across them)
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
@@ -98,7 +93,8 @@ struct Params {
     int n_blocks;       // ceil(S / 128) key blocks
     int n_items;        // B * H * q_items
     float scale_log2e;
-    int debug;          // profiling only: 1 skip ex2, 2 skip P stores, 4 skip PV MMAs, 8 skip S MMAs, 16 skip K/V TMA loads
+    int debug;          // profiling only: 1 skip ex2, 2 skip P stores, 4 skip PV MMAs, 8 skip S MMAs, 16 skip K/V TMA loads, 64 no ping-pong
+    long long *trace;   // profiling only: CTA 0 records clock64() at phase boundaries, [5 roles][256] (mse_debug_attention mode bit 256)
 };
 
 // tm64: box {64, 1, 128} SWIZZLE_128B; tm16: box {16, 1, 128} SWIZZLE_32B; both over qkv viewed as [B*S][3H][72]
@@ -115,7 +111,7 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (warp == kSoftmaxWarps && lane == 0) {
+    if (warp == 8 && lane == 0) {
         ptx::prefetch_tensormap(&tm64);
         ptx::prefetch_tensormap(&tm16);
         ptx::mbar_init(q_full, 1);
@@ -123,14 +119,14 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
         for (int i = 0; i < kKVStages; i++) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 2); }
         for (int i = 0; i < 2; i++) {
             ptx::mbar_init(&s_full[i], 1);
-            ptx::mbar_init(&s_empty[i], 256);
-            ptx::mbar_init(&p_full[i], 256);
+            ptx::mbar_init(&s_empty[i], 128);
+            ptx::mbar_init(&p_full[i], 128);
             ptx::mbar_init(&o_full[i], 1);
-            ptx::mbar_init(&o_empty[i], 256);
+            ptx::mbar_init(&o_empty[i], 128);
         }
         ptx::fence_barrier_init();
     }
-    if (warp == kSoftmaxWarps + 1) {
+    if (warp == 9) {
         ptx::tmem_alloc(tmem_slot, kTmemCols);
         ptx::tmem_relinquish();
     }
@@ -139,11 +135,15 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nb = p.n_blocks;
+    int tr_n = 0;
+    auto TR = [&](int role) {
+        if (p.trace && blockIdx.x == 0 && tr_n < 256) p.trace[role * 256 + tr_n++] = clock64();
+    };
 
     // register budget: the two softmax groups need their 128-score row in registers; the TMA / MMA group needs almost none
-    if (warp >= kSoftmaxWarps) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == kSoftmaxWarps) {
+    if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 8) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t item_n = 0, kv_n = 0;
@@ -165,20 +165,20 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                     const int key0 = tok0 + j * kBN;
                     tma_load_3d(kv, &tm64, &kv_full[st], 0, p.H + h, key0);
                     tma_load_3d(kv + kT64, &tm16, &kv_full[st], 64, p.H + h, key0);
-                    tma_load_3d(kv + kT64 + kT16, &tm64, &kv_full[st], 0, 2 * p.H + h, key0);
-                    tma_load_3d(kv + 2 * kT64 + kT16, &tm16, &kv_full[st], 64, 2 * p.H + h, key0);
+                    // V as five [128 keys][16 dims] SWIZZLE_32B tiles, 4 KB apart: one MN-major B operand of N = 80 for the P V MMA
+#pragma unroll
+                    for (int c = 0; c < 5; c++) tma_load_3d(kv + kT64 + kT16 + c * kT16, &tm16, &kv_full[st], 16 * c, 2 * p.H + h, key0);
                 }
             }
         }
-    } else if (warp == kSoftmaxWarps + 1 || warp == kSoftmaxWarps + 2) {
+    } else if (warp == 9 || warp == 10) {
         // ------------------------------------------------------------ MMA issuers: warp 9 drives query tile A, warp 10 tile B.
         // The MMAs of this kernel are small (N = 128 / 64 / 16), so the instruction stream of the issuing thread -- not the
         // tensor pipe -- sets the pace: two issuers run in parallel and every descriptor is a precomputed base plus a constant.
         if (lane == 0) {
-            const uint32_t t = warp - (kSoftmaxWarps + 1);
+            const uint32_t t = warp - 9;
             constexpr uint32_t idesc_s = ptx::umma_idesc_f16(kBM, kBN, 0);
-            constexpr uint32_t idesc_o64 = idesc_f16_bmn(kBM, 64);
-            constexpr uint32_t idesc_o16 = idesc_f16_bmn(kBM, 16);
+            constexpr uint32_t idesc_o80 = idesc_f16_bmn(kBM, 80);
             // descriptor halves: lo = (addr >> 4) | LBO(1) << 16; hi = SBO >> 4 | version 1 << 14 | layout << 29
             constexpr uint32_t kHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
             constexpr uint32_t kHi32 = (256u >> 4) | (1u << 14) | (6u << 29);
@@ -193,7 +193,9 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
             auto issue_s = [&](uint32_t kvn, uint32_t bn) {
                 const uint32_t st = kvn % kKVStages, ph = (kvn / kKVStages) & 1;
                 ptx::mbar_wait(&kv_full[st], ph);
+                TR(2 + (int)t);                  // 0: K/V landed
                 ptx::mbar_wait(&s_empty[t], (bn & 1) ^ 1);
+                TR(2 + (int)t);                  // 1: S buffer free
                 ptx::tc_fence_after();
                 const uint32_t k_lo = kv_lo0 + st * (kKVBytes >> 4);
                 if (!(p.debug & 8)) {
@@ -202,25 +204,28 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                 ptx::umma_f16(d_s, d64(q2_lo, kHi32), d64(k_lo + (kT64 >> 4), kHi32), idesc_s, 1u);
                 }
                 ptx::umma_commit(&s_full[t]);
+                TR(2 + (int)t);                  // 2: S issued
             };
             // O_t += P_t(block) V(block): accumulates in TMEM across the key blocks of an item
             auto issue_pv = [&](uint32_t kvn, uint32_t bn, bool first_block, uint32_t itn) {
                 const uint32_t st = kvn % kKVStages;
                 ptx::mbar_wait(&p_full[t], bn & 1);
+                TR(2 + (int)t);                  // 3: P ready
                 if (first_block) ptx::mbar_wait(&o_empty[t], (itn & 1) ^ 1);  // previous item's output has been read out
                 ptx::tc_fence_after();
-                const uint32_t v_lo = kv_lo0 + st * (kKVBytes >> 4) + ((kT64 + kT16) >> 4), v2_lo = v_lo + (kT64 >> 4);
+                // V: five SW32 MN-major tiles [key][16 dh]; atoms of 8 keys x 32 B = 256 B follow each other along the keys (SBO = 256),
+                // the next 16 dims are the next tile (LBO = 4096): ONE N = 80 MMA per 16 keys reads P once (the r01 kernel issued an
+                // N = 64 and an N = 16 MMA, each fetching the whole P operand; the issuing thread, ~100 cycles per MMA, set the pace)
+                const uint32_t v_lo = (kv_lo0 & 0xFFFFu) + st * (kKVBytes >> 4) + ((kT64 + kT16) >> 4);
                 if (!(p.debug & 4))
 #pragma unroll
                 for (uint32_t ks = 0; ks < kBN / 16; ks++) {
                     const uint64_t pa = d64(p_lo + (ks >> 2) * (kT64 >> 4) + 2 * (ks & 3), kHi128);
                     const uint32_t accum = (!first_block || ks != 0) ? 1u : 0u;
-                    // V tile [key][64 dh] SW128 MN-major: 16 keys = 2 atoms of 8 keys x 128 B -> +2048 B per k-step
-                    ptx::umma_f16(d_o, pa, d64(v_lo + ks * (2048 >> 4), kHi128), idesc_o64, accum);
-                    // V tile [key][16 dh] SW32 MN-major: 16 keys x 32 B -> +512 B per k-step
-                    ptx::umma_f16(d_o + 64, pa, d64(v2_lo + ks * (512 >> 4), kHi32), idesc_o16, accum);
+                    ptx::umma_f16(d_o, pa, d64((v_lo + ks * (512 >> 4)) | ((kT16 >> 4) << 16), kHi32), idesc_o80, accum);   // +16 keys = 512 B
                 }
                 ptx::umma_commit(&o_full[t]);
+                TR(2 + (int)t);                  // 4: PV issued
             };
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, item_n++) {
                 ptx::mbar_wait(q_full, item_n & 1);
@@ -240,65 +245,69 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
         }
     }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-        // ------------------------------------------------------------ softmax / output groups (thread = query row x 64 keys)
-        // Every score is read from TMEM exactly once: the thread keeps its 64-key half row in registers.  The output accumulates in
-        // TMEM across key blocks; it is rescaled in place only when the running max has grown by more than 2^8 since the reference
-        // the P tiles are expressed in (P <= 256 fits fp16 comfortably), which after the first block or two almost never happens.
-        const uint32_t t = warp >> 3;          // query tile owned by this group of eight warps
-        const uint32_t hf = (warp >> 2) & 1;   // which 64 keys of a block (and which 40 output columns)
-        const uint32_t quad = warp & 3;        // TMEM lane quadrant = warp id % 4
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // ------------------------------------------------------------ softmax / output groups (thread = query row)
+        // TMEM -> register bandwidth (64 B/clk/SM) is the scarce resource, so every score is read exactly once: the thread
+        // keeps its whole 128-key row in registers.  The output accumulates in TMEM across key blocks; it is rescaled in
+        // place only when the running max has grown by more than 2^8 since the reference the P tiles are expressed in
+        // (P <= 256 fits fp16 comfortably), which after the first block or two almost never happens.
+        const uint32_t t = warp >> 2;  // query tile owned by this group
+        const uint32_t quad = warp & 3;
         const uint32_t row = quad * 32 + lane;
         const uint32_t lane_base = (quad * 32) << 16;
         const float sc = p.scale_log2e;
-        const uint32_t ts = tmem_base + lane_base + kTmS + t * kBN + hf * 64;
-        const uint32_t to = tmem_base + lane_base + kTmO + t * 128 + hf * 40;
-        uint8_t *pt = smem + kOffP + t * kPBytes + hf * kT64 + row * 128;      // this half's 64-key SW128 tile
-        float *xch = (float *)(smem + kOffX) + t * 768;                        // [slot][half][row]
-        const uint32_t bar_id = 1 + t;                                         // named barrier of the tile's 256 threads
+        const uint32_t ts = tmem_base + lane_base + kTmS + t * kBN;
+        const uint32_t to = tmem_base + lane_base + kTmO + t * 128;
+        uint8_t *pt = smem + kOffP + t * kPBytes + row * 128;
         uint32_t blk_n = 0, item_n = 0;
+        // The exponentials are MUFU-bound (16 ex2/clk/SM: a tile's 128 x 128 block is 1024 cycles when it has the unit to itself) and
+        // the rest of a block -- score load, P stores, barrier round trips -- is not.  Left alone the two tiles run in lockstep and
+        // share the MUFU in the same phase (2 x ~2500 cycles per block, phase timeline in profiles/r02_attention_timeline.md); a token
+        // passed between the two softmax groups on a pair of named barriers makes them alternate, so one tile's exponentials overlap
+        // the other tile's loads and stores.
+        const bool pingpong = !(p.debug & 64);
+        if (pingpong && t == 1) ptx::named_bar_arrive(2, 256);   // tile A goes first
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, item_n++) {
             const int qi = item % p.q_items, bh = item / p.q_items, h = bh % p.H, b = bh / p.H;
-            float m_ref = -INFINITY;  // reference max the P tiles / O / l are expressed against (identical in both halves)
-            float l_run = 0.f;        // this half's part of the row sum
+            float m_ref = -INFINITY;  // reference max the P tiles / O / l are expressed against
+            float l_run = 0.f;
             for (int j = 0; j < nb; j++) {
                 const uint32_t bn = blk_n + j;
                 ptx::mbar_wait(&s_full[t], bn & 1);
                 ptx::tc_fence_after();
-                uint32_t v[64];
-                ptx::tmem_ld_32x32(ts, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                ptx::tmem_ld_32x32(ts + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                if (row == 0) TR((int)t);        // 0: S ready
+                uint32_t v[kBN];
+#pragma unroll
+                for (int c = 0; c < kBN / 32; c++) ptx::tmem_ld_32x32(ts + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&s_empty[t]);  // the score buffer can take block j+1 while we work from registers
-                const int kvalid = p.S - j * kBN - (int)hf * 64;   // keys of this half block that exist; only the last block is partial
-                if (kvalid < 64) {                  // warp-uniform
+                if (row == 0) TR((int)t);        // 1: scores in registers
+                if (pingpong) ptx::named_bar_sync(2 + t, 256);     // wait for the MUFU token
+                const int kvalid = p.S - j * kBN;   // keys of this block that exist (>= 1); only the last block is partial
+                if (kvalid < kBN) {                 // warp-uniform
 #pragma unroll
-                    for (int i = 0; i < 64; i++) v[i] = (i < kvalid) ? v[i] : 0xff800000u;  // -inf
+                    for (int i = 0; i < kBN; i++) v[i] = (i < kvalid) ? v[i] : 0xff800000u;  // -inf
                 }
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 64; i += 4) {
+                for (int i = 0; i < kBN; i += 4) {
                     mx0 = fmaxf(mx0, __uint_as_float(v[i]));
                     mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
                     mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
                     mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
                 }
-                const float m_half = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                float *xb = xch + (bn & 1) * 256;
-                xb[hf * 128 + row] = m_half;
-                ptx::named_bar_sync(bar_id, 256);
-                const float m_blk = fmaxf(m_half, xb[(hf ^ 1) * 128 + row]) * sc;   // both halves compute the same value
+                const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
                 const bool grow = m_blk > m_ref + 8.0f;  // also true on the first block (m_ref = -inf)
                 const float f = grow ? ex2_approx(m_ref - m_blk) : 1.0f;  // rescale of O and l if the reference moves
                 if (grow) m_ref = m_blk;
                 const float neg_m = -m_ref;
-                // the 64 exponentials first, packed to fp16 in registers: none of this needs the P buffer or O, so it overlaps the
-                // P V MMAs of the previous block
-                uint32_t pk[32];
+                // all 128 exponentials first, packed to fp16 in registers: none of this needs the P buffer or O, so it
+                // overlaps the P V MMAs of the previous block
+                uint32_t pk[kBN / 2];
                 float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
+                for (int i = 0; i < kBN / 2; i++) {
                     float p0 = fmaf(__uint_as_float(v[2 * i]), sc, neg_m), p1 = fmaf(__uint_as_float(v[2 * i + 1]), sc, neg_m);
                     if (!(p.debug & 1)) { p0 = ex2_approx(p0); p1 = ex2_approx(p1); }
                     rs0 += p0;
@@ -306,61 +315,63 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                     __half2 hh = __floats2half2_rn(p0, p1);
                     pk[i] = *(uint32_t *)&hh;
                 }
+                if (pingpong) ptx::named_bar_arrive(2 + (t ^ 1), 256);   // hand the token to the other tile
+                if (row == 0) TR((int)t);        // 2: max + exps done
                 if (j > 0) {
                     // P V of block j-1 must be complete before O is touched or the P buffer is overwritten
                     ptx::mbar_wait(&o_full[t], (bn - 1) & 1);
                     ptx::tc_fence_after();
-                    if (__any_sync(0xffffffffu, grow)) {   // same rows, same decision in both halves; each rescales its 40 columns
-                        uint32_t a[32], d2[8];
+                    if (__any_sync(0xffffffffu, grow)) {
+                        uint32_t a[32], c2[32], d2[8];
                         ptx::tmem_ld_32x32(to, a);
-                        tmem_ld_32x32_x8(to + 32, d2);
+                        ptx::tmem_ld_32x32(to + 32, c2);
+                        tmem_ld_32x32_x8(to + 64, d2);
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; i++) a[i] = __float_as_uint(__uint_as_float(a[i]) * f);
 #pragma unroll
+                        for (int i = 0; i < 32; i++) c2[i] = __float_as_uint(__uint_as_float(c2[i]) * f);
+#pragma unroll
                         for (int i = 0; i < 8; i++) d2[i] = __float_as_uint(__uint_as_float(d2[i]) * f);
                         tmem_st_32x32(to, a);
-                        tmem_st_32x32_x8(to + 32, d2);
+                        tmem_st_32x32(to + 32, c2);
+                        tmem_st_32x32_x8(to + 64, d2);
                         tmem_st_wait();
                     }
                 }
+                if (row == 0) TR((int)t);        // 3: PV(j-1) done (+ rescale)
                 l_run = fmaf(l_run, f, rs0 + rs1);
-                // 64 keys = 8 chunks of 8 halfs in this half's SW128 tile: chunk c8 lives at slot c8 ^ (row & 7)
+                // 128 keys = 16 chunks of 8 halfs; chunk c8 lives in 64-key SW128 tile (c8 >> 3) at slot (c8 & 7) ^ (row & 7)
                 if (!(p.debug & 2))
 #pragma unroll
-                for (int c8 = 0; c8 < 8; c8++) {
-                    const uint32_t chunk = (uint32_t)c8 ^ (row & 7);
-                    *(uint4 *)(pt + chunk * 16) = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+                for (int c8 = 0; c8 < kBN / 8; c8++) {
+                    const uint32_t chunk = (uint32_t)(c8 & 7) ^ (row & 7);
+                    *(uint4 *)(pt + (c8 >> 3) * kT64 + chunk * 16) = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
                 }
                 // P written: make the generic-proxy stores (and the TMEM rescale) visible to the tensor core
                 ptx::tc_fence_before();
                 ptx::fence_proxy_async();
                 ptx::mbar_arrive(&p_full[t]);
+                if (row == 0) TR((int)t);        // 4: P stored
             }
-            // output: O / l for this row -> out[b*S + q][h*72 + hf*40 .. ), 40 columns from half 0, 32 from half 1
+            // output: O / l for this row -> out[b*S + q][h*72 .. +72)
             ptx::mbar_wait(&o_full[t], (blk_n + nb - 1) & 1);
             ptx::tc_fence_after();
             {
-                uint32_t a[32], d2[8];
+                uint32_t a[32], c2[32], d2[8];
                 ptx::tmem_ld_32x32(to, a);
-                tmem_ld_32x32_x8(to + 32, d2);
+                ptx::tmem_ld_32x32(to + 32, c2);
+                tmem_ld_32x32_x8(to + 64, d2);
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&o_empty[t]);
-                // row sum = both halves' parts (own exchange slot: a fast thread may already be in the next item's first block)
-                float *xb = xch + 2 * 256;
-                xb[hf * 128 + row] = l_run;
-                ptx::named_bar_sync(bar_id, 256);
-                const float l_tot = hf == 0 ? l_run + xb[128 + row] : xb[row] + l_run;   // same order in both halves
                 const int qrow = (qi * 2 + (int)t) * kBM + (int)row;
                 if (qrow < p.S) {
-                    const float inv = 1.f / l_tot;
-                    __half *dst = out + ((size_t)(b * p.S + qrow) * p.H + h) * kDH + hf * 40;
-                    const int nchunk = hf == 0 ? 5 : 4;   // 40 columns, or the 32 that remain of the 72
+                    const float inv = 1.f / l_run;
+                    __half *dst = out + ((size_t)(b * p.S + qrow) * p.H + h) * kDH;
 #pragma unroll
-                    for (int c = 0; c < 5; c++) {
-                        if (c >= nchunk) break;
-                        const uint32_t *src = c < 4 ? &a[c * 8] : &d2[0];
+                    for (int c = 0; c < 9; c++) {
+                        const uint32_t *src = c < 4 ? &a[c * 8] : (c < 8 ? &c2[(c - 4) * 8] : &d2[0]);
                         uint4 u;
                         __half2 *hh = (__half2 *)&u;
 #pragma unroll
@@ -375,7 +386,7 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == kSoftmaxWarps + 1) {
+    if (warp == 9) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
     }

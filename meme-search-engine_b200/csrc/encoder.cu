@@ -788,11 +788,31 @@ MSE_API int mse_debug_attention(int device, int B, int S, int mode, int iters, f
     ap.n_blocks = (S + attn_tc::kBN - 1) / attn_tc::kBN;
     ap.n_items = B * H * ap.q_items;
     ap.scale_log2e = (1.0f / sqrtf((float)attn::kDH)) * 1.4426950408889634f;
-    ap.debug = mode;
+    ap.debug = mode & 255;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int grid = std::min(ap.n_items, sm_count(device));
     for (int i = 0; i < 2; i++) attn_tc::k_mha_tc<<<grid, attn_tc::kThreads, attn_tc::kSmemBytes>>>(tm64, tm16, out, ap);
+    if (mode & 256) {
+        // phase timeline of CTA 0 (clock64 at the kernel's trace points), printed as cycles since the first stamp
+        long long *tr = nullptr;
+        MSE_CUDA(cudaMalloc(&tr, 5 * 256 * 8));
+        cudaMemset(tr, 0, 5 * 256 * 8);
+        ap.trace = tr;
+        attn_tc::k_mha_tc<<<grid, attn_tc::kThreads, attn_tc::kSmemBytes>>>(tm64, tm16, out, ap);
+        std::vector<long long> h(5 * 256);
+        cudaMemcpy(h.data(), tr, h.size() * 8, cudaMemcpyDeviceToHost);
+        cudaFree(tr);
+        ap.trace = nullptr;
+        long long t0 = 0;
+        for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+        const char *names[4] = {"softmax_A", "softmax_B", "issuer_A", "issuer_B"};
+        for (int r = 0; r < 4; r++) {
+            printf("trace %s:", names[r]);
+            for (int i = 0; i < 100 && h[r * 256 + i]; i++) printf(" %lld", h[r * 256 + i] - t0);
+            printf("\n");
+        }
+    }
     cudaEventRecord(e0);
     for (int i = 0; i < iters; i++) attn_tc::k_mha_tc<<<grid, attn_tc::kThreads, attn_tc::kSmemBytes>>>(tm64, tm16, out, ap);
     cudaEventRecord(e1);

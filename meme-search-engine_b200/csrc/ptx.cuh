@@ -84,6 +84,10 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// arrive without waiting (the other half of a producer/consumer pair on a named barrier)
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // createpolicy encodings as CUTLASS uses them (TMA::CacheHintSm90)
 static constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 static constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
