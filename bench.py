@@ -611,23 +611,20 @@ def main():
         def build_index(lo_, hi_, seed_off):
             vl_ = dk.VectorList(D, device=local_rank, id_base=lo_)
             vl_.reserve(hi_ - lo_)
-            head = None
             for c0 in range(lo_ // data.chunk * data.chunk, hi_, data.chunk):
                 xb = data.rows(c0, data.chunk)
                 a, b = max(lo_, c0) - c0, min(hi_, c0 + data.chunk) - c0
                 xs = xb[a:b].contiguous()
                 vl_.add_f16_dev(xs.data_ptr(), b - a, stream)
-                if head is None:
-                    head = xs[: min(b - a, 100_000)].float().mean(dim=0).cpu().numpy()    # RabitQ "training": the dataset mean (rabitq.py:14)
                 del xb, xs
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             dk.random_fill_graph(vl_, R, seed=1 + seed_off)
             med_ = dk.medioid(vl_)
             bst_ = dk.build_graph(vl_, med_, dk.IndexBuildConfig(r=R, l=192, maxc=750), seed=7 + seed_off)
-            return vl_, med_, bst_, time.perf_counter() - t0, head
+            return vl_, med_, bst_, time.perf_counter() - t0
 
-        vl, med, bst, build_s, x_head = build_index(lo, hi, rank)
+        vl, med, bst, build_s = build_index(lo, hi, rank)
         q16 = data.queries(nq, n_total)
         q32 = q16.float().contiguous()
         q16_host = q16.cpu().pin_memory()
@@ -680,9 +677,9 @@ def main():
                                "traffic_note": f"ratio from the ncu capture {trg_src} (1 M rows): every gathered row leaves HBM once"}}
 
         # ---- C4 proper: RabitQ codes for the frontier, exact rows for expanded nodes (query_disk_index.rs:144-212), beam W
-        gm = torch.Generator(device=dev).manual_seed(11)
-        P = torch.linalg.qr(torch.randn((D, D), generator=gm, device=dev))[0][:512].contiguous()
-        rq = dk.RabitQ(x_head, P.cpu().numpy(), device=local_rank)
+        t0 = time.perf_counter()
+        rq = dk.RabitQ.train(vl, sample_rows=100_000, output_dims=512, seed=11)   # rabitq.py:11-28 on the device: mean + random orthogonal P
+        train_s = time.perf_counter() - t0
         t0 = time.perf_counter()
         rq.encode_index(vl, 0)                                    # rows are encoded where they lie in HBM
         torch.cuda.synchronize()
@@ -763,7 +760,7 @@ def main():
                               "kernel_ms_per_step": ms_bk, "kernel_share_of_step": ms_bk / hv["ms_per_step"], "traffic": None},
                  "sweep": {s: {kk: vv for kk, vv in v.items() if kk not in ("clocks", "bytes", "unit")} for s, v in variants.items()},
                  "greedy_exact": greedy, "greedy_clocks": gclocks,
-                 "build": {"seconds": build_s, "points_per_s": n_local / build_s, "stats": bst, "rabitq_encode_seconds": enc_s}}
+                 "build": {"seconds": build_s, "points_per_s": n_local / build_s, "stats": bst, "rabitq_train_seconds": train_s, "rabitq_encode_seconds": enc_s}}
         rq.close()
         vl.close()
         del vl
@@ -774,7 +771,7 @@ def main():
             from oracle import oracle as O
             O.build()
             n_cpu = min(args.cpu_sample_graph_rows, per_gpu) // data.chunk * data.chunk or min(args.cpu_sample_graph_rows, per_gpu)
-            svl, smed, _, sbuild_s, s_head = build_index(0, n_cpu, 100)
+            svl, smed, _, sbuild_s = build_index(0, n_cpu, 100)
             x_host = np.empty((n_cpu, D), np.float16)
             for c0 in range(0, n_cpu, data.chunk):
                 x_host[c0:c0 + data.chunk] = data.rows(c0, data.chunk)[: n_cpu - c0].cpu().numpy()
@@ -801,7 +798,7 @@ def main():
                                                                f"oracle greedy_search L={L}, OpenMP over queries",
                                                      "distances_per_query": float(o_dist.mean()), "gpu_results_bit_identical": same_g}
             # RabitQ beam on the CPU: one query per thread through the oracle's orc_beam_search_rabitq
-            srq = dk.RabitQ(s_head, P.cpu().numpy(), device=local_rank)
+            srq = dk.RabitQ.train(svl, sample_rows=100_000, output_dims=512, seed=11)
             srq.encode_index(svl, 0)
             codes_h, norms_h, dots_h = srq.quantize(x_host)
             scale_h = (norms_h * dots_h).astype(np.float32)

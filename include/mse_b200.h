@@ -265,6 +265,12 @@ void mse_pq_destroy(mse_pq *pq);
 typedef struct mse_rabitq mse_rabitq;
 int mse_rabitq_create(const float *mean, const float *transform, uint32_t n_dims, uint32_t output_dims, int device, mse_rabitq **out);
 int mse_rabitq_load(const uint8_t *msgpack, size_t len, int device, mse_rabitq **out);
+/* the script's "training" (rabitq.py:11-28) over rows already in HBM: mean of the first sample_rows rows (0 = all; the script
+ * takes 100 000) and the first output_dims rows of a random orthogonal matrix (seeded Gaussian rows orthonormalised on the device) */
+int mse_rabitq_train(mse_index *ix, uint64_t sample_rows, uint32_t output_dims, uint64_t seed, mse_rabitq **out);
+int mse_rabitq_info(const mse_rabitq *r, uint32_t out[2]); /* n_dims, output_dims */
+/* mean [n_dims], transform [output_dims][n_dims] row-major -- what rabitq.msgpack stores (rabitq.py:62-68) */
+int mse_rabitq_export(const mse_rabitq *r, float *mean, float *transform);
 /* quantize (rabitq.py:30-36): codes [n][output_dims/8] sign bits, norms [n] = |o - mean|, dots [n] = <o_bar, P o_hat> */
 int mse_rabitq_encode(mse_rabitq *r, const uint16_t *x_f16, uint64_t n, uint8_t *codes, float *norms, float *dots);
 /* approx_dot (rabitq.py:42-48) of one f32 query against n encoded vectors */

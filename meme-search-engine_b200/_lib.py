@@ -100,6 +100,9 @@ _SIGS = {
     "mse_pq_destroy": (None, [_vp]),
     "mse_rabitq_create": (_i32, [_vp, _vp, _u32, _u32, _i32, C.POINTER(_vp)]),
     "mse_rabitq_load": (_i32, [_vp, C.c_size_t, _i32, C.POINTER(_vp)]),
+    "mse_rabitq_train": (_i32, [_vp, _u64, _u32, _u64, C.POINTER(_vp)]),
+    "mse_rabitq_info": (_i32, [_vp, _vp]),
+    "mse_rabitq_export": (_i32, [_vp, _vp, _vp]),
     "mse_rabitq_encode": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "mse_rabitq_estimate": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "mse_rabitq_preprocess_query": (_i32, [_vp, _vp, _u32, _vp, _vp]),

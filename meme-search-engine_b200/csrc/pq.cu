@@ -213,6 +213,72 @@ __global__ void k_rabitq_scales(const float *__restrict__ norms, const float *__
     if (v < n) out[v] = divide ? norms[v] / dots[v] : norms[v] * dots[v];
 }
 
+// ---- RabitQ "training" (diskann/rabitq.py:11-28): dataset mean + the first output_dims rows of a random orthogonal matrix
+
+// column means of fp16 rows [n][D], f64 accumulation: block = 32 columns x 8 row lanes
+__global__ void __launch_bounds__(256) k_col_mean(const __half *__restrict__ x, uint64_t n, uint32_t D, float *__restrict__ mean) {
+    __shared__ double part[8][33];
+    const uint32_t col = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+    double acc = 0.0;
+    if (col < D)
+        for (uint64_t r = ry; r < n; r += 8) acc += (double)__half2float(x[r * D + col]);
+    part[ry][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (ry == 0 && col < D) {
+        double t = 0.0;
+        for (int i = 0; i < 8; i++) t += part[i][threadIdx.x & 31];
+        mean[col] = (float)(t / (double)n);
+    }
+}
+
+// standard normal entries from a counter-based generator (splitmix64 of seed and index, Box-Muller)
+__global__ void k_gauss_fill(float *__restrict__ g, uint64_t n, uint64_t seed) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto mix = [](uint64_t z) { z += 0x9e3779b97f4a7c15ull; z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31); };
+    const uint64_t a = mix(seed * 0x2545f4914f6cdd1dull + 2 * i), b = mix(seed * 0x2545f4914f6cdd1dull + 2 * i + 1);
+    const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740993.0), u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+    g[i] = (float)(sqrt(-2.0 * log(u1)) * cospi(2.0 * u2));
+}
+
+// one Gram-Schmidt step: rows j > i lose their component along row i.  One block per row j.
+__global__ void __launch_bounds__(256) k_mgs_step(float *__restrict__ g, uint32_t D, uint32_t i) {
+    __shared__ double red[2][8];
+    const uint32_t j = i + 1 + blockIdx.x;
+    const float *ri = g + (size_t)i * D;
+    float *rj = g + (size_t)j * D;
+    double dot = 0.0, nn = 0.0;
+    for (uint32_t k = threadIdx.x; k < D; k += blockDim.x) { const double a = ri[k]; dot += a * (double)rj[k]; nn += a * a; }
+    for (int o = 16; o; o >>= 1) { dot += __shfl_xor_sync(0xffffffffu, dot, o); nn += __shfl_xor_sync(0xffffffffu, nn, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = dot; red[1][threadIdx.x >> 5] = nn; }
+    __syncthreads();
+    dot = 0.0; nn = 0.0;
+    for (int w = 0; w < 8; w++) { dot += red[0][w]; nn += red[1][w]; }
+    const double c = nn > 0.0 ? dot / nn : 0.0;
+    for (uint32_t k = threadIdx.x; k < D; k += blockDim.x) rj[k] = (float)((double)rj[k] - c * (double)ri[k]);
+}
+
+// unit rows, written transposed: Pt[k][o] = P[o][k]
+__global__ void __launch_bounds__(256) k_normalise_transpose(const float *__restrict__ g, uint32_t O, uint32_t D, float *__restrict__ Pt) {
+    __shared__ double red[8];
+    const uint32_t o = blockIdx.x;
+    const float *r = g + (size_t)o * D;
+    double nn = 0.0;
+    for (uint32_t k = threadIdx.x; k < D; k += blockDim.x) nn += (double)r[k] * r[k];
+    for (int s = 16; s; s >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nn;
+    __syncthreads();
+    nn = 0.0;
+    for (int w = 0; w < 8; w++) nn += red[w];
+    const double inv = 1.0 / sqrt(nn);
+    for (uint32_t k = threadIdx.x; k < D; k += blockDim.x) Pt[(size_t)k * O + o] = (float)((double)r[k] * inv);
+}
+
+__global__ void k_untranspose(const float *__restrict__ Pt, uint32_t O, uint32_t D, float *__restrict__ P) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (uint64_t)O * D) { const uint32_t o = (uint32_t)(i / D), k = (uint32_t)(i % D); P[i] = Pt[(size_t)k * O + o]; }
+}
+
 // ---- minimal msgpack reader for opq.msgpack / rabitq.msgpack (maps of str -> int | float array)
 struct MpReader {
     const uint8_t *p, *end;
@@ -448,6 +514,71 @@ MSE_API int mse_rabitq_create(const float *mean, const float *transform, uint32_
     cudaMemcpy(r->mean, mean, D * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(r->Pt, pt.data(), D * O * 4, cudaMemcpyHostToDevice);
     *out = r;
+    return MSE_OK;
+}
+
+// rabitq.py:11-28 on the GPU, over the rows already in HBM: mean of the first sample_rows rows (the script takes 100 000), and P =
+// output_dims orthonormal rows (seeded Gaussian rows, two Gram-Schmidt sweeps -- Haar distributed like the Q of the script's QR)
+MSE_API int mse_rabitq_train(mse_index *ix, uint64_t sample_rows, uint32_t output_dims, uint64_t seed, mse_rabitq **out) {
+    MSE_REQUIRE(ix && out, MSE_ERR_INVALID, "rabitq_train: NULL argument");
+    *out = nullptr;
+    MSE_REQUIRE(ix->n > 0, MSE_ERR_STATE, "rabitq_train: the index is empty");
+    MSE_REQUIRE(output_dims >= 32 && output_dims % 32 == 0 && output_dims <= ix->d && output_dims <= 4096, MSE_ERR_INVALID,
+                "rabitq_train: output_dims=%u must be a multiple of 32 and <= n_dims=%u", output_dims, ix->d);
+    MSE_CHECK(use_device(ix->device));
+    const uint64_t ns = sample_rows == 0 ? ix->n : std::min<uint64_t>(sample_rows, ix->n);
+    const uint32_t D = ix->d, O = output_dims;
+    mse_rabitq *r = new mse_rabitq();
+    r->device = ix->device; r->D = D; r->O = O;
+    float *g = nullptr;
+    if (cudaMalloc(&r->mean, (size_t)D * 4) != cudaSuccess || cudaMalloc(&r->Pt, (size_t)D * O * 4) != cudaSuccess ||
+        cudaMalloc(&g, (size_t)D * O * 4) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (g) cudaFree(g);
+        mse_rabitq_destroy(r);
+        set_error("rabitq_train: device allocation failed");
+        return MSE_ERR_OOM;
+    }
+    k_col_mean<<<(D + 31) / 32, 256>>>(ix->x, ns, D, r->mean);
+    count_launch();
+    k_gauss_fill<<<(uint32_t)(((size_t)D * O + 255) / 256), 256>>>(g, (uint64_t)D * O, seed);
+    count_launch();
+    for (int sweep = 0; sweep < 2; sweep++)
+        for (uint32_t i = 0; i + 1 < O; i++) {
+            k_mgs_step<<<O - 1 - i, 256>>>(g, D, i);
+            count_launch();
+        }
+    k_normalise_transpose<<<O, 256>>>(g, O, D, r->Pt);
+    count_launch();
+    const cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(g);
+    if (e != cudaSuccess) {
+        set_error("rabitq_train: %s", cudaGetErrorString(e));
+        mse_rabitq_destroy(r);
+        return MSE_ERR_CUDA;
+    }
+    *out = r;
+    return MSE_OK;
+}
+
+MSE_API int mse_rabitq_info(const mse_rabitq *r, uint32_t out[2]) {
+    MSE_REQUIRE(r && out, MSE_ERR_INVALID, "rabitq_info: NULL argument");
+    out[0] = r->D; out[1] = r->O;
+    return MSE_OK;
+}
+
+// mean [n_dims] and transform [output_dims][n_dims] row-major: the two arrays rabitq.msgpack stores (rabitq.py:62-68)
+MSE_API int mse_rabitq_export(const mse_rabitq *r, float *mean, float *transform) {
+    MSE_REQUIRE(r && mean && transform, MSE_ERR_INVALID, "rabitq_export: NULL argument");
+    MSE_CHECK(use_device(r->device));
+    DevBuf p;
+    MSE_CHECK(p.ensure((size_t)r->D * r->O * 4));
+    k_untranspose<<<(uint32_t)(((size_t)r->D * r->O + 255) / 256), 256>>>(r->Pt, r->O, r->D, p.as<float>());
+    count_launch();
+    cudaError_t e = cudaMemcpy(transform, p.p, (size_t)r->D * r->O * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(mean, r->mean, (size_t)r->D * 4, cudaMemcpyDeviceToHost);
+    p.release();
+    MSE_REQUIRE(e == cudaSuccess, MSE_ERR_CUDA, "rabitq_export: %s", cudaGetErrorString(e));
     return MSE_OK;
 }
 

@@ -298,6 +298,30 @@ class RabitQ:
         check(lib().mse_rabitq_load(_p(buf), buf.size, device, C.byref(self._h)), "mse_rabitq_load")
         return self
 
+    @classmethod
+    def train(cls, vecs: "VectorList", sample_rows: int = 100_000, output_dims: int = 512, seed: int = 0) -> "RabitQ":
+        """rabitq.py:11-28 on the GPU over the rows of `vecs`: dataset mean + truncated random orthogonal transform."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        check(lib().mse_rabitq_train(vecs._h, sample_rows, output_dims, seed, C.byref(self._h)), "mse_rabitq_train")
+        info = (C.c_uint32 * 2)()
+        check(lib().mse_rabitq_info(self._h, info), "mse_rabitq_info")
+        self.n_dims, self.output_dims = int(info[0]), int(info[1])
+        return self
+
+    def export(self):
+        """-> (mean f32[n_dims], transform f32[output_dims, n_dims])"""
+        mean = np.empty(self.n_dims, np.float32)
+        tr = np.empty((self.output_dims, self.n_dims), np.float32)
+        check(lib().mse_rabitq_export(self._h, _p(mean), _p(tr)), "mse_rabitq_export")
+        return mean, tr
+
+    def to_msgpack(self) -> bytes:
+        """rabitq.msgpack as rabitq.py:62-68 writes it"""
+        import msgpack
+        mean, tr = self.export()
+        return msgpack.packb({"mean": mean.tolist(), "transform": tr.flatten().tolist(), "output_dims": int(self.output_dims), "n_dims": int(self.n_dims)})
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             try:

@@ -81,3 +81,32 @@ def test_cuda_query_side_and_traversal_estimate_match_the_script(mse, oracle):
     est = oracle.rabitq_direct_estimates(qtm, np.float32(1.0 / np.sqrt(1152.0)), G["qsample"], (G["norms"] * G["dots"]).astype(np.float32))
     assert np.abs(est - G["approx_results"]).max() < 5e-4
     rq.close()
+
+
+@pytest.mark.gpu
+def test_train_on_device(mse):
+    """mse_rabitq_train (rabitq.py:11-28 on the GPU): the mean is the script's mean of the sample; the transform has orthonormal rows;
+    codes / estimates made with the trained codec agree with the numpy restatement given the same (mean, P); msgpack round trip."""
+    from helpers import clustered_f16, unit_rows
+    from oracle.rabitq_np import RabitQ as NpRabitQ
+    x = clustered_f16(91, 2000, n_clusters=16)
+    vl = mse.diskann.VectorList.from_f16s(x)
+    rq = mse.diskann.RabitQ.train(vl, sample_rows=1500, output_dims=512, seed=7)
+    mean, P = rq.export()
+    assert np.allclose(mean, x[:1500].astype(np.float32).mean(axis=0), atol=2e-6)      # :14
+    assert P.shape == (512, 1152) and np.abs(P.astype(np.float64) @ P.astype(np.float64).T - np.eye(512)).max() < 2e-6   # :22-28
+    assert abs(float(P.mean())) < 5e-3 and 0.9 < float(P.std() * np.sqrt(1152.0)) < 1.1   # looks Haar: entries ~ N(0, 1/1152)
+    other = mse.diskann.RabitQ.train(vl, sample_rows=1500, output_dims=512, seed=8)
+    assert np.abs(other.export()[1] - P).max() > 1e-2                                   # the seed matters
+    ref = NpRabitQ(mean, P)
+    bits, norms, dots, xs = ref.quantize(x[:300])
+    codes, gn, gd = rq.quantize(x[:300])
+    diff = np.unpackbits(codes ^ NpRabitQ.pack(bits), axis=1, bitorder="little").astype(bool)
+    assert (np.abs(xs[diff]) < 1e-6).all()
+    q = unit_rows(92, 1)[0]
+    assert np.abs(rq.approx_dot(codes, gn, gd, q) - ref.approx_dot(bits, norms, dots, q)).max() < 2e-4
+    again = mse.diskann.RabitQ.from_msgpack(rq.to_msgpack())
+    assert np.array_equal(again.quantize(x[:50])[0], codes[:50])
+    for h in (rq, other, again):
+        h.close()
+    vl.close()
