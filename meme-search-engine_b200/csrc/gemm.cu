@@ -71,10 +71,30 @@ static int launch_skinny(int out_device, const __half *dA, const __half *dB, uin
     return MSE_OK;
 }
 
+// M <= 64: activation panel resident in shared memory, the pipeline streams weights only (gemm_skinny.cuh, namespace pr)
+template <int BN>
+static int launch_skinny_pr(int device, const __half *dA, const __half *dB, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb, const GemmOut &out,
+                            cudaStream_t st) {
+    auto kern = skinny::pr::k_gemm_skinny_pr<BN>;
+    static PerDeviceOnce once;
+    if (once.first(device)) MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skinny::pr::smem_bytes<BN>()));
+    kern<<<(N + BN - 1) / BN, skinny::pr::kThreads, skinny::pr::smem_bytes<BN>(), st>>>(dA, dB, M, N, K, lda, ldb, out);
+    MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
 int gemm_f16_tn_dev(int device, const __half *dA, const __half *dB, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb,
                     const GemmOut &out, cudaStream_t st) {
     MSE_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, MSE_ERR_UNSUPPORTED, "gemm: K, lda, ldb must be multiples of 8");
     MSE_REQUIRE(M > 0 && N > 0 && K > 0, MSE_ERR_INVALID, "gemm: empty shape");
+    static const bool no_pr = getenv("MSE_GEMM_NO_PANEL") != nullptr;   // profiling only
+    if (M <= (uint32_t)skinny::pr::kBM && force_bn == 0 && ((uintptr_t)dA & 15) == 0 && ((uintptr_t)dB & 15) == 0 && !no_pr && getenv("MSE_GEMM_NO_SKINNY") == nullptr) {
+        GemmOut o = out;
+        o.res_in_place = 0;
+        o.splitk_ws = nullptr;
+        // slice width: ~one CTA per SM (1152 columns -> 144 slices of 8; 3456 -> 108 and 4304 -> 135 slices of 32)
+        return N <= 2048 ? launch_skinny_pr<8>(device, dA, dB, M, N, K, lda, ldb, o, st) : launch_skinny_pr<32>(device, dA, dB, M, N, K, lda, ldb, o, st);
+    }
     if (M <= kSkinnyMaxM && force_bn == 0 && ((uintptr_t)dA & 15) == 0 && ((uintptr_t)dB & 15) == 0 && getenv("MSE_GEMM_NO_SKINNY") == nullptr) {
         GemmOut o = out;
         o.res_in_place = 0;

@@ -195,5 +195,153 @@ __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restri
     }
 }
 
+// ------------------------------------------------------------------ panel-resident variant, M <= 64 (one text query = 64 tokens)
+//
+// ncu of k_gemm_skinny at 64 rows (profiles/r01p_skinny_gemm_ncu_full.md): two thirds of every pipeline stage is the 64-row activation
+// panel, re-read from L2 by every CTA, so only 12-24 KB of WEIGHT bytes are in flight per SM -- far below what HBM latency needs
+// (~45 KB per SM at the copy peak).  Here the panel (64 x Kc halfs, Kc <= 1152: 148 KB) is loaded into shared memory ONCE per CTA and
+// the cp.async ring carries weights only: BN x 64 halfs per stage, 16-60 stages, 32-60 KB of HBM traffic in flight per SM.  A K larger
+// than the panel (fc2: 4304) is processed in panel-sized chunks with the accumulators kept in registers.  N is cut into 8- or
+// 32-column slices so that ~all SMs stream: 1152 -> 144 CTAs, 3456 -> 108, 4304 -> 135.
+namespace pr {
+
+static constexpr int kBM = 64, kBK = 64, kThreads = 256, kPitchB = kBK + 8;   // 8 warps: 4 row groups x 2 halves of every 64-wide k tile
+static constexpr int kKcMax = 1152;                                          // panel depth (halfs)
+static constexpr int kPitchA = kKcMax + 8;                                   // 2320 B rows: ldmatrix rows land in distinct banks
+static constexpr uint32_t kPanelBytes = (uint32_t)kBM * kPitchA * 2;         // 148 480
+static constexpr uint32_t kSmemBudget = 227u * 1024u - 1024u;
+
+template <int BN>
+constexpr int stages() {
+    constexpr int per = BN * kPitchB * 2;
+    constexpr int n = (int)((kSmemBudget - kPanelBytes) / per);
+    return n > 48 ? 48 : n;
+}
+template <int BN>
+constexpr uint32_t smem_bytes() { return kPanelBytes + (uint32_t)stages<BN>() * BN * kPitchB * 2; }
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads) k_gemm_skinny_pr(const __half *__restrict__ A, const __half *__restrict__ B, uint32_t M, uint32_t N, uint32_t K,
+                                                             uint32_t lda, uint32_t ldb, GemmOut o) {
+    constexpr int kStagesB = stages<BN>();
+    constexpr int NT = BN / 8;                                        // n8 tiles per CTA
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __half *sA = (__half *)smem_raw;                                  // [64][kPitchA]
+    __half *sB = sA + (size_t)kBM * kPitchA;                          // [stage][BN][kPitchB]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wr = warp & 3, kh = warp >> 2;                          // row group, which two k16 steps of a k tile
+    const uint32_t n0 = blockIdx.x * BN;
+
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+
+    for (uint32_t kc0 = 0; kc0 < K; kc0 += kKcMax) {
+        const uint32_t kc = min((uint32_t)kKcMax, K - kc0);
+        const uint32_t nk = (kc + kBK - 1) / kBK;
+        if (kc0) __syncthreads();                                     // everyone is done with the previous panel chunk and ring
+        // panel chunk: 64 rows x kc halfs, 16-byte chunks; rows >= M and columns >= K are zero-filled
+        {
+            const uint32_t chunks_per_row = nk * 8;
+            for (uint32_t c = tid; c < kBM * chunks_per_row; c += kThreads) {
+                const uint32_t r = c / chunks_per_row, kk = (c % chunks_per_row) * 8;
+                const bool ok = r < M && kc0 + kk < K;
+                cp_async16(sA + r * kPitchA + kk, A + (size_t)(ok ? r : 0) * lda + (ok ? kc0 + kk : 0), ok);
+            }
+            cp_async_commit();
+        }
+        auto load_b = [&](uint32_t kt, int st) {
+            const uint32_t k0 = kc0 + kt * kBK;
+            __half *b = sB + (size_t)st * BN * kPitchB;
+            for (int c = tid; c < BN * 8; c += kThreads) {
+                const int r = c >> 3, kk = (c & 7) * 8;
+                const bool ok = n0 + r < N && k0 + kk < K;
+                cp_async16(b + r * kPitchB + kk, B + (size_t)(ok ? n0 + r : 0) * ldb + (ok ? k0 + kk : 0), ok);
+            }
+        };
+#pragma unroll 1
+        for (int s = 0; s < kStagesB - 1; s++) {
+            if ((uint32_t)s < nk) load_b(s, s);
+            cp_async_commit();
+        }
+        for (uint32_t kt = 0; kt < nk; kt++) {
+            cp_async_wait<kStagesB - 2>();                            // the panel group is older than every weight stage: it has landed too
+            __syncthreads();
+            const uint32_t nxt = kt + kStagesB - 1;
+            if (nxt < nk) load_b(nxt, nxt % kStagesB);
+            cp_async_commit();
+            const __half *b = sB + (size_t)(kt % kStagesB) * BN * kPitchB;
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++) {
+                const int kq = kh * 2 + ks;                           // k16 step inside the k tile
+                uint32_t af[4];
+                ldmatrix_x4(af, sA + (wr * 16 + (lane & 15)) * kPitchA + kt * kBK + kq * 16 + (lane >> 4) * 8);
+                if constexpr (BN >= 16) {
+#pragma unroll
+                    for (int j = 0; j < BN / 16; j++) {               // two n8 tiles per ldmatrix.x4
+                        uint32_t bf[4];
+                        ldmatrix_x4(bf, b + (j * 16 + (lane & 7) + (lane >> 4) * 8) * kPitchB + kq * 16 + ((lane >> 3) & 1) * 8);
+                        mma_16816(acc[2 * j], af, bf[0], bf[1]);
+                        mma_16816(acc[2 * j + 1], af, bf[2], bf[3]);
+                    }
+                } else {                                              // BN = 8: one n8 tile; lanes 16-31 repeat the addresses of 0-15
+                    uint32_t bf[4];
+                    ldmatrix_x4(bf, b + (lane & 7) * kPitchB + kq * 16 + ((lane >> 3) & 1) * 8);
+                    mma_16816(acc[0], af, bf[0], bf[1]);
+                }
+            }
+        }
+        cp_async_wait<0>();
+    }
+    __syncthreads();                                                  // the ring is free: reuse it for the two-way reduction over the k halves
+    float *red = (float *)sB;                                         // [4 row groups][NT * 4][32 lanes]
+    if (kh == 1) {
+#pragma unroll
+        for (int j = 0; j < NT; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) red[((wr * NT + j) * 4 + e) * 32 + lane] = acc[j][e];
+    }
+    __syncthreads();
+    if (kh != 0) return;
+#pragma unroll
+    for (int j = 0; j < NT; j++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) acc[j][e] += red[((wr * NT + j) * 4 + e) * 32 + lane];   // fixed order: half 0 + half 1
+    // thread holds rows g and g + 8 (g = lane / 4), columns 2 (lane % 4) + {0, 1} of every n8 tile
+    const uint32_t g = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t row = wr * 16 + g + h * 8, col = n0 + j * 8 + t2;
+            if (row >= M || col >= N) continue;
+            float v0 = acc[j][2 * h], v1 = acc[j][2 * h + 1];
+            const bool two = col + 1 < N;
+            if (o.bias) { v0 += o.bias[col]; if (two) v1 += o.bias[col + 1]; }
+            if (o.act == ACT_GELU_ERF) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
+            else if (o.act == ACT_GELU_TANH) { v0 = gelu_tanh(v0); v1 = gelu_tanh(v1); }
+            if (o.res) {
+                const uint32_t rr = o.res_mod ? row % o.res_mod : row;
+                const __half *rp = o.res + (size_t)rr * o.ldc + col;
+                v0 += __half2float(rp[0]);
+                if (two) v1 += __half2float(rp[1]);
+            }
+            if (o.debug_no_store) continue;
+            if (o.c16) {
+                __half *cp = o.c16 + (size_t)row * o.ldc + col;
+                if (two && ((o.ldc | col) & 1) == 0) *(__half2 *)cp = __floats2half2_rn(v0, v1);
+                else { cp[0] = __float2half_rn(v0); if (two) cp[1] = __float2half_rn(v1); }
+            }
+            if (o.c32) {
+                float *cp = o.c32 + (size_t)row * o.ldc + col;
+                cp[0] = v0;
+                if (two) cp[1] = v1;
+            }
+        }
+    }
+}
+
+}  // namespace pr
+
 }  // namespace skinny
 }  // namespace mse

@@ -22,12 +22,9 @@ stream = torch.cuda.current_stream().cuda_stream
 data = GraphData(kind, dev)
 vl = dk.VectorList(D)
 vl.reserve(n)
-head = None
 for c0 in range(0, n, data.chunk):
     xb = data.rows(c0, data.chunk)[: n - c0].contiguous()
     vl.add_f16_dev(xb.data_ptr(), xb.shape[0], stream)
-    if head is None:
-        head = xb[:100_000].float().mean(dim=0).cpu().numpy()
     del xb
 q16 = data.queries(nq, n)
 q32 = q16.float().contiguous()
@@ -41,8 +38,7 @@ gt = torch.empty((nq, k), dtype=torch.int32, device=dev)
 gts = torch.empty((nq, k), dtype=torch.float32, device=dev)
 vl.search_dev(q32.data_ptr(), nq, k, gt.data_ptr(), gts.data_ptr(), stream)
 vl.check()
-P = torch.linalg.qr(torch.randn((D, D), generator=torch.Generator(device=dev).manual_seed(11), device=dev))[0][:512].contiguous()
-rq = dk.RabitQ(head, P.cpu().numpy())
+rq = dk.RabitQ.train(vl, sample_rows=100_000, output_dims=512, seed=11)
 rq.encode_index(vl, 0)
 qtm = torch.empty((nq, 513), dtype=torch.float32, device=dev)
 rq.query_dev(q32.data_ptr(), nq, qtm.data_ptr(), stream)
