@@ -87,8 +87,12 @@ int gemm_f16_tn_dev(int device, const __half *dA, const __half *dB, uint32_t M, 
                     const GemmOut &out, cudaStream_t st) {
     MSE_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, MSE_ERR_UNSUPPORTED, "gemm: K, lda, ldb must be multiples of 8");
     MSE_REQUIRE(M > 0 && N > 0 && K > 0, MSE_ERR_INVALID, "gemm: empty shape");
-    static const bool no_pr = getenv("MSE_GEMM_NO_PANEL") != nullptr;   // profiling only
-    if (M <= (uint32_t)skinny::pr::kBM && force_bn == 0 && ((uintptr_t)dA & 15) == 0 && ((uintptr_t)dB & 15) == 0 && !no_pr && getenv("MSE_GEMM_NO_SKINNY") == nullptr) {
+    // Panel-resident variant: measured NO faster than the ring-buffer kernel below (tools/gemm_probe.py, 64 rows: QKV 12.4 vs 10.9 us, out-proj
+    // 10.3 vs 10.3, fc1 12.4 vs 12.4, fc2 30.8 vs 22.6) -- at these sizes a layer is ~4 us of SM-active time inside a ~10 us launch-to-drain
+    // envelope (ncu: profiles/r01p_skinny_gemm_ncu_full.md), so what is left for batch-1 latency is the NUMBER of kernels (194 per forward),
+    // not their insides.  Kept behind MSE_GEMM_PANEL=1 for experiments.
+    static const bool use_pr = getenv("MSE_GEMM_PANEL") != nullptr;
+    if (use_pr && M <= (uint32_t)skinny::pr::kBM && force_bn == 0 && ((uintptr_t)dA & 15) == 0 && ((uintptr_t)dB & 15) == 0 && getenv("MSE_GEMM_NO_SKINNY") == nullptr) {
         GemmOut o = out;
         o.res_in_place = 0;
         o.splitk_ws = nullptr;
