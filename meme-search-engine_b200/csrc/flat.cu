@@ -12,6 +12,7 @@
 //   The tensor path then re-scores its kp survivors in fp64 and certifies the cut (see k_finalize).
 #include "internal.h"
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace mse {
@@ -19,6 +20,7 @@ namespace mse {
 static constexpr uint32_t kSortMax = 8192;    // elements k_select can sort in shared memory
 static constexpr uint32_t kKpMax = 2048;      // largest running list
 static constexpr uint64_t kChunk0 = 4096;     // first chunk (thr = -inf there, so it must fit the buffer)
+static constexpr uint64_t kGrowth = 4;        // a chunk is kGrowth x the rows before it (see ChunkPlan)
 
 // ------------------------------------------------------------------ index maintenance kernels
 
@@ -478,13 +480,17 @@ static void prof_collect(mse_index *ix) {
 }
 
 // Chunk schedule.  After N rows the threshold is the kp-th best of those N, so under exchangeable row order a further chunk of
-// g*N rows contributes ~g*kp candidates per query; g is chosen so that this stays at a third of the candidate buffer
-// (g = 1, i.e. doubling, for the largest kp; up to 15 for small k: 10 M rows are 5 launches instead of 13).  Row orders that
-// defeat the estimate overflow the buffer, which is detected and repaired by the exact re-run (fixed chunks).
+// g*N rows contributes ~g*kp candidates per query.  Every chunk costs a launch + a select, every candidate an append in the scoring
+// epilogue (whose threshold is stale for the whole chunk): measured at 1024 queries (r02, MSE_FLAT_GROWTH): g = 1 / 2 / 4 / 12 ->
+// 19.8 / 19.7 / 19.5 / 19.7 ms over 10 M rows and 2.63 / 2.57 / 2.54 / 2.58 ms over 1.25 M (the 8-GPU shard).  g = 4, capped so that
+// g*kp stays below a third of the candidate buffer.  Row orders that defeat the estimate overflow the buffer, which is detected and
+// repaired by the exact re-run (fixed chunks).
 struct ChunkPlan {
     std::vector<std::pair<uint64_t, uint64_t>> chunks;  // (row0, nrows)
     ChunkPlan(uint64_t n, uint64_t fixed, uint32_t kp, uint32_t cap) {
-        const uint64_t g = std::min<uint64_t>(15, std::max<uint64_t>(1, cap / (3ull * std::max(kp, 1u))));
+        static const long g_env = getenv("MSE_FLAT_GROWTH") ? atol(getenv("MSE_FLAT_GROWTH")) : 0;   // tuning aid
+        const uint64_t g_max = std::min<uint64_t>(15, std::max<uint64_t>(1, cap / (3ull * std::max(kp, 1u))));
+        const uint64_t g = std::min<uint64_t>(g_max, g_env > 0 ? (uint64_t)g_env : kGrowth);
         uint64_t row0 = 0;
         while (row0 < n) {
             const uint64_t sz = fixed ? fixed : (row0 == 0 ? kChunk0 : g * row0);
