@@ -66,3 +66,63 @@ def test_encode_build_serve(tmp_path_factory, mse, oracle):
     assert 3 in res.ids[0, :3]
     vl.close()
     enc.close()
+
+
+def test_http_embed_service_on_gpu(tmp_path_factory, mse):
+    """clip_server boundary end to end on the GPU: concurrent HTTP/msgpack requests -> coalescer -> the real towers behind the C ABI ->
+    fp16 byte strings.  Every returned vector matches the fp32 oracle (cosine >= 1 - 1e-3) and is unit norm; concurrent requests
+    share tower calls."""
+    import asyncio
+    import io
+
+    import msgpack
+    from aiohttp.test_utils import TestClient, TestServer
+    from PIL import Image
+    from prometheus_client import CollectorRegistry
+
+    from mse_b200.clip_server import ClipServer
+    from oracle import towers as T
+    v, t = T.build_vision(depth=2, seed=42), T.build_text(depth=2, seed=43)
+    sd = T.export_openclip(v, t)
+    path = str(tmp_path_factory.mktemp("w") / "towers2.msew")
+    mse.weights.save_weights(path, sd, mse.weights.config_for(sd))
+    token_rows = T.synthetic_token_ids(5, 6)
+
+    class IdTokenizer:                      # no SentencePiece model offline: "text" i stands for the i-th synthetic token row
+        def __call__(self, texts):
+            return np.stack([token_rows[int(s)] for s in texts]).astype(np.int32)
+
+    cfg = {"device": "cuda:0", "model": "ViT-SO400M-14-SigLIP-384", "model_name": "siglip-test", "max_batch_size": 8, "port": 0,
+           "model_path": path, "batch_window_ms": 30}
+    srv = ClipServer(cfg, tokenizer=IdTokenizer(), registry=CollectorRegistry())
+    imgs = T.synthetic_images(21, 6)
+
+    def bmp(a):
+        buf = io.BytesIO()
+        Image.fromarray(a).save(buf, format="BMP")
+        return buf.getvalue()
+
+    async def go():
+        async with TestClient(TestServer(srv.app)) as c:
+            r = await c.get("/config")
+            assert msgpack.loads(await r.read()) == {"model": "ViT-SO400M-14-SigLIP-384", "batch": 8, "image_size": [384, 384], "embedding_size": 1152}
+
+            async def post(body):
+                r = await c.post("/", data=msgpack.dumps(body))
+                assert r.status == 200, await r.read()
+                return [np.frombuffer(b, "<f2").astype(np.float32) for b in msgpack.loads(await r.read())]
+            reqs = [{"images": [bmp(imgs[0]), bmp(imgs[1])]}, {"images": [bmp(imgs[2])]}, {"text": ["0", "1"]}, {"images": [bmp(imgs[3]), bmp(imgs[4]), bmp(imgs[5])]},
+                    {"text": ["2"]}, {"text": ["3", "4", "5"]}]
+            return await asyncio.gather(*[post(r) for r in reqs])
+    outs = asyncio.new_event_loop().run_until_complete(go())
+    got_img = np.stack(outs[0] + outs[1] + outs[3])
+    got_txt = np.stack(outs[2] + outs[4] + outs[5])
+    ref_img, ref_txt = T.encode_image(v, imgs), T.encode_text(t, token_rows)
+
+    def cos(a, b):
+        return ((a.astype(np.float64) * b).sum(1) / (np.linalg.norm(a.astype(np.float64), axis=1) * np.linalg.norm(b, axis=1))).min()
+    assert cos(got_img, ref_img) >= 1 - 1e-3 and cos(got_txt, ref_txt) >= 1 - 1e-3
+    assert np.allclose(np.linalg.norm(got_img, axis=1), 1.0, atol=2e-3) and np.allclose(np.linalg.norm(got_txt, axis=1), 1.0, atol=2e-3)
+    batches = srv.registry.get_sample_value("modelserver_batchcount_total", {"model": "siglip-test"})
+    assert batches is not None and batches < 6                       # six requests, fewer tower calls
+    srv.encoder.close()
