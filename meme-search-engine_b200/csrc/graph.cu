@@ -15,6 +15,7 @@
 #include "fastdot.cuh"
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 
 namespace mse {
 
@@ -1009,6 +1010,19 @@ static int check_dev_start(const mse_index *ix, const uint32_t *d_starts, uint32
     return MSE_OK;
 }
 
+// visited_adjacent table of the beam search: 4 x stride x L slots (>= 8192).  Keys inserted per query: ~2.1-3.0 k at L = 64, 3.3-4.4 k at 128,
+// 4.9-6.8 k at 256, 6.6-14.8 k at 512 (1 M - 12.5 M rows, R = 64); the kernels stop with an overflow status at 75 % fill.  The table is
+// where the kernel's DRAM traffic comes from (ncu r02u, L = 512: 17.4 GB read + 4.5 GB written per launch against 1.5 GB of algorithmic
+// bytes: every probe of a cold table is a sector from HBM, every query clears its table), but HALVING it measured slower, not faster
+// (12.5 M rows: L = 64 2.91 -> 3.67 ms, L = 512 21.1 -> 21.6 ms; MSE_BEAM_HASH_PER_L): longer probe chains are dependent round trips.
+static uint32_t beam_hash_capacity(uint32_t L, uint32_t stride) {
+    static const long env = getenv("MSE_BEAM_HASH_PER_L") ? atol(getenv("MSE_BEAM_HASH_PER_L")) : 0;   // tuning aid: slots per unit of L
+    uint64_t v = (uint64_t)std::max<uint32_t>(L, 64) * (env > 0 ? (uint64_t)env : 4ull * stride);
+    uint32_t p = 8192;
+    while (p < v && p < (1u << 30)) p <<= 1;
+    return p;
+}
+
 static uint32_t pow2_at_least(uint64_t v) {
     uint32_t p = 1024;
     while (p < v && p < (1u << 30)) p <<= 1;
@@ -1207,7 +1221,7 @@ static int search_beam_impl(mse_index *ix, const uint16_t *q_f16, const float *l
     MSE_REQUIRE(smem <= 220 * 1024, MSE_ERR_UNSUPPORTED, "search_beam: L=%u with a %zu-byte LUT does not fit shared memory", L, lut_bytes);
     MSE_CUDA(cudaFuncSetAttribute(k_beam_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t grid = std::min<uint32_t>(nq, (uint32_t)sm_count(ix->device) * 2);
-    const uint32_t hcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * ix->graph_stride * 4);
+    const uint32_t hcap = beam_hash_capacity(L, ix->graph_stride);
     const uint32_t vcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * 16);
     DevBuf b_q, b_lut, b_ds, b_ids, b_sc, b_len, b_c, b_p, b_st, b_h, b_starts, b_cb;
     int rc = MSE_OK;
@@ -1289,7 +1303,7 @@ MSE_API int mse_search_beam_dev(mse_index *ix, const uint16_t *d_q_f16, const fl
     const uint32_t M = ix->code_size, C = d_qtm ? 0u : n_centroids;
     MSE_REQUIRE(d_qtm || C >= 1, MSE_ERR_INVALID, "search_beam_dev: n_centroids is 0");
     MSE_REQUIRE(!d_qtm || rabitq_output_dims == 32 * kRqWords, MSE_ERR_UNSUPPORTED, "search_beam_dev: RabitQ traversal supports output_dims = %d", 32 * kRqWords);
-    const uint32_t hcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * ix->graph_stride * 4);
+    const uint32_t hcap = beam_hash_capacity(L, ix->graph_stride);
     const uint32_t vcap = pow2_at_least((uint64_t)std::max<uint32_t>(L, 64) * 16);
     const uint32_t cap = std::max<uint32_t>(8 * L + 64, topk);
     MSE_CHECK(ix->gw_status.ensure((size_t)nq * 4));

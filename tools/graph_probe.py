@@ -2,7 +2,7 @@
 the GPU, then times the exact greedy_search ("g:L") and the RabitQ beam search ("b:L:W") variants named on the command line and
 reports q/s, recall@10 against the flat ground truth and the kernels' own counters.  Also the workload for ncu captures:
   ncu --set full --import-source on -k regex:k_beam_search_wq -c 1 -o gpurun_out/x python tools/graph_probe.py 1000000 families b:64:4
-usage: graph_probe.py [rows] [families|mixture|latent] [variant ...] [--reps N]"""
+usage: graph_probe.py [rows] [families|mixture|latent] [variant ...] [--reps N] [--cuda-profiler]"""
 import json, sys, time
 sys.path.insert(0, ".")
 import torch
@@ -58,6 +58,9 @@ def timed(fn):
     return e0.elapsed_time(e1) / reps
 
 
+if "--cuda-profiler" in sys.argv:      # ncu --profile-from-start off: capture the search kernels, not the build's
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
 for v in variants:
     p = v.split(":")
     if p[0] == "g":
