@@ -44,9 +44,14 @@ TEXT_WEIGHT_BYTES = 0.826e9  # 412.9 M parameters touched x 2 B
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernels from the committed `ncu --set full` captures (per launch
 # or per algorithmic byte).  Measured under a profiler on the named capture, not by this run.
 NCU_TRAFFIC = {
-    "tower_gemm_bytes_per_step_b256": (27 * (2.065 + 3.454 + 1.682 + 1.262) * 1e9, "profiles/r01b_tower_ncu_full.md"),
-    "flat_gemm_bytes_per_row_byte": ((3.745176 + 0.005563) / 3.74, "profiles/r01_flat_gemm_ncu_full.md"),
-    "greedy_bytes_per_row_byte": ((14.376188 + 0.651920) / (1589.4404296875 * 4096 * 2304 / 1e9), "profiles/r01i_greedy_1m_ncu_full.md"),
+    # profiles/r02t_ncu_full.md: one block at batch 256 = fc2 2.573 + QKV 1.680 + out-proj 1.257 + fc1 2.004 GB (read + write); x 27 blocks
+    "tower_gemm_bytes_per_step_b256": (27 * (2.573 + 1.680 + 1.257 + 2.004) * 1e9, "profiles/r02t_ncu_full.md"),
+    # profiles/r02t_ncu_full.md: 17.155 GB read + 10.8 MB written for the 17.150 GB of rows the launch scored
+    "flat_gemm_bytes_per_row_byte": ((17.154500 + 0.010778) / 17.149723, "profiles/r02t_ncu_full.md"),
+    # profiles/r02t_ncu_full.md (12.5 M rows, 4096 queries): greedy L = 64: 14.872 GB read + 0.594 GB written for 15.17 GB of gathered rows;
+    # RabitQ beam L = 512: 17.377 + 4.516 GB per launch (visited-set tables), 1.53 GB algorithmic
+    "greedy_bytes_per_row_byte": ((14.872 + 0.594) / 15.17, "profiles/r02t_ncu_full.md"),
+    "beam_l512_bytes_per_launch": ((17.377 + 4.516) * 1e9, "profiles/r02t_ncu_full.md"),
 }
 
 
@@ -757,7 +762,10 @@ def main():
                               "bound": "hbm", "achieved": hv["bytes"] / (ms_bk * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                               "frac": hv["bytes"] / (ms_bk * 1e-3) / 1e9 / pk["hbm"],
                               "algorithmic_bytes": "expanded nodes x (2304 B row + 256 B adjacency) + scored candidates x (64 B code + 4 B scale), from the kernel's counters",
-                              "kernel_ms_per_step": ms_bk, "kernel_share_of_step": ms_bk / hv["ms_per_step"], "traffic": None},
+                              "kernel_ms_per_step": ms_bk, "kernel_share_of_step": ms_bk / hv["ms_per_step"],
+                              "traffic": NCU_TRAFFIC["beam_l512_bytes_per_launch"][0] if (Lh, Wh, per_gpu) == (512, 4, 12_500_000) else None,
+                              "traffic_note": "ncu capture " + NCU_TRAFFIC["beam_l512_bytes_per_launch"][1] + " (L = 512, W = 4, 12.5 M rows): 14 x the algorithmic "
+                                              "bytes -- the visited-set tables (cleared per query, one cold sector per probe)"},
                  "sweep": {s: {kk: vv for kk, vv in v.items() if kk not in ("clocks", "bytes", "unit")} for s, v in variants.items()},
                  "greedy_exact": greedy, "greedy_clocks": gclocks,
                  "build": {"seconds": build_s, "points_per_s": n_local / build_s, "stats": bst, "rabitq_train_seconds": train_s, "rabitq_encode_seconds": enc_s}}
