@@ -679,7 +679,7 @@ def main():
                                "achieved": g_bytes / (ms_gk * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": g_bytes / (ms_gk * 1e-3) / 1e9 / pk["hbm"],
                                "algorithmic_bytes": "distances x 2304 B (gathered rows; adjacency lists and the query are < 2 %)",
                                "kernel_ms_per_step": ms_gk, "kernel_share_of_step": ms_gk / ms_g, "traffic": trg * g_bytes,
-                               "traffic_note": f"ratio from the ncu capture {trg_src} (1 M rows): every gathered row leaves HBM once"}}
+                               "traffic_note": f"ratio from the ncu capture {trg_src} (12.5 M rows, L = 64): every gathered row leaves HBM once"}}
 
         # ---- C4 proper: RabitQ codes for the frontier, exact rows for expanded nodes (query_disk_index.rs:144-212), beam W
         t0 = time.perf_counter()

@@ -36,8 +36,18 @@ struct NbView {
 __device__ __forceinline__ void nb_insert(NbView &b, uint32_t id, long long score, int lane) {
     if (b.cap == 0) return;
     if (b.len == b.cap && b.scores[b.len - 1] > score) return;                     // :118
-    int g = 0, e = 0;                                                              // binary_search_by on the descending list:
-    for (int i0 = 0; i0 < b.len; i0 += 32) {                                       // g = #entries > score, e = #entries == score
+    int g = 0, e = 0, c0 = 0;                                                      // binary_search_by on the descending list:
+    if (b.len > 128 && b.len <= 1024) {
+        // long lists: lane k looks at the head of chunk k first.  The chunks whose head is above `score` form a prefix and all of them
+        // but the last lie entirely above it (every entry of chunk k is >= the head of chunk k+1), so the scan can start at the last
+        const int nch = (b.len + 31) >> 5;
+        const bool hin = lane < nch;
+        const long long h = hin ? b.scores[lane << 5] : 0;
+        const int G = __popc(__ballot_sync(0xffffffffu, hin && h > score));
+        c0 = G > 0 ? G - 1 : 0;
+        g = c0 << 5;
+    }
+    for (int i0 = c0 << 5; i0 < b.len; i0 += 32) {                                 // g = #entries > score, e = #entries == score
         const int i = i0 + lane;
         const bool in = i < b.len;
         const long long s = in ? b.scores[i] : 0;
