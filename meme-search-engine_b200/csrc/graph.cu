@@ -758,6 +758,14 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
                 if (lane == 0) { pt_scores[i] = s0; pt_scores[j] = s1; }
             }
             __syncwarp();
+            // the adjacency lists (and degrees) of all popped nodes are fetched together into the candidate array: one exposed round trip per
+            // iteration instead of one per node.  The array is compacted in place below -- the write index never passes the read index.
+            const uint32_t my_deg = (uint32_t)lane < np ? g.deg[pts[lane]] : 0u;
+            for (uint32_t b = 0; b < np; b++) {
+                const uint32_t *nbrs = g.adj + (size_t)pts[b] * S;
+                for (uint32_t i = lane; i < S; i += 32) pre[b * S + i] = nbrs[i];
+            }
+            __syncwarp();
             int n_pre = 0;
             for (uint32_t b = 0; b < np; b++) {
                 const uint32_t id = pts[b];
@@ -777,21 +785,19 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
                     n_out++;
                 }
                 // out-neighbours not seen as a neighbour before, first occurrence first
-                const uint32_t dgl = g.deg[id];
-                const uint32_t *nbrs = g.adj + (size_t)id * S;
-                for (uint32_t b0 = 0; b0 < S; b0 += 32) {
+                const uint32_t dg = min(__shfl_sync(full, my_deg, (int)b), S);
+                for (uint32_t b0 = 0; b0 < dg; b0 += 32) {
                     const uint32_t i = b0 + lane;
-                    const uint32_t rawid = i < S ? nbrs[i] : kEmpty;                  // issued before the degree is known
-                    const uint32_t dg = min(dgl, S);
-                    if (b0 >= dg) break;
                     const bool have = i < dg;
-                    const uint32_t nid = have ? rawid : kEmpty;
+                    const uint32_t nid = have ? pre[b * S + i] : kEmpty;
+                    __syncwarp();                                                     // every lane has read its slot before the compaction writes
                     const unsigned same = __match_any_sync(full, nid);
                     bool ins = false;
                     if (have && (same & ((1u << lane) - 1)) == 0) ins = hs_insert_nc(hadj, hmask, nid);
                     const unsigned m = __ballot_sync(full, ins);
                     if (ins) pre[n_pre + __popc(m & ((1u << lane) - 1))] = nid;
                     n_pre += __popc(m);
+                    __syncwarp();
                 }
             }
             fill_adj += n_pre;
