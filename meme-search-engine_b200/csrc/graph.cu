@@ -795,7 +795,13 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
                     bool ins = false;
                     if (have && (same & ((1u << lane) - 1)) == 0) ins = hs_insert_nc(hadj, hmask, nid);
                     const unsigned m = __ballot_sync(full, ins);
-                    if (ins) pre[n_pre + __popc(m & ((1u << lane) - 1))] = nid;
+                    if (ins) {
+                        pre[n_pre + __popc(m & ((1u << lane) - 1))] = nid;
+                        // the candidate's code and scale are needed a few hundred cycles from now: start them towards L2 while the
+                        // remaining nodes of the iteration go through their visited-set round trips
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ba.codes + (size_t)nid * ba.M));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ba.code_scale + nid));
+                    }
                     n_pre += __popc(m);
                     __syncwarp();
                 }
