@@ -306,6 +306,11 @@ int mse_encoder_create(const char *weights_path, int device, int max_batch, mse_
 int mse_encoder_config(const mse_encoder *e, int32_t out[16]);
 int mse_encode_images_u8(mse_encoder *e, const uint8_t *rgb_hwc, int batch, uint16_t *out_f16);
 int mse_encode_images_u8_dev(mse_encoder *e, const uint8_t *d_rgb_hwc, int batch, uint16_t *d_out_f16, void *stream);
+/* The files the reference's clients actually send (src/common.rs:42-53 resize_for_embed_sync: image_size x image_size 24-bit BI_RGB BMPs
+ * written by the image crate's BmpEncoder; clip_server.py:140 opens them with PIL): bmps[i] / lens[i] are host pointers to whole BMP
+ * files, the headers are read on the host and the pixel arrays (BGR, bottom-up) are unpacked on the device.  Any other size or pixel
+ * format is MSE_ERR_UNSUPPORTED -- decode it on the host and call mse_encode_images_u8. */
+int mse_encode_images_bmp(mse_encoder *e, const uint8_t *const *bmps, const size_t *lens, int batch, uint16_t *out_f16);
 int mse_encode_text_ids(mse_encoder *e, const int32_t *ids, int batch, uint16_t *out_f16);
 int mse_encode_text_ids_dev(mse_encoder *e, const int32_t *d_ids, int batch, uint16_t *d_out_f16, void *stream);
 /* per-layer parity hooks: token activations [batch*S][dim] fp16 after the embedding and the first n_blocks blocks */

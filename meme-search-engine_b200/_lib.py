@@ -113,6 +113,7 @@ _SIGS = {
     "mse_encoder_config": (_i32, [_vp, _vp]),
     "mse_encode_images_u8": (_i32, [_vp, _vp, _i32, _vp]),
     "mse_encode_images_u8_dev": (_i32, [_vp, _vp, _i32, _vp, _vp]),
+    "mse_encode_images_bmp": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "mse_encode_text_ids": (_i32, [_vp, _vp, _i32, _vp]),
     "mse_encode_text_ids_dev": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "mse_encode_images_hidden": (_i32, [_vp, _vp, _i32, _i32, _vp]),

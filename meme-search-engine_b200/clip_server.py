@@ -81,6 +81,16 @@ class SiglipTokenizer:
         return rows
 
 
+def is_client_bmp(data: bytes, size: int) -> bool:
+    """True for exactly what src/common.rs:42-53 produces: a size x size 24-bit uncompressed BMP (54-byte header + BGR rows)."""
+    if len(data) < 54 or data[:2] != b"BM":
+        return False
+    w, h = int.from_bytes(data[18:22], "little", signed=True), int.from_bytes(data[22:26], "little", signed=True)
+    bpp, comp, off = int.from_bytes(data[28:30], "little"), int.from_bytes(data[30:34], "little"), int.from_bytes(data[10:14], "little")
+    stride = (size * 3 + 3) & ~3
+    return w == size and abs(h) == size and bpp == 24 and comp == 0 and off + stride * size <= len(data)
+
+
 def decode_image(data: bytes, size: int) -> np.ndarray:
     """Encoded image bytes -> [size, size, 3] u8 RGB.  The reference's clients send size x size 24-bit BMPs
     (src/common.rs:31-54), for which open_clip's Resize is the identity; anything else is squashed bicubically."""
@@ -94,8 +104,8 @@ def decode_image(data: bytes, size: int) -> np.ndarray:
 @dataclass
 class _Ticket:
     """Rows of one request waiting for a tower call."""
-    modality: str                      # "text" | "image"
-    rows: np.ndarray                   # [m, 64] int32 token ids or [m, S, S, 3] u8 pixels
+    modality: str                      # "text" | "image" (decoded pixels) | "bmp" (whole client BMP files, unpacked on the device)
+    rows: np.ndarray                   # [m, 64] int32 token ids, [m, S, S, 3] u8 pixels, or [m, file length] u8
     done: asyncio.Future = field(repr=False)
     arrived: float = field(default_factory=time.monotonic)
 
@@ -147,7 +157,7 @@ class Coalescer:
                     t = await asyncio.wait_for(self._waiting.get(), wait)
                 except asyncio.TimeoutError:
                     break
-            if t.modality != head.modality or rows + t.rows.shape[0] > self._limit:
+            if t.modality != head.modality or t.rows.shape[1:] != head.rows.shape[1:] or rows + t.rows.shape[0] > self._limit:
                 self._held = t                      # opens the next call; arrival order is kept
                 break
             group.append(t)
@@ -194,6 +204,7 @@ class ClipServer:
         self.tokenizer = tokenizer
         self.image_size = int(getattr(encoder, "image_size", 384))
         self.queue_depth = int(config.get("queue_depth", 10))
+        self.bmp_on_device = bool(config.get("bmp_on_device", True)) and hasattr(encoder, "encode_image_bmp")
         self.registry = registry if registry is not None else REGISTRY
         self.items_ctr = Counter("modelserver_total_items", "Items run through model server", ["model", "modality"], registry=self.registry)
         self.inference_time_hist = Histogram("modelserver_inftime", "Time running inference", ["model", "batch_size"], registry=self.registry)
@@ -217,9 +228,15 @@ class ClipServer:
     # -- GPU lane ------------------------------------------------------------------------------------------------
     def _tower_call(self, modality: str, rows: np.ndarray, n_requests: int) -> np.ndarray:
         n = rows.shape[0]
-        self.items_ctr.labels(self.model_label, modality).inc(n)
-        with self.inference_time_hist.labels(f"{self.model_label}-{modality}", n).time():
-            feats = self.encoder.encode_text(rows) if modality == "text" else self.encoder.encode_image(rows)
+        self.items_ctr.labels(self.model_label, "image" if modality == "bmp" else modality).inc(n)
+        label = "image" if modality == "bmp" else modality
+        with self.inference_time_hist.labels(f"{self.model_label}-{label}", n).time():
+            if modality == "text":
+                feats = self.encoder.encode_text(rows)
+            elif modality == "bmp":                       # whole BMP files, unpacked on the device (mse_encode_images_bmp)
+                feats = self.encoder.encode_image_bmp(list(rows))
+            else:
+                feats = self.encoder.encode_image(rows)
         self.batch_count_ctr.labels(self.model_label).inc()
         self.coalesced_hist.labels(self.model_label).observe(n_requests)
         return feats
@@ -239,6 +256,9 @@ class ClipServer:
         if images:
             if len(images) > self.max_batch:
                 raise RequestError(f"max batch size is {self.max_batch}")
+            # the reference's clients send image_size x image_size 24-bit BMPs (src/common.rs:42-53): those go to the GPU as they are
+            if self.bmp_on_device and all(is_client_bmp(b, self.image_size) for b in images) and len({len(b) for b in images}) == 1:
+                return "bmp", np.stack([np.frombuffer(b, np.uint8) for b in images])
             return "image", np.stack([decode_image(b, self.image_size) for b in images])
         raise RequestError("images or text required")
 

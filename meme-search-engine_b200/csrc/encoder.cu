@@ -48,6 +48,21 @@ __global__ void __launch_bounds__(256) k_im2col_patch14(const uint8_t *__restric
     }
 }
 
+// 24-bit BI_RGB BMP pixel arrays (BGR, rows padded to 4 bytes, bottom-up unless the header's height is negative) -> RGB top-down HWC:
+// the container the reference's clients send (src/common.rs:42-53), unpacked on the device instead of by PIL (clip_server.py:140).
+// meta[b] = {byte offset of the pixel array in `files`, row stride, bottom_up, 0}.  grid (img rows, batch)
+__global__ void __launch_bounds__(256) k_bmp24_to_rgb(const uint8_t *__restrict__ files, const uint32_t *__restrict__ meta, uint8_t *__restrict__ out,
+                                                      int img_size) {
+    const int y = blockIdx.x, b = blockIdx.y;
+    const uint32_t off = meta[4 * b], stride = meta[4 * b + 1], bottom_up = meta[4 * b + 2];
+    const uint8_t *src = files + off + (size_t)(bottom_up ? img_size - 1 - y : y) * stride;
+    uint8_t *dst = out + ((size_t)b * img_size + y) * img_size * 3;
+    for (int i = threadIdx.x; i < img_size * 3; i += blockDim.x) {
+        const int x = i / 3, c = i % 3;
+        dst[i] = src[x * 3 + (2 - c)];
+    }
+}
+
 // LayerNorm over the last dim (D % 8 == 0, D <= 256 * NV), fp32 statistics, one warp per row; NV = 16-byte pieces per lane
 template <int NV>
 __global__ void __launch_bounds__(256) k_layernorm(const __half *__restrict__ x, __half *__restrict__ y, const float *__restrict__ g,
@@ -296,6 +311,9 @@ struct mse_encoder {
     __half *x = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr, *pool = nullptr, *y = nullptr, *yn = nullptr,
            *hh = nullptr, *z = nullptr, *outb = nullptr;
     uint8_t *img_dev = nullptr;
+    uint8_t *bmp_dev = nullptr;        // staging for mse_encode_images_bmp (allocated on first use)
+    size_t bmp_cap = 0;
+    uint32_t *bmp_meta = nullptr;
     int32_t *ids_dev = nullptr;
     float *splitk_ws = nullptr;       // skinny GEMM scratch (gemm_skinny.cuh): partial tiles + arrival counters
     uint32_t *splitk_cnt = nullptr;
@@ -543,6 +561,8 @@ MSE_API void mse_encoder_destroy(mse_encoder *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void *p : e->allocs) cudaFree(p);
     for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
+    if (e->bmp_dev) cudaFree(e->bmp_dev);
+    if (e->bmp_meta) cudaFree(e->bmp_meta);
     for (cudaGraphExec_t gx : e->text_graph)
         if (gx) cudaGraphExecDestroy(gx);
     if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
@@ -756,6 +776,63 @@ MSE_API int mse_encode_text_ids(mse_encoder *e, const int32_t *ids, int batch, u
 MSE_API int mse_encode_text_ids_dev(mse_encoder *e, const int32_t *d_ids, int batch, uint16_t *d_out_f16, void *stream) {
     return encode_text_impl(e, d_ids, true, batch, d_out_f16, true, -1, (cudaStream_t)stream);
 }
+// The files the reference's clients send (src/common.rs:42-53: image_size x image_size 24-bit BI_RGB BMPs from the image crate's BmpEncoder):
+// headers are read on the host, the pixel arrays are unpacked on the device.  Anything else is MSE_ERR_UNSUPPORTED -- decode it on the host
+// and call mse_encode_images_u8.
+MSE_API int mse_encode_images_bmp(mse_encoder *e, const uint8_t *const *bmps, const size_t *lens, int batch, uint16_t *out_f16) {
+    MSE_REQUIRE(e != nullptr, MSE_ERR_INVALID, "encode_images_bmp: NULL handle");
+    MSE_REQUIRE(e->cfg[9], MSE_ERR_STATE, "encode_images_bmp: this encoder was loaded without a vision tower");
+    MSE_REQUIRE(batch >= 0 && (batch == 0 || (bmps && lens && out_f16)), MSE_ERR_INVALID, "encode_images_bmp: bad argument");
+    MSE_REQUIRE(batch <= e->max_batch, MSE_ERR_INVALID, "encode_images_bmp: max batch size is %d", e->max_batch);
+    if (batch == 0) return MSE_OK;
+    MSE_CHECK(use_device(e->device));
+    const int S = e->cfg[0];
+    auto rd32 = [](const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
+    std::vector<uint32_t> meta((size_t)batch * 4);
+    size_t total = 0;
+    for (int i = 0; i < batch; i++) {
+        const uint8_t *f = bmps[i];
+        MSE_REQUIRE(f && lens[i] >= 54 && f[0] == 'B' && f[1] == 'M', MSE_ERR_UNSUPPORTED, "encode_images_bmp: image %d is not a BMP file", i);
+        const uint32_t data_off = rd32(f + 10), dib = rd32(f + 14);
+        const int32_t w = (int32_t)rd32(f + 18), h = (int32_t)rd32(f + 22);
+        const uint32_t bpp = f[28] | (f[29] << 8), comp = rd32(f + 30);
+        const uint32_t stride = ((uint32_t)S * 3 + 3) & ~3u;
+        MSE_REQUIRE(dib >= 40 && bpp == 24 && comp == 0 && w == S && (h == S || h == -S), MSE_ERR_UNSUPPORTED,
+                    "encode_images_bmp: image %d is %dx%d, %u bpp, compression %u; only %dx%d 24-bit BI_RGB is unpacked on the device", i, w, h, bpp, comp, S, S);
+        MSE_REQUIRE((size_t)data_off + (size_t)stride * S <= lens[i], MSE_ERR_INVALID, "encode_images_bmp: image %d is truncated", i);
+        meta[4 * i] = (uint32_t)total + data_off;
+        meta[4 * i + 1] = stride;
+        meta[4 * i + 2] = h > 0 ? 1u : 0u;
+        meta[4 * i + 3] = 0;
+        total += (lens[i] + 15) & ~(size_t)15;
+        MSE_REQUIRE(total < (1ull << 32), MSE_ERR_UNSUPPORTED, "encode_images_bmp: batch too large");
+    }
+    if (total > e->bmp_cap) {
+        if (e->bmp_dev) cudaFree(e->bmp_dev);
+        e->bmp_dev = nullptr; e->bmp_cap = 0;
+        MSE_CUDA(cudaMalloc(&e->bmp_dev, total + total / 4));
+        e->bmp_cap = total + total / 4;
+    }
+    if (!e->bmp_meta) MSE_CUDA(cudaMalloc(&e->bmp_meta, (size_t)e->max_batch * 16));
+    cudaStream_t st = e->stream;
+    size_t at = 0;
+    for (int i = 0; i < batch; i++) {
+        MSE_CUDA(cudaMemcpyAsync(e->bmp_dev + at, bmps[i], lens[i], cudaMemcpyHostToDevice, st));
+        at += (lens[i] + 15) & ~(size_t)15;
+    }
+    MSE_CUDA(cudaMemcpyAsync(e->bmp_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, st));
+    MSE_CUDA(cudaStreamSynchronize(st));                         // `meta` lives on this stack frame
+    prof_begin(e);
+    const uint64_t l0 = g_launches.load();
+    k_bmp24_to_rgb<<<dim3(S, batch), 256, 0, st>>>(e->bmp_dev, e->bmp_meta, e->img_dev, S);
+    MSE_LAUNCH_OK();
+    MSE_CHECK(vision_forward(e, (uint32_t)batch, -1, st));
+    e->stats[4] = g_launches.load() - l0;
+    MSE_CUDA(cudaMemcpyAsync(out_f16, e->outb, (size_t)batch * e->cfg[2] * 2, cudaMemcpyDeviceToHost, st));
+    MSE_CUDA(cudaStreamSynchronize(st));
+    return MSE_OK;
+}
+
 MSE_API int mse_encode_images_hidden(mse_encoder *e, const uint8_t *rgb_hwc, int batch, int n_blocks, uint16_t *out_tokens_f16) {
     MSE_REQUIRE(n_blocks >= 0, MSE_ERR_INVALID, "encode_images_hidden: n_blocks must be >= 0");
     return encode_images_impl(e, rgb_hwc, false, batch, out_tokens_f16, false, n_blocks, e ? e->stream : nullptr);

@@ -40,6 +40,17 @@ class Encoder:
         check(lib().mse_encode_images_u8(self._h, x.ctypes.data_as(C.c_void_p), x.shape[0], out.ctypes.data_as(C.c_void_p)), "mse_encode_images_u8")
         return out
 
+    def encode_image_bmp(self, files) -> np.ndarray:
+        """files: image_size x image_size 24-bit BMP files (bytes / uint8 arrays) as the reference's clients send them; unpacked on the
+        device.  Raises MseError (MSE_ERR_UNSUPPORTED) for anything else."""
+        bufs = [np.frombuffer(f, np.uint8) if isinstance(f, (bytes, bytearray, memoryview)) else np.ascontiguousarray(f, np.uint8) for f in files]
+        n = len(bufs)
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        lens = (C.c_size_t * n)(*[b.size for b in bufs])
+        out = np.empty((n, self.dim), np.float16)
+        check(lib().mse_encode_images_bmp(self._h, ptrs, lens, n, out.ctypes.data_as(C.c_void_p)), "mse_encode_images_bmp")
+        return out
+
     def encode_text(self, ids: np.ndarray) -> np.ndarray:
         """ids: [B, ctx] token ids (int). -> [B, dim] fp16."""
         t = np.ascontiguousarray(ids, np.int32)

@@ -122,3 +122,34 @@ def test_full_depth_text_tower(tmp_path_factory, mse):
     out8 = enc.encode_text(ids)
     assert _cos(out8, ref).min() >= 1 - TOL, float(_cos(out8, ref).min())
     assert np.array_equal(out8, enc.encode_text(ids))
+
+
+def test_bmp_files_unpacked_on_device(setup, mse):
+    """mse_encode_images_bmp: the 24-bit BMP files the reference's clients send (src/common.rs:42-53) give the same features as the
+    decoded pixels through mse_encode_images_u8 -- bit for bit; bottom-up and top-down row order; other formats are refused."""
+    import io
+    from PIL import Image
+    T, _, _, enc = setup
+    imgs = T.synthetic_images(31, 3)
+    want = enc.encode_image(imgs)
+
+    def bmp(a):
+        buf = io.BytesIO()
+        Image.fromarray(a).save(buf, format="BMP")
+        return buf.getvalue()
+    files = [bmp(a) for a in imgs]
+    assert np.array_equal(enc.encode_image_bmp(files), want)
+    # top-down variant: negative height, rows in display order
+    f = bytearray(files[0])
+    stride, off = 384 * 3, int.from_bytes(f[10:14], "little")
+    rows = [bytes(f[off + r * stride: off + (r + 1) * stride]) for r in range(384)]
+    f[22:26] = (-384).to_bytes(4, "little", signed=True)
+    f[off:] = b"".join(reversed(rows))
+    assert np.array_equal(enc.encode_image_bmp([bytes(f)]), want[:1])
+    small = io.BytesIO()
+    Image.fromarray(imgs[0][:100, :100]).save(small, format="BMP")
+    png = io.BytesIO()
+    Image.fromarray(imgs[0]).save(png, format="PNG")
+    for bad in (small.getvalue(), png.getvalue(), files[0][:1000]):
+        with pytest.raises(mse.MseError):
+            enc.encode_image_bmp([bad])

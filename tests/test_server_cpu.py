@@ -218,3 +218,33 @@ def test_get_total_embedding_and_select_shard(mse):
     q = cents[3][0] * 2 + 0.01
     assert select_shard(cents, q) == 3
     assert select_shard([(cents[0][0], 1), (cents[0][0], 2)], q) == 1  # ties keep the last maximum
+
+
+def test_client_bmps_take_the_device_path(mse):
+    """size x size 24-bit BMPs (what src/common.rs:42-53 sends) reach the encoder as files; anything else is decoded on the host"""
+    from mse_b200.clip_server import ClipServer, is_client_bmp
+    from PIL import Image
+
+    class BmpEncoder(FakeEncoder):
+        def encode_image_bmp(self, files):
+            self.calls.append(("bmp", len(files)))
+            assert all(is_client_bmp(bytes(f), 384) for f in files)
+            return np.tile((np.ones(1152, np.float32) / np.sqrt(1152)).astype(np.float16), (len(files), 1))
+    enc = BmpEncoder()
+    srv = ClipServer({"device": "cuda:0", "model": "m", "model_name": "m", "max_batch_size": 4, "port": 0}, encoder=enc, tokenizer=FakeTokenizer(),
+                     registry=CollectorRegistry())
+    png = io.BytesIO()
+    Image.fromarray(np.zeros((384, 384, 3), np.uint8)).save(png, format="PNG")
+    small = io.BytesIO()
+    Image.fromarray(np.zeros((100, 100, 3), np.uint8)).save(small, format="BMP")
+    assert is_client_bmp(_bmp(1), 384) and not is_client_bmp(png.getvalue(), 384) and not is_client_bmp(small.getvalue(), 384)
+
+    async def scenario(c):
+        r = await c.post("/", data=msgpack.dumps({"images": [_bmp(1), _bmp(2)]}))
+        assert r.status == 200 and len(msgpack.loads(await r.read())) == 2
+        r = await c.post("/", data=msgpack.dumps({"images": [_bmp(1), png.getvalue()]}))
+        assert r.status == 200 and len(msgpack.loads(await r.read())) == 2
+        m = (await (await c.get("/metrics")).read()).decode()
+        assert 'modelserver_total_items_total{modality="image",model="m"} 4.0' in m
+    _run(srv, scenario)
+    assert ("bmp", 2) in enc.calls and ("image", 2) in enc.calls
