@@ -25,28 +25,67 @@ struct GemmOut {
     size_t splitk_ws_floats;
 };
 
-// erf-GELU x * Phi(x) with Phi(x) - 1/2 = x * P(x^2): degree-13 Chebyshev fit on |x| <= 5.6 evaluated by Horner in fp32 (x is clamped;
-// 1 - Phi(5.6) = 1e-8).  Max abs error of the GELU value against the erf form: 3.1e-6 (fit script: see DESIGN.md 4.1), far below
-// the fp16 resolution of the activations it produces.  16 FMA-pipe instructions per element instead of ~30 for 0.5*x*(1+erff(x/sqrt2));
-// a MUFU-based erf (rcp + ex2) was measured 35 % slower: the epilogue's eight warps share one 16/clk MUFU pipe.
+// erf-GELU x * Phi(x) = x / 2 + |x| * t,  t = Phi(|x|) - 1/2 = xa * P(u),  xa = min(|x|, 4.75),  u = 2 xa^2 / 4.75^2 - 1:
+// degree-10 minimax fit (weighted by x^2, Lawson iteration; script in DESIGN.md 4.1) evaluated by Horner in fp32.  Max abs error of
+// the GELU value against the erf form: 3.8e-6 inside the clamp, |x| (1 - Phi(4.75)) = |x| * 1e-6 beyond it -- far below the fp16
+// resolution of the activations it produces.  A MUFU-based erf (rcp + ex2) was measured 35 % slower: the epilogue's eight warps
+// share one 16/clk MUFU pipe.  gelu_erf_x2 is the same arithmetic, two columns per instruction with sm_100's packed fp32
+// (fma.rn.f32x2 -> FFMA2): 10 issue slots per element instead of 21 -- the fc1 epilogue ran at 0.78 of its tile's MMA time.
+#define MSE_GELU_COEFFS(X)                                                                                                             \
+    X(-0.0037710467566411787f) X(0.0050159604463918773f) X(-0.007168797293015801f)                                                     \
+    X(0.013405637279248876f) X(-0.021649570172050516f) X(0.03040285206127552f) X(-0.040568225240212849f)                               \
+    X(0.053235260469440548f) X(-0.073667546748732174f) X(0.14874829418180313f)
+static constexpr float kGeluC10 = 0.0012802706565601153f;   // leading coefficient, the others follow in Horner order
+static constexpr float kGeluClamp = 4.75f, kGeluUScale = 2.0f / (4.75f * 4.75f);
+
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float xc = fminf(fmaxf(x, -5.6f), 5.6f);
-    const float u = fmaf(xc * xc, 2.0f / 31.36f, -1.0f);
-    float p = -0.0018866477767005563f;
-    p = fmaf(p, u, 0.0037634270265698433f);
-    p = fmaf(p, u, -0.0009497968712821603f);
-    p = fmaf(p, u, 0.0012473699171096087f);
-    p = fmaf(p, u, -0.00902568269520998f);
-    p = fmaf(p, u, 0.013778206892311573f);
-    p = fmaf(p, u, -0.01513815950602293f);
-    p = fmaf(p, u, 0.019960511475801468f);
-    p = fmaf(p, u, -0.02644316665828228f);
-    p = fmaf(p, u, 0.03213409334421158f);
-    p = fmaf(p, u, -0.03833318129181862f);
-    p = fmaf(p, u, 0.04697057232260704f);
-    p = fmaf(p, u, -0.06305162608623505f);
-    p = fmaf(p, u, 0.1262596994638443f);
-    return fmaf(x, xc * p, 0.5f * x);
+    const float xa = fminf(fabsf(x), kGeluClamp);
+    const float u = fmaf(xa * xa, kGeluUScale, -1.0f);
+    float p = kGeluC10;
+#define MSE_GELU_STEP(c) p = fmaf(p, u, c);
+    MSE_GELU_COEFFS(MSE_GELU_STEP)
+#undef MSE_GELU_STEP
+    return fmaf(fabsf(x), xa * p, 0.5f * x);
+}
+
+namespace f32x2 {
+__device__ __forceinline__ unsigned long long pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+}  // namespace f32x2
+
+// two columns at once; bit-identical to gelu_erf per element (the same fp32 operations in the same order)
+__device__ __forceinline__ void gelu_erf_x2(float &x0, float &x1) {
+    const float a0 = fminf(fabsf(x0), kGeluClamp), a1 = fminf(fabsf(x1), kGeluClamp);
+    const unsigned long long xa = f32x2::pack(a0, a1), x = f32x2::pack(x0, x1);
+    const unsigned long long u = f32x2::fma(f32x2::mul(xa, xa), f32x2::pack(kGeluUScale, kGeluUScale), f32x2::pack(-1.0f, -1.0f));
+    unsigned long long p = f32x2::pack(kGeluC10, kGeluC10);
+#define MSE_GELU_STEP(c) p = f32x2::fma(p, u, f32x2::pack(c, c));
+    MSE_GELU_COEFFS(MSE_GELU_STEP)
+#undef MSE_GELU_STEP
+    float t0, t1, h0, h1;
+    f32x2::unpack(f32x2::mul(xa, p), t0, t1);
+    f32x2::unpack(f32x2::mul(x, f32x2::pack(0.5f, 0.5f)), h0, h1);
+    x0 = fmaf(fabsf(x0), t0, h0);
+    x1 = fmaf(fabsf(x1), t1, h1);
 }
 __device__ __forceinline__ float gelu_tanh(float x) {
     const float k0 = 0.7978845608028654f, k1 = 0.044715f;
@@ -86,7 +125,12 @@ struct LinearEpilogueT {
         }
         if (o.act == ACT_GELU_ERF) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = __float_as_uint(gelu_erf(__uint_as_float(v[j])));
+            for (int j = 0; j < 32; j += 2) {
+                float x0 = __uint_as_float(v[j]), x1 = __uint_as_float(v[j + 1]);
+                gelu_erf_x2(x0, x1);
+                v[j] = __float_as_uint(x0);
+                v[j + 1] = __float_as_uint(x1);
+            }
         } else if (o.act == ACT_GELU_TANH) {
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] = __float_as_uint(gelu_tanh(__uint_as_float(v[j])));

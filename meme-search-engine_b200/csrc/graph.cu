@@ -269,6 +269,15 @@ __global__ void __launch_bounds__(kGsThreads) k_greedy_search(GraphArgs g, const
 // pass, fastdot.cuh wq_score2), which is what hides the HBM gather latency: 0.49 of the HBM copy peak at 4096 queries.
 
 static constexpr int kWqWarps = 4;   // warps (queries in flight) per CTA
+// greedy search: rows started towards L2 ahead of the scoring pass (0 = off; MSE_GREEDY_PF overrides, a tuning aid).  Measured at the
+// C4 shard (12.5 M rows, 4096 queries, L = 64; profiles/r03b_greedy_prefetch_sweep.json): 0 rows 5.30 ms, 6 rows 4.36 ms, 10 rows 4.95 ms,
+// 16 rows 5.22 ms -- deeper prefetch evicts rows from L2 before their pass reads them (4096 queries x 6 rows x 2304 B = 57 MB in flight).
+// Also measured without effect: prefetching the next hop's adjacency list during the inserts (4.37 ms), halving the visited-set tables (4.42 ms).
+static int greedy_pf_rows() {
+    const char *e = getenv("MSE_GREEDY_PF");
+    const int v = e ? atoi(e) : 6;
+    return v < 0 ? 0 : (v > 64 ? 64 : v);
+}
 
 __host__ __device__ static size_t wq_warp_bytes(uint32_t L, uint32_t stride, uint32_t d) {
     size_t o = (size_t)(L + 1) * 8 + (size_t)stride * 8 + (size_t)(L + 1) * 4 + (size_t)stride * 4 + (size_t)stride * 4 + (size_t)d * 4 + (L + 1);
@@ -291,7 +300,7 @@ template <int NC2>
 __global__ void __launch_bounds__(kWqWarps * 32, 8) k_greedy_search_wq(GraphArgs g, const __half *__restrict__ queries, const uint32_t *__restrict__ q_rows,
                                                                        uint32_t nq, const uint32_t *__restrict__ starts, uint32_t start_all, uint32_t L,
                                                                        uint32_t filter_from_all, uint32_t filter_self_from, uint32_t *htabs, uint32_t hcap,
-                                                                       GreedyOut out) {
+                                                                       GreedyOut out, int pf_rows) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t S = g.stride;
@@ -359,9 +368,17 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_greedy_search_wq(GraphArgs
                 n_pre += __popc(m);
                 __syncwarp();
             }
-            // exact scores, two rows per pass (:201-204)
+            // exact scores, two rows per pass (:201-204).  A pass is one dependent round trip to HBM (the loads of a pass are issued together,
+            // the passes follow each other), so the rows of the passes pf_rows / 2 ahead are started towards L2 while this one is scored:
+            // lane l < lines asks for the l-th 128-byte line of a row.
+            const int lines = (int)((g.d * 2 + 127) / 128);
+            auto prefetch_row = [&](int r) {
+                if (r < n_pre && lane < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)(g.x + (size_t)pre[r] * g.d) + lane * 128));
+            };
+            for (int r = 0; r < pf_rows; r++) prefetch_row(r);
             for (int i = 0; i < n_pre; i += 2) {
                 const int j = i + 1 < n_pre ? i + 1 : i;
+                if (pf_rows) { prefetch_row(i + pf_rows); prefetch_row(i + pf_rows + 1); }
                 long long s0, s1;
                 wq_score2<NC2>(qs, g.x + (size_t)pre[i] * g.d, g.x + (size_t)pre[j] * g.d, g.d, lane, s0, s1);
                 if (lane == 0) { pre_scores[i] = s0; pre_scores[j] = s1; }
@@ -950,7 +967,9 @@ __global__ void k_check_adjacency(const uint32_t *__restrict__ adj, const uint32
 // table under ~15 % full, and the kernels stop with an overflow status at 75 % rather than degrade (the tables are cleared per
 // query, so their size is HBM write traffic)
 uint32_t greedy_hash_capacity(uint32_t L, uint32_t stride) {
-    uint64_t v = (uint64_t)(L > 64 ? L : 64) * stride * 4;
+    const char *e = getenv("MSE_GREEDY_HASH_SCALE");   // tuning aid
+    const long scale = e ? atol(e) : 4;
+    uint64_t v = (uint64_t)(L > 64 ? L : 64) * stride * (uint64_t)(scale > 0 ? scale : 4);
     uint32_t p = 1024;
     while (p < v && p < (1u << 30)) p <<= 1;
     return p;
@@ -982,10 +1001,10 @@ int greedy_search_launch(mse_index *ix, const __half *d_queries, const uint32_t 
             const uint32_t grid = std::min<uint32_t>(workers / kWqWarps, (nq + kWqWarps - 1) / kWqWarps);
             if (fixed) {
                 MSE_CUDA(cudaFuncSetAttribute(k_greedy_search_wq<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_greedy_search_wq<18><<<grid, kWqWarps * 32, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, filter_self_from, d_htabs, hcap, o);
+                k_greedy_search_wq<18><<<grid, kWqWarps * 32, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, filter_self_from, d_htabs, hcap, o, greedy_pf_rows());
             } else {
                 MSE_CUDA(cudaFuncSetAttribute(k_greedy_search_wq<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_greedy_search_wq<0><<<grid, kWqWarps * 32, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, filter_self_from, d_htabs, hcap, o);
+                k_greedy_search_wq<0><<<grid, kWqWarps * 32, smem, st>>>(g, d_queries, d_q_rows, nq, d_starts, start, L, filter_from, filter_self_from, d_htabs, hcap, o, greedy_pf_rows());
             }
             MSE_LAUNCH_OK();
             return MSE_OK;

@@ -63,12 +63,21 @@ if "--cuda-profiler" in sys.argv:      # ncu --profile-from-start off: capture t
     torch.cuda.cudart().cudaProfilerStart()
 for v in variants:
     p = v.split(":")
-    if p[0] == "g":
+    if p[0] == "g":                      # g:L[:pf=<rows prefetched>][:hs=<visited-set scale>]  (tuning aids of csrc/graph.cu)
         L = int(p[1])
+        import os
+        for kv in p[2:]:
+            key, val = kv.split("=")
+            os.environ[{"pf": "MSE_GREEDY_PF", "hs": "MSE_GREEDY_HASH_SCALE"}[key]] = val
         ids = torch.empty((nq, L), dtype=torch.int32, device=dev); sc = torch.empty((nq, L), dtype=torch.int64, device=dev)
         ln = torch.empty(nq, dtype=torch.int32, device=dev); dist = torch.empty(nq, dtype=torch.int64, device=dev)
         ms = timed(lambda: dk.greedy_search_dev(vl, q16.data_ptr(), nq, L, med, ids.data_ptr(), sc.data_ptr(), ln.data_ptr(), dist.data_ptr(), stream))
-        dk.greedy_search_check(vl, nq)
+        try:
+            dk.greedy_search_check(vl, nq)
+        except Exception as e:   # e.g. a visited-set overflow with a tuning override
+            out[v] = {"ms": ms, "error": str(e)}
+            print(json.dumps({v: out[v]}), flush=True)
+            continue
         nd = float(dist.double().sum().item())
         out[v] = {"ms": ms, "qps": nq / ms * 1e3, "recall_at_10": recall(ids), "distances_per_query": nd / nq, "row_gbs": nd * D * 2 / (ms * 1e-3) / 1e9}
     else:
@@ -81,4 +90,5 @@ for v in variants:
         ex, co = float(cm.double().sum().item()), float(pc.double().sum().item())
         out[v] = {"ms": ms, "qps": nq / ms * 1e3, "recall_at_10": recall(ti), "exact_rows_per_query": ex / nq, "codes_per_query": co / nq,
                   "algorithmic_gbs": (ex * (D * 2 + R * 4) + co * 68) / (ms * 1e-3) / 1e9}
+    print(json.dumps({v: out[v]}), flush=True)
 print(json.dumps(out))
