@@ -12,6 +12,7 @@
 // (zero columns) and handled as 9 n-tiles of 8 for P V.  Tensor-core math is warp-level mma.sync m16n8k16
 // (fp16 in, fp32 accumulate).  10 % of the tower's FLOPs live here; the GEMMs are on tcgen05.
 #pragma once
+#include "common.cuh"
 #include <cuda_fp16.h>
 #include <stdint.h>
 
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(kThreads) k_mha_fwd(const __half *__restrict__
     const __half *kg = base + D + (size_t)h * kDH;
     const __half *vg = base + 2 * D + (size_t)h * kDH;
 
+    pdl_trigger();
     // zero the pad columns [72, 88) of every tile row once; cp.async never writes them
     for (int i = tid; i < kBM + 4 * kBN; i += kThreads) {
         __half *row = i < kBM ? sm.q[i] : (i < kBM + 2 * kBN ? sm.k[(i - kBM) / kBN][(i - kBM) % kBN]
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(kThreads) k_mha_fwd(const __half *__restrict__
         *(uint4 *)(row + 72) = make_uint4(0, 0, 0, 0);
         *(uint4 *)(row + 80) = make_uint4(0, 0, 0, 0);
     }
+    pdl_wait();   // qkv is the previous kernel's output (launched with launch_pdl: common.cuh)
     // Q tile + first K/V tile
     for (int i = tid; i < kBM * 9; i += kThreads) {
         int r = i / 9, c = i % 9;

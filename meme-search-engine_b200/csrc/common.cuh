@@ -54,6 +54,37 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
     } while (0)
 
 int use_device(int device);   // cudaSetDevice + verifies compute capability 10.x
+bool pdl_enabled();            // MSE_NO_PDL=1 switches programmatic dependent launch off (A/B measurements)
+
+// Programmatic dependent launch (PDL).  A kernel launched with launch_pdl may start while its predecessor on the stream is still
+// running: everything it does before pdl_wait() (index math, shared-memory setup, prefetch of WEIGHTS -- nothing the predecessor
+// writes) overlaps the predecessor's tail; pdl_wait() returns once the predecessor has completed and its writes are visible.
+// pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as every CTA of this one has called it.  The batch-1 text tower is
+// 194 dependent kernels of a few microseconds: the launch-to-launch gap and the cold start of each weight stream are what PDL hides.
+// Measured (profiles/r03c_text_latency_pdl.md): letting the next kernel's CTAs in EARLY (pdl_trigger at kernel start) is a loss -- the
+// co-resident CTAs of up to three kernels fight over shared memory and HBM (batch 1: 2.57 ms against 1.84 ms without PDL); with the
+// implicit trigger at kernel exit the pre-staged launch still saves 0.45 ms of an eager forward pass (2.24 -> 1.79 ms) and 0.07 ms of
+// the graph replay (1.84 -> 1.77 ms).
+// Rule: a kernel is launched with launch_pdl only if it calls pdl_wait() before its first dependent access.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
 
 // cudaFuncSetAttribute applies to the current device only: a call site remembers which devices it has configured
 // (handles are independent across devices, so one process may drive several)

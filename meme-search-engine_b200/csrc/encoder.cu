@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(256) k_layernorm(const __half *__restrict__ x,
                                                    uint32_t in_stride, uint32_t in_offset) {
     const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
     if (row >= rows) return;
     const uint4 *xr = (const uint4 *)(x + (size_t)row * in_stride + in_offset);
     const uint32_t nv = D >> 3;
@@ -182,6 +184,8 @@ __global__ void __launch_bounds__(128) k_map_pool(const __half *__restrict__ kv,
 __global__ void __launch_bounds__(256) k_l2norm_f16(const __half *__restrict__ x, __half *__restrict__ out, uint32_t rows, uint32_t D) {
     const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
     if (row >= rows) return;
     float s = 0.f;
     for (uint32_t j = lane; j < D; j += 32) {
@@ -198,6 +202,8 @@ __global__ void __launch_bounds__(256) k_text_embed(const int32_t *__restrict__ 
                                                     __half *__restrict__ x, uint32_t rows, uint32_t S, uint32_t D, uint32_t vocab) {
     const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();   // the previous forward pass may still be reading x
     if (row >= rows) return;
     uint32_t id = (uint32_t)ids[row];
     if (id >= vocab) id = 0;
@@ -212,6 +218,8 @@ __global__ void __launch_bounds__(256) k_text_embed(const int32_t *__restrict__ 
 // gather one token per sequence: out[b] = x[b*S + idx]
 __global__ void k_gather_token(const __half *__restrict__ x, __half *__restrict__ out, uint32_t B, uint32_t S, uint32_t idx, uint32_t D) {
     const uint32_t b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     for (uint32_t j = threadIdx.x; j < D / 8; j += blockDim.x)
         ((uint4 *)(out + (size_t)b * D))[j] = ((const uint4 *)(x + ((size_t)b * S + idx) * D))[j];
 }
@@ -461,8 +469,8 @@ int gemm(mse_encoder *e, const __half *A, const __half *W, uint32_t M, uint32_t 
 }
 
 int layernorm(const __half *x, __half *y, const float *g, const float *b, uint32_t rows, uint32_t D, cudaStream_t st) {
-    if (D <= 5 * 256) k_layernorm<5><<<(rows * 32 + 255) / 256, 256, 0, st>>>(x, y, g, b, rows, D, 1e-6f, D, 0);
-    else k_layernorm<8><<<(rows * 32 + 255) / 256, 256, 0, st>>>(x, y, g, b, rows, D, 1e-6f, D, 0);
+    if (D <= 5 * 256) launch_pdl(k_layernorm<5>, (rows * 32 + 255) / 256, 256, 0, st, x, y, g, b, rows, D, 1e-6f, D, 0u);
+    else launch_pdl(k_layernorm<8>, (rows * 32 + 255) / 256, 256, 0, st, x, y, g, b, rows, D, 1e-6f, D, 0u);
     MSE_LAUNCH_OK();
     return MSE_OK;
 }
@@ -497,8 +505,8 @@ int run_blocks(mse_encoder *e, const TowerW &tw, int depth, uint32_t B, uint32_t
         if (use_tc)
             attn_tc::k_mha_tc<<<std::min(ap.n_items, sm_count(e->device)), attn_tc::kThreads, attn_tc::kSmemBytes, st>>>(tm64, tm16, e->att, ap);
         else
-            attn::k_mha_fwd<<<dim3((S + attn::kBM - 1) / attn::kBM, H, B), attn::kThreads, sizeof(attn::Smem), st>>>(e->qkv, e->att, (int)S, (int)H,
-                                                                                                                       scale_log2e);
+            launch_pdl(attn::k_mha_fwd, dim3((S + attn::kBM - 1) / attn::kBM, H, B), attn::kThreads, sizeof(attn::Smem), st, (const __half *)e->qkv, e->att,
+                       (int)S, (int)H, scale_log2e);
         prof_mark(e, 1, st);
         MSE_LAUNCH_OK();
         MSE_CHECK(gemm(e, e->att, L.proj_w, T, D, D, e->x, L.proj_b, ACT_NONE, e->x, 0, st));
@@ -530,23 +538,23 @@ int vision_forward(mse_encoder *e, uint32_t B, int layer_stop, cudaStream_t st) 
     MSE_CHECK(layernorm(e->y, e->yn, e->pln_g, e->pln_b, B, D, st));
     MSE_CHECK(gemm(e, e->yn, e->pfc1_w, B, F, D, e->hh, e->pfc1_b, act, nullptr, 0, st));
     MSE_CHECK(gemm(e, e->hh, e->pfc2_w, B, D, F, e->z, e->pfc2_b, ACT_NONE, e->y, 0, st));
-    k_l2norm_f16<<<(B * 32 + 255) / 256, 256, 0, st>>>(e->z, e->outb, B, D);
+    launch_pdl(k_l2norm_f16, (B * 32 + 255) / 256, 256, 0, st, e->z, e->outb, B, D);
     MSE_LAUNCH_OK();
     return MSE_OK;
 }
 
 int text_forward(mse_encoder *e, uint32_t B, int layer_stop, cudaStream_t st) {
     const uint32_t D = e->cfg[2], S = e->cfg[7], T = B * S;
-    k_text_embed<<<(T * 32 + 255) / 256, 256, 0, st>>>(e->ids_dev, e->tok_emb, e->pos_t, e->x, T, S, D, (uint32_t)e->cfg[6]);
+    launch_pdl(k_text_embed, (T * 32 + 255) / 256, 256, 0, st, e->ids_dev, e->tok_emb, e->pos_t, e->x, T, S, D, (uint32_t)e->cfg[6]);
     MSE_LAUNCH_OK();
     const int depth = layer_stop >= 0 ? std::min(layer_stop, (int)e->cfg[11]) : (int)e->cfg[11];
     MSE_CHECK(run_blocks(e, e->txt, depth, B, S, st));
     if (layer_stop >= 0) return MSE_OK;
     MSE_CHECK(layernorm(e->x, e->xn, e->txt.lnf_g, e->txt.lnf_b, T, D, st));
-    k_gather_token<<<B, 128, 0, st>>>(e->xn, e->pool, B, S, S - 1, D);
+    launch_pdl(k_gather_token, B, 128, 0, st, e->xn, e->pool, B, S, S - 1, D);
     MSE_LAUNCH_OK();
     MSE_CHECK(gemm(e, e->pool, e->tproj_w, B, D, D, e->z, e->tproj_b, ACT_NONE, nullptr, 0, st));
-    k_l2norm_f16<<<(B * 32 + 255) / 256, 256, 0, st>>>(e->z, e->outb, B, D);
+    launch_pdl(k_l2norm_f16, (B * 32 + 255) / 256, 256, 0, st, e->z, e->outb, B, D);
     MSE_LAUNCH_OK();
     return MSE_OK;
 }

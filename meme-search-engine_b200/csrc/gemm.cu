@@ -66,7 +66,7 @@ static int launch_skinny(int out_device, const __half *dA, const __half *dB, uin
         splits = std::max<uint32_t>(1, std::min<uint32_t>(nk, (uint32_t)sm_count(out_device) / (slices * mt)));
         while (splits > 1 && (size_t)splits * mt * skinny::kBM * slices * BN > out.splitk_ws_floats) splits--;
     }
-    kern<<<dim3(slices, mt, splits), skinny::kThreads, skinny::smem_bytes<BN>(), st>>>(dA, dB, M, N, K, lda, ldb, out);
+    launch_pdl(kern, dim3(slices, mt, splits), skinny::kThreads, skinny::smem_bytes<BN>(), st, dA, dB, M, N, K, lda, ldb, out);
     MSE_LAUNCH_OK();
     return MSE_OK;
 }
@@ -78,7 +78,7 @@ static int launch_skinny_pr(int device, const __half *dA, const __half *dB, uint
     auto kern = skinny::pr::k_gemm_skinny_pr<BN>;
     static PerDeviceOnce once;
     if (once.first(device)) MSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skinny::pr::smem_bytes<BN>()));
-    kern<<<(N + BN - 1) / BN, skinny::pr::kThreads, skinny::pr::smem_bytes<BN>(), st>>>(dA, dB, M, N, K, lda, ldb, out);
+    launch_pdl(kern, (N + BN - 1) / BN, skinny::pr::kThreads, skinny::pr::smem_bytes<BN>(), st, dA, dB, M, N, K, lda, ldb, out);
     MSE_LAUNCH_OK();
     return MSE_OK;
 }
@@ -102,6 +102,7 @@ int gemm_f16_tn_dev(int device, const __half *dA, const __half *dB, uint32_t M, 
     if (M <= kSkinnyMaxM && force_bn == 0 && ((uintptr_t)dA & 15) == 0 && ((uintptr_t)dB & 15) == 0 && getenv("MSE_GEMM_NO_SKINNY") == nullptr) {
         GemmOut o = out;
         o.res_in_place = 0;
+        { const char *t = getenv("MSE_PDL_TRIGGER"); o.pdl_trigger_at = t ? atoi(t) : 2; }   // tuning aid; measured at batch 1: 0 -> 2.57 ms, 1 -> 1.93 ms, 2 -> 1.77 ms (no PDL: 1.84 ms)
         // Wide slices + split over K (few readers of the activation panel, every SM busy) -- measured SLOWER than one narrow slice per
         // CTA (text tower at batch 1: 4.0 ms vs 2.12 ms, profiles/r01p_skinny_gemm_ncu_full.md): the last CTA of a tile serialises the
         // fixed-order reduction of up to 16 partial tiles behind a device-wide fence.  Kept for experiments only.

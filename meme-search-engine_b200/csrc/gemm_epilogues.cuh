@@ -23,6 +23,7 @@ struct GemmOut {
     float *splitk_ws;      // [splits][rows rounded to 64][ldws] fp32
     uint32_t *splitk_cnt;  // [n-slices x m-tiles]
     size_t splitk_ws_floats;
+    int pdl_trigger_at;    // skinny kernels: where the CTA lets the next kernel's CTAs be scheduled (common.cuh): 0 start, 1 after the main loop, 2 never
 };
 
 // erf-GELU x * Phi(x) = x / 2 + |x| * t,  t = Phi(|x|) - 1/2 = xa * P(u),  xa = min(|x|, 4.75),  u = 2 xa^2 / 4.75^2 - 1:

@@ -9,6 +9,7 @@
 // (fp16 x fp16 -> fp32) -- at 2 FLOP/B the tensor pipe idles either way; tcgen05 would add TMEM round trips for no gain.
 // Epilogue: GemmOut semantics of gemm_epilogues.cuh (bias, erf/tanh GELU, residual or position embedding, fp16 / fp32 stores).
 #pragma once
+#include "common.cuh"
 #include "gemm_epilogues.cuh"
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -63,17 +64,18 @@ __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restri
     const uint32_t kt0 = (uint32_t)((uint64_t)nk_all * blockIdx.z / splits), kt1 = (uint32_t)((uint64_t)nk_all * (blockIdx.z + 1) / splits);
     const uint32_t nk = kt1 - kt0;
 
-    auto load_stage = [&](uint32_t kt, int st) {
+    auto load_a = [&](uint32_t kt, int st) {                           // A: 64 rows x 8 chunks of 16 B = one chunk per thread
         const uint32_t k0 = (kt0 + kt) * kBK;
         __half *a = sA + (size_t)st * kBM * kPitch;
+        const int r = tid >> 3, kc = (tid & 7) * 8;
+        const bool ok = m0 + r < M && k0 + kc < K;                    // K % 8 == 0: a chunk is entirely inside or outside
+        cp_async16(a + r * kPitch + kc, A + (size_t)(ok ? m0 + r : 0) * lda + (ok ? k0 + kc : 0), ok);
+    };
+    auto load_b = [&](uint32_t kt, int st) {                           // B: BN rows x 8 chunks
+        const uint32_t k0 = (kt0 + kt) * kBK;
         __half *b = sB + (size_t)st * BN * kPitch;
-        {                                                              // A: 64 rows x 8 chunks of 16 B = one chunk per thread
-            const int r = tid >> 3, kc = (tid & 7) * 8;
-            const bool ok = m0 + r < M && k0 + kc < K;                // K % 8 == 0: a chunk is entirely inside or outside
-            cp_async16(a + r * kPitch + kc, A + (size_t)(ok ? m0 + r : 0) * lda + (ok ? k0 + kc : 0), ok);
-        }
 #pragma unroll
-        for (int i = 0; i < (BN * 8 + kThreads - 1) / kThreads; i++) {  // B: BN rows x 8 chunks
+        for (int i = 0; i < (BN * 8 + kThreads - 1) / kThreads; i++) {
             const int c = tid + i * kThreads, r = c >> 3, kc = (c & 7) * 8;
             if (c < BN * 8) {
                 const bool ok = n0 + r < N && k0 + kc < K;
@@ -81,14 +83,23 @@ __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restri
             }
         }
     };
+    auto load_stage = [&](uint32_t kt, int st) { load_a(kt, st); load_b(kt, st); };
 
     float acc[BN / 8][4];
 #pragma unroll
     for (int j = 0; j < BN / 8; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 
+    // Programmatic dependent launch (common.cuh): the WEIGHT tiles of the first stages do not depend on the previous kernel, so they are
+    // requested before pdl_wait() and stream in while the previous kernel drains; the activation tiles follow after it.  All of these
+    // weight requests belong to the first commit group, which every later wait covers.
+    if (o.pdl_trigger_at == 0) pdl_trigger();
+#pragma unroll
+    for (int s = 0; s < kStages - 1; s++)
+        if ((uint32_t)s < nk) load_b(s, s);
+    pdl_wait();
 #pragma unroll
     for (int s = 0; s < kStages - 1; s++) {
-        if ((uint32_t)s < nk) load_stage(s, s);
+        if ((uint32_t)s < nk) load_a(s, s);
         cp_async_commit();
     }
     for (uint32_t kt = 0; kt < nk; kt++) {
@@ -110,6 +121,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_skinny(const __half *__restri
         }
     }
     cp_async_wait<0>();
+    if (o.pdl_trigger_at == 1) pdl_trigger();
     __syncthreads();                                                  // the pipeline buffers are free: reuse them for the reduction
     float *red = (float *)smem_raw;                                   // [3][4 warps][BN / 2][32 lanes]
     if (kq > 0) {
@@ -240,6 +252,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_skinny_pr(const __half *__res
         const uint32_t kc = min((uint32_t)kKcMax, K - kc0);
         const uint32_t nk = (kc + kBK - 1) / kBK;
         if (kc0) __syncthreads();                                     // everyone is done with the previous panel chunk and ring
+        else pdl_wait();   // TODO(perf): the first weight stages could be requested before this wait, as in k_gemm_skinny
         // panel chunk: 64 rows x kc halfs, 16-byte chunks; rows >= M and columns >= K are zero-filled
         {
             const uint32_t chunks_per_row = nk * 8;

@@ -1,6 +1,7 @@
 // Library-wide state: error string, device checks, launch counter.
 #include "common.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace mse {
 
@@ -12,6 +13,11 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(t_err, sizeof(t_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    const char *e = getenv("MSE_NO_PDL");   // read per call: a tuning switch, not a hot path
+    return !(e && atoi(e) != 0);
 }
 
 static std::mutex g_dev_mu;

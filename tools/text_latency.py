@@ -15,7 +15,7 @@ del sd
 enc = mse_b200.Encoder(path, device=0, max_batch=64)
 os.remove(path)
 out = {"floor_ms_weights_over_hbm": 0.826e9 / (peaks()["hbm"] * 1e9) * 1e3}
-for B in (1, 2, 4, 8, 16, 32, 64):
+for B in ([int(a) for a in sys.argv[1:]] or [1, 2, 4, 8, 16, 32, 64]):   # usage: text_latency.py [batch ...]
     ids = torch.randint(2, 32000, (B, 64), dtype=torch.int32, device=dev)
     feat = torch.empty((B, 1152), dtype=torch.float16, device=dev)
     for _ in range(5):
