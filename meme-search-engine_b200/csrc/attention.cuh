@@ -64,13 +64,13 @@ struct Smem {
     __half v[2][kBN][kPitch];
 };
 
-// grid: (ceil(S / 64), H, B)
-__global__ void __launch_bounds__(kThreads) k_mha_fwd(const __half *__restrict__ qkv, __half *__restrict__ out, int S, int H,
-                                                      float scale_log2e) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+// One tile of 64 query rows of one (b, h).  NT threads take part in the loads and the barriers; warps 0-3 (16 rows each) do the math, so
+// the function serves both the 128-thread kernel below and the 512-thread persistent text kernel (text_mega.cuh).
+template <int NT>
+__device__ __forceinline__ void mha_tile(const __half *__restrict__ qkv, __half *__restrict__ out, Smem &sm, int S, int H, int q0, int h, int b,
+                                         float scale_log2e) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q0 = blockIdx.x * kBM, h = blockIdx.y, b = blockIdx.z;
+    const bool math = warp < kBM / 16;
     const int D = H * kDH;
     const size_t ld = (size_t)3 * D;
     const __half *base = qkv + (size_t)b * S * ld;
@@ -78,23 +78,21 @@ __global__ void __launch_bounds__(kThreads) k_mha_fwd(const __half *__restrict__
     const __half *kg = base + D + (size_t)h * kDH;
     const __half *vg = base + 2 * D + (size_t)h * kDH;
 
-    pdl_trigger();
     // zero the pad columns [72, 88) of every tile row once; cp.async never writes them
-    for (int i = tid; i < kBM + 4 * kBN; i += kThreads) {
+    for (int i = tid; i < kBM + 4 * kBN; i += NT) {
         __half *row = i < kBM ? sm.q[i] : (i < kBM + 2 * kBN ? sm.k[(i - kBM) / kBN][(i - kBM) % kBN]
                                                              : sm.v[(i - kBM - 2 * kBN) / kBN][(i - kBM - 2 * kBN) % kBN]);
         *(uint4 *)(row + 72) = make_uint4(0, 0, 0, 0);
         *(uint4 *)(row + 80) = make_uint4(0, 0, 0, 0);
     }
-    pdl_wait();   // qkv is the previous kernel's output (launched with launch_pdl: common.cuh)
     // Q tile + first K/V tile
-    for (int i = tid; i < kBM * 9; i += kThreads) {
+    for (int i = tid; i < kBM * 9; i += NT) {
         int r = i / 9, c = i % 9;
         bool ok = q0 + r < S;
         cp_async16(&sm.q[r][c * 8], qg + (size_t)(ok ? q0 + r : 0) * ld + c * 8, ok);
     }
     auto load_kv = [&](int buf, int k0) {
-        for (int i = tid; i < kBN * 9; i += kThreads) {
+        for (int i = tid; i < kBN * 9; i += NT) {
             int r = i / 9, c = i % 9;
             bool ok = k0 + r < S;
             size_t off = (size_t)(ok ? k0 + r : 0) * ld + c * 8;
@@ -122,6 +120,7 @@ __global__ void __launch_bounds__(kThreads) k_mha_fwd(const __half *__restrict__
             cp_async_wait<0>();
         }
         __syncthreads();
+        if (math) {
         if (t == 0) {
 #pragma unroll
             for (int ks = 0; ks < 5; ks++)
@@ -193,8 +192,10 @@ __global__ void __launch_bounds__(kThreads) k_mha_fwd(const __half *__restrict__
             ldsm_x2_t(b0, b1, &sm.v[buf][ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][64]);
             mma16816(o[8], pf[ks], b0, b1);
         }
+        }
         __syncthreads();  // everyone is done with buf before the next iteration's prefetch overwrites it
     }
+    if (!math) return;
     // finalize: rows (lane/4) and (lane/4 + 8) of this warp
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -208,6 +209,16 @@ __global__ void __launch_bounds__(kThreads) k_mha_fwd(const __half *__restrict__
         if (r0 < S) *(__half2 *)(ob + (size_t)r0 * D + j * 8) = __floats2half2_rn(o[j][0] * i0, o[j][1] * i0);
         if (r1 < S) *(__half2 *)(ob + (size_t)r1 * D + j * 8) = __floats2half2_rn(o[j][2] * i1, o[j][3] * i1);
     }
+}
+
+// grid: (ceil(S / 64), H, B)
+__global__ void __launch_bounds__(kThreads) k_mha_fwd(const __half *__restrict__ qkv, __half *__restrict__ out, int S, int H,
+                                                      float scale_log2e) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    pdl_trigger();
+    pdl_wait();   // qkv is the previous kernel's output (launched with launch_pdl: common.cuh)
+    mha_tile<kThreads>(qkv, out, sm, S, H, blockIdx.x * kBM, blockIdx.y, blockIdx.z, scale_log2e);
 }
 
 }  // namespace attn

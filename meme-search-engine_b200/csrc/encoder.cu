@@ -14,6 +14,7 @@
 #include "gemm_epilogues.cuh"
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "text_mega.cuh"
 #include "gemm_sm100.cuh"
 #include <math.h>
 #include <stdio.h>
@@ -341,6 +342,10 @@ struct mse_encoder {
     cudaGraphExec_t text_graph[kGraphMaxBatch + 1] = {nullptr};
     uint64_t text_graph_launches[kGraphMaxBatch + 1] = {0};
     cudaStream_t cap_stream = nullptr;
+    // one text query (64 tokens): the blocks as one persistent kernel (text_mega.cuh)
+    tmega::LayerP *mega_layers = nullptr;   // device array [depth_t], LN folded into the qkv / fc1 weights
+    uint32_t *mega_bar = nullptr;
+    int mega_grid = 0;                      // 0: not available for this tower shape / device
 };
 
 namespace {
@@ -475,10 +480,80 @@ int layernorm(const __half *x, __half *y, const float *g, const float *b, uint32
     return MSE_OK;
 }
 
+// text_mega.cuh: fold LN1 / LN2 into the qkv / fc1 weights of every text block and size the persistent grid
+int prepare_text_mega(mse_encoder *e) {
+    const uint32_t D = e->cfg[2], F = e->cfg[5], H = e->cfg[4], S = e->cfg[7];
+    const int depth = e->cfg[11];
+    e->mega_grid = 0;
+    if (getenv("MSE_NO_TEXT_MEGA")) return MSE_OK;
+    if (S != 64 || D % 64 != 0 || D != H * attn::kDH || F % 8 != 0 || depth <= 0) return MSE_OK;
+    auto slices = [](uint32_t n, int bn) { return (n + (uint32_t)bn - 1) / (uint32_t)bn; };
+    const uint32_t items = std::max(std::max(slices(3 * D, tmega::kBnQkv), slices(D, tmega::kBnProj)),
+                                    std::max(std::max(slices(F, tmega::kBnFc1), slices(D, tmega::kBnFc2) * tmega::kFc2Splits), H));
+    if (items > (uint32_t)sm_count(e->device) || slices(D, tmega::kBnFc2) > 256 ||
+        (size_t)tmega::kFc2Splits * 64 * D > mse_encoder::kSplitkFloats)
+        return MSE_OK;
+    MSE_CUDA(cudaFuncSetAttribute(tmega::k_text_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmega::kSmemBytes));
+    int per_sm = 0;
+    MSE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tmega::k_text_blocks, tmega::kThreads, tmega::kSmemBytes));
+    if (per_sm < 1) return MSE_OK;
+    std::vector<tmega::LayerP> lp(depth);
+    for (int l = 0; l < depth; l++) {
+        const LayerW &L = e->txt.layers[l];
+        __half *qw = nullptr, *fw = nullptr;
+        float *qcs = nullptr, *qb = nullptr, *fcs = nullptr, *fb = nullptr;
+        MSE_CHECK(dev_alloc(e, (void **)&qw, (size_t)3 * D * D * 2));
+        MSE_CHECK(dev_alloc(e, (void **)&fw, (size_t)F * D * 2));
+        MSE_CHECK(dev_alloc(e, (void **)&qcs, (size_t)3 * D * 4));
+        MSE_CHECK(dev_alloc(e, (void **)&qb, (size_t)3 * D * 4));
+        MSE_CHECK(dev_alloc(e, (void **)&fcs, (size_t)F * 4));
+        MSE_CHECK(dev_alloc(e, (void **)&fb, (size_t)F * 4));
+        tmega::k_fold_ln<<<(3 * D * 32 + 255) / 256, 256>>>(L.qkv_w, L.qkv_b, L.ln1_g, L.ln1_b, 3 * D, D, qw, qcs, qb);
+        tmega::k_fold_ln<<<(F * 32 + 255) / 256, 256>>>(L.fc1_w, L.fc1_b, L.ln2_g, L.ln2_b, F, D, fw, fcs, fb);
+        MSE_LAUNCH_OK();
+        lp[l] = tmega::LayerP{qw, L.proj_w, fw, L.fc2_w, qb, qcs, L.proj_b, fb, fcs, L.fc2_b};
+    }
+    MSE_CHECK(dev_alloc(e, (void **)&e->mega_layers, sizeof(tmega::LayerP) * depth));
+    MSE_CHECK(dev_alloc(e, (void **)&e->mega_bar, 64));
+    MSE_CUDA(cudaMemcpy(e->mega_layers, lp.data(), sizeof(tmega::LayerP) * depth, cudaMemcpyHostToDevice));
+    MSE_CUDA(cudaDeviceSynchronize());
+    e->mega_grid = (int)items;
+    return MSE_OK;
+}
+
+int run_text_mega(mse_encoder *e, int depth, cudaStream_t st) {
+    tmega::Params p{};
+    p.layers = e->mega_layers;
+    p.depth = depth;
+    p.D = e->cfg[2]; p.F = e->cfg[5]; p.H = e->cfg[4];
+    p.x = e->x; p.qkv = e->qkv; p.att = e->att; p.h = e->hbuf;
+    p.ws = e->splitk_ws; p.cnt = e->splitk_cnt; p.bar = e->mega_bar;
+    p.scale_log2e = (1.0f / sqrtf((float)attn::kDH)) * 1.4426950408889634f;
+    p.eps = 1e-6f;
+    p.act = e->cfg[8];
+    { const char *d = getenv("MSE_TMEGA_DEBUG"); p.debug = d ? atoi(d) : 0; }
+    MSE_CUDA(cudaMemsetAsync(e->mega_bar, 0, 4, st));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)e->mega_grid);
+    cfg.blockDim = dim3(tmega::kThreads);
+    cfg.dynamicSmemBytes = tmega::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the kernel synchronises the grid itself
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MSE_CUDA(cudaLaunchKernelEx(&cfg, tmega::k_text_blocks, p));
+    MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
 // the 27 pre-LN blocks shared by both towers (aitemplate/model.py:26-55)
 int run_blocks(mse_encoder *e, const TowerW &tw, int depth, uint32_t B, uint32_t S, cudaStream_t st) {
     const uint32_t D = e->cfg[2], F = e->cfg[5], H = e->cfg[4], T = B * S;
     const int act = e->cfg[8];
+    if (&tw == &e->txt && B == 1 && S == 64 && e->mega_grid > 0 && !e->profile && depth > 0 && getenv("MSE_NO_TEXT_MEGA") == nullptr)
+        return run_text_mega(e, depth, st);
     static PerDeviceOnce attr_once;
     if (attr_once.first(e->device)) MSE_CUDA(cudaFuncSetAttribute(attn::k_mha_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::Smem)));
     const float scale_log2e = (1.0f / sqrtf((float)attn::kDH)) * 1.4426950408889634f;
@@ -650,6 +725,7 @@ MSE_API int mse_encoder_create(const char *weights_path, int device, int max_bat
             if ((rc = upload(e, wf, "text.ln_final.bias", false, (void **)&e->txt.lnf_b, D))) break;
             if ((rc = upload(e, wf, "text.text_projection.weight", true, (void **)&e->tproj_w, (size_t)D * D))) break;
             if ((rc = upload(e, wf, "text.text_projection.bias", false, (void **)&e->tproj_b, D))) break;
+            if ((rc = prepare_text_mega(e))) break;
         }
         const size_t S_max = std::max<size_t>(has_v ? Sv : 0, has_t ? (size_t)ctx : 0);
         const size_t T = (size_t)max_batch * S_max;
