@@ -262,6 +262,24 @@ int mse_pq_preprocess_query(mse_pq *pq, const float *q, uint32_t nq, float *lut)
 int mse_pq_adc(mse_pq *pq, const float *lut, const uint8_t *codes, uint64_t n, int64_t *scores); /* asymmetric_dot_product :387-405 */
 void mse_pq_destroy(mse_pq *pq);
 
+/* =====================================================================================
+ * Shard centroids (kmeans.py) and shard assignment (src/dump_processor.rs:426-457) over the rows of a handle.
+ * centroids: host f32 [k][d] row-major (centroids.bin decoded, dump_processor.rs:196-207).  k <= 256, spill <= 4.
+ * ===================================================================================== */
+/* kmeans.py:78-95 `fitness`: top-`spill` centroids of every row by inner product (normalize != 0: against the L2-normalised
+ * centroids, :82), counts [spill][k] = the histogram of rank-j assignments (`cluster_sizes`), assign (optional, host) [n][spill].
+ * Equal scores: the lower centroid index ranks first. */
+int mse_kmeans_assign(mse_index *ix, const float *centroids, uint32_t k, uint32_t spill, int normalize, uint32_t *counts, uint32_t *assign);
+/* kmeans.py:73-131 `simulated_annealing` (the script's loop; Gaussian steps from a seeded host generator, fitness on the device).
+ * centroids_out [k][d] L2-normalised (:131); fitness_out = max |cluster size - n / k| of the accepted state; iters_out = iterations run. */
+int mse_kmeans_anneal(mse_index *ix, uint32_t k, uint32_t spill, uint32_t max_iter, uint64_t seed, float *centroids_out, float *fitness_out,
+                      uint32_t *iters_out);
+/* dump_processor.rs:438-457: record i goes to the `spill` shards that come first when the shards are ordered (stable, in place) by
+ * -scale_dot_result_f64(dot(centroid, row) - balance_fudge * shard_count / bal_count).  shard_counts [k] and bal_count carry the state
+ * across calls (the reference starts them at 0 and 1); assign: host [n][spill] shard indices.  Dots are f32 on the device. */
+int mse_shard_assign(mse_index *ix, const float *centroids, uint32_t k, uint32_t spill, double balance_fudge, uint64_t *shard_counts,
+                     uint64_t *bal_count, uint32_t *assign);
+
 typedef struct mse_rabitq mse_rabitq;
 int mse_rabitq_create(const float *mean, const float *transform, uint32_t n_dims, uint32_t output_dims, int device, mse_rabitq **out);
 int mse_rabitq_load(const uint8_t *msgpack, size_t len, int device, mse_rabitq **out);

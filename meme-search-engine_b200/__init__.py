@@ -6,6 +6,7 @@ that ABI (the reference's host code is Rust, which this image lacks; see INTEGRA
 
   flat.FlatIndex          faiss IndexScalarQuantizer(QT_fp16, IP) as src/main.rs:822,858,900 uses it
   diskann                 the diskann crate's public names (diskann/src/lib.rs, diskann/src/vector.rs)
+  kmeans                  kmeans.py's shard centroids (fitness / simulated_annealing) and the indexer's shard assignment
 
 The directory name contains a hyphen, so it is imported through ``mse_b200.py`` at the repository root
 (``import mse_b200``), which loads this package under that name.
@@ -17,6 +18,7 @@ from ._lib import MseError, build, check, lib, lib_path, last_error, launch_coun
 from .flat import FlatIndex, merge_topk  # noqa: F401
 from .encoder import Encoder  # noqa: F401
 from . import diskann  # noqa: F401
+from . import kmeans  # noqa: F401
 from . import weights  # noqa: F401
 from . import sharding  # noqa: F401
 from .sharding import ShardGroup  # noqa: F401

@@ -109,6 +109,9 @@ _SIGS = {
     "mse_index_encode_rabitq": (_i32, [_vp, _vp, _i32]),
     "mse_rabitq_query_dev": (_i32, [_vp, _vp, _u32, _vp, _vp]),
     "mse_rabitq_destroy": (None, [_vp]),
+    "mse_kmeans_assign": (_i32, [_vp, _vp, _u32, _u32, _i32, _vp, _vp]),
+    "mse_kmeans_anneal": (_i32, [_vp, _u32, _u32, _u32, _u64, _vp, _vp, _vp]),
+    "mse_shard_assign": (_i32, [_vp, _vp, _u32, _u32, C.c_double, _vp, _vp, _vp]),
     "mse_encoder_create": (_i32, [C.c_char_p, _i32, _i32, C.POINTER(_vp)]),
     "mse_encoder_config": (_i32, [_vp, _vp]),
     "mse_encode_images_u8": (_i32, [_vp, _vp, _i32, _vp]),

@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "gemm_epilogues.cuh"
 #include "gemm_skinny.cuh"
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
 
@@ -101,8 +102,15 @@ struct Params {
 };
 
 // ---- device-wide barrier: every CTA of the (cooperative, co-resident) grid calls it the same number of times
+#ifndef MSE_TMEGA_BARRIER
+#define MSE_TMEGA_BARRIER 0
+#endif
 __device__ __forceinline__ void grid_sync(uint32_t *bar, uint32_t &target, int debug = 0) {
     if (debug & 4) { __syncthreads(); return; }
+#if MSE_TMEGA_BARRIER == 2
+    cooperative_groups::this_grid().sync();
+    return;
+#endif
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
@@ -111,9 +119,13 @@ __device__ __forceinline__ void grid_sync(uint32_t *bar, uint32_t &target, int d
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
         uint32_t v;
-        do {
+        for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-        } while ((int32_t)(v - target) < 0);
+            if ((int32_t)(v - target) >= 0) break;
+#if MSE_TMEGA_BARRIER == 1
+            __nanosleep(40);
+#endif
+        }
     }
     __syncthreads();
 }

@@ -1,0 +1,134 @@
+"""f4 (shard k-means + shard assignment), pinned to an EXECUTION OF THE REFERENCE: tests/golden/kmeans_reference.json holds the
+`last_fitness, new_fitness, temperature` lines the reference's own `simulated_annealing` (kmeans.py:73-131, ast-extracted and run
+unchanged by tests/golden/make_kmeans_golden.py) printed for seeded inputs.  The test replays the script's torch RNG calls to rebuild
+the candidate centroids of every iteration; the numpy restatement (oracle/kmeans_np.py) and -- on the GPU -- the CUDA kernel
+(mse_kmeans_assign) must give the printed fitness values exactly (they are integer-valued cluster-size deviations)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import clustered_f16, unit_rows
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kmeans_reference.json")))
+
+
+def replay_candidates():
+    """The centroid matrices the script evaluated: :75 randn(k, n_dims), then per iteration :104 centroids + randn_like * temperature,
+    accepted iff new < last (:107); temperatures follow :109,:113,:123.  No reroll within the golden's 6 iterations (:115 needs > 100)."""
+    import torch
+    torch.manual_seed(G["seed"])
+    k = G["k"]
+    cur = torch.randn(k, 1152)
+    cands, temp = [cur.numpy().copy()], 1.0
+    for last, new, printed_temp in G["printed"]:
+        assert abs(temp - printed_temp) < 1e-12
+        n = cur + torch.randn_like(cur) * temp
+        cands.append(n.numpy().copy())
+        if new < last:
+            cur, temp = n, temp * 0.999
+        else:
+            temp = temp * 0.9995
+        temp = min(1.5, temp)
+    return cands
+
+
+def golden_fitness_sequence():
+    """fitness of candidate 0 = the first line's `last`; candidate i >= 1 = line i's `new`."""
+    return [G["printed"][0][0]] + [ln[1] for ln in G["printed"]]
+
+
+def rows_f32():
+    return clustered_f16(71, G["rows"], n_clusters=16).astype(np.float32)
+
+
+def test_numpy_restatement_matches_the_script():
+    from oracle import kmeans_np as K
+    x = rows_f32()
+    for c, want in zip(replay_candidates(), golden_fitness_sequence()):
+        got, worst = K.fitness(x, c, 2)
+        assert got == want
+        assert worst.shape == (2,)
+    # the script returns normalize(centroids) of the last accepted state (:131)
+    assert np.allclose(G["result_norms"], 1.0, atol=1e-6)
+
+
+def test_shard_assign_restatement_properties():
+    """dump_processor.rs:438-457: every record lands in exactly SHARD_SPILL distinct shards; with fudge 0 the choice is the plain top-2."""
+    from oracle import kmeans_np as K
+    x = clustered_f16(72, 400, n_clusters=6).astype(np.float32)
+    c = unit_rows(73, 6)
+    a, counts, bal = K.shard_assign(x, c, 2, 0.2)
+    assert (a[:, 0] != a[:, 1]).all() and counts.sum() == 800 and bal == 401
+    a0, _, _ = K.shard_assign(x, c, 2, 0.0)
+    _, top = K.cluster_sizes(x, c, 2, norm=False)
+    assert np.array_equal(a0, top)
+    # the fudge pulls records away from crowded shards: sizes are no less balanced than without it
+    c0 = np.bincount(a0.ravel(), minlength=6)
+    assert counts.max() - counts.min() <= c0.max() - c0.min()
+
+
+@pytest.mark.gpu
+def test_cuda_fitness_matches_the_script(mse):
+    from mse_b200 import diskann as dk, kmeans as km
+    x16 = clustered_f16(71, G["rows"], n_clusters=16)
+    vl = dk.VectorList.from_f16(x16)
+    for c, want in zip(replay_candidates(), golden_fitness_sequence()):
+        got, worst = km.fitness(vl, c, 2)
+        assert got == want
+
+
+@pytest.mark.gpu
+def test_cuda_assignment_matches_oracle(mse):
+    """counts and per-row top-`spill` ids against the numpy restatement: ragged row counts, d = 1152 and a d with a tail, spill 1..4."""
+    from mse_b200 import diskann as dk, kmeans as km
+    from oracle import kmeans_np as K
+    for n, d, k, spill in ((1, 1152, 3, 2), (1031, 1152, 42, 2), (517, 200, 17, 4), (64, 64, 5, 1)):
+        x16 = clustered_f16(80 + n, n, n_clusters=8, d=d)
+        c = unit_rows(81 + n, k, d) * np.float32(1.7)      # not unit length: normalize must matter
+        vl = dk.VectorList.from_f16(x16)
+        counts, assign = km.cluster_sizes(vl, c, spill, True, want_assignment=True)
+        oc, otop = K.cluster_sizes(x16.astype(np.float32), c, spill)
+        sims = x16.astype(np.float64) @ K.normalize(c).astype(np.float64).T
+        # a row may legitimately differ only where two centroids are closer than f32 rounding
+        diff = np.nonzero((assign.astype(np.int64) != otop).any(axis=1))[0]
+        for i in diff:
+            s = np.sort(sims[i])[::-1]
+            assert np.min(np.abs(np.diff(s[: spill + 1]))) < 1e-5, (n, d, i)
+        if len(diff) == 0:
+            assert np.array_equal(counts.astype(np.int64), oc)
+        assert counts.sum() == n * spill
+
+
+@pytest.mark.gpu
+def test_cuda_anneal_improves_balance(mse):
+    from mse_b200 import diskann as dk, kmeans as km
+    x16 = clustered_f16(90, 4000, n_clusters=32)
+    vl = dk.VectorList.from_f16(x16)
+    cent, fit, its = km.simulated_annealing(vl, 8, max_iter=60, seed=5)
+    assert its <= 60 and np.allclose(np.linalg.norm(cent, axis=1), 1.0, atol=1e-5)
+    f_check, _ = km.fitness(vl, cent, 2)
+    assert f_check == fit                                   # the reported fitness is the returned centroids' fitness
+    cent1, fit1, _ = km.simulated_annealing(vl, 8, max_iter=0, seed=5)
+    assert fit <= fit1                                      # accepted steps only ever lower it (kmeans.py:107)
+    cent2, fit2, _ = km.simulated_annealing(vl, 8, max_iter=60, seed=5)
+    assert np.array_equal(cent, cent2) and fit == fit2      # seeded: reproducible
+
+
+@pytest.mark.gpu
+def test_cuda_shard_assign_matches_oracle(mse):
+    from mse_b200 import diskann as dk, kmeans as km
+    from oracle import kmeans_np as K
+    x16 = clustered_f16(95, 700, n_clusters=10)
+    c = unit_rows(96, 7).astype(np.float16).astype(np.float32)      # centroids.bin is fp16 (dump_processor.rs:197)
+    vl = dk.VectorList.from_f16(x16)
+    sa = km.ShardAssigner(c, balance_fudge=0.2)
+    got = sa.assign(vl)
+    want, counts, bal = K.shard_assign(x16.astype(np.float32), c, 2, 0.2)
+    assert np.array_equal(got.astype(np.int64), want)
+    assert np.array_equal(sa.shard_counts.astype(np.int64), counts) and int(sa.bal_count[0]) == bal
+    # the state carries over: a second batch continues where the first stopped
+    got2 = sa.assign(vl)
+    want2, counts2, bal2 = K.shard_assign(x16.astype(np.float32), c, 2, 0.2, shard_counts=counts, bal_count=bal)
+    assert np.array_equal(got2.astype(np.int64), want2) and int(sa.bal_count[0]) == bal2
