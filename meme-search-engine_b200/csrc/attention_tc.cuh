@@ -40,7 +40,9 @@ static constexpr uint32_t kOffP = kOffKV + kKVStages * kKVBytes;        // + 122
 static constexpr uint32_t kOffBar = kOffP + 2 * kPBytes;                // + 65536 = 229376
 static constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;
 static constexpr uint32_t kTmemCols = 512;
-static constexpr uint32_t kTmS = 0, kTmO = 256;  // S_A @0, S_B @128, O_A @256, O_B @384
+// S_A @0, S_B @128 (fp32 scores), O_A @256, O_B @336 (80 fp32 columns each), P @416: ONE fp16 probability tile [128 rows][128 keys] = 64
+// columns shared by the two query tiles -- they take turns (ping-pong), and a tile writes P only after the other tile's P V has read it
+static constexpr uint32_t kTmS = 0, kTmO = 256, kTmOStride = 80, kTmP = 416;
 
 // K-major SWIZZLE_32B tile (rows of 32 bytes, 8-row atoms of 256 bytes)
 __device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t smem_addr) {
@@ -77,6 +79,17 @@ __device__ __forceinline__ void tmem_st_32x32_x8(uint32_t taddr, const uint32_t 
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M rows = lanes, K fp16 elements packed two per 32-bit column) is read from tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -185,9 +198,8 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
             auto lo_of = [&](uint32_t off) { return ((ptx::smem_u32(smem + off) & 0x3FFFFu) >> 4) | (1u << 16); };
             auto d64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
             const uint32_t q_lo = lo_of(kOffQ + t * (kT64 + kT16)), q2_lo = q_lo + (kT64 >> 4);
-            const uint32_t p_lo = lo_of(kOffP + t * kPBytes);
             const uint32_t kv_lo0 = lo_of(kOffKV);
-            const uint32_t d_s = tmem_base + kTmS + t * kBN, d_o = tmem_base + kTmO + t * 128;
+            const uint32_t d_s = tmem_base + kTmS + t * kBN, d_o = tmem_base + kTmO + t * kTmOStride;
             uint32_t item_n = 0, kv_n = 0, blk_n = 0;  // blk_n: running count of key blocks (phase of the per-tile barriers)
             // S_t(block) = Q_t K^T into the tile's score buffer
             auto issue_s = [&](uint32_t kvn, uint32_t bn) {
@@ -220,9 +232,9 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                 if (!(p.debug & 4))
 #pragma unroll
                 for (uint32_t ks = 0; ks < kBN / 16; ks++) {
-                    const uint64_t pa = d64(p_lo + (ks >> 2) * (kT64 >> 4) + 2 * (ks & 3), kHi128);
                     const uint32_t accum = (!first_block || ks != 0) ? 1u : 0u;
-                    ptx::umma_f16(d_o, pa, d64((v_lo + ks * (512 >> 4)) | ((kT16 >> 4) << 16), kHi32), idesc_o80, accum);   // +16 keys = 512 B
+                    // P from tensor memory: 16 keys = 8 columns of packed fp16 pairs
+                    umma_f16_ts(d_o, tmem_base + kTmP + ks * 8, d64((v_lo + ks * (512 >> 4)) | ((kT16 >> 4) << 16), kHi32), idesc_o80, accum);   // +16 keys = 512 B
                 }
                 ptx::umma_commit(&o_full[t]);
                 TR(2 + (int)t);                  // 4: PV issued
@@ -257,15 +269,15 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
         const uint32_t lane_base = (quad * 32) << 16;
         const float sc = p.scale_log2e;
         const uint32_t ts = tmem_base + lane_base + kTmS + t * kBN;
-        const uint32_t to = tmem_base + lane_base + kTmO + t * 128;
-        uint8_t *pt = smem + kOffP + t * kPBytes + row * 128;
+        const uint32_t to = tmem_base + lane_base + kTmO + t * kTmOStride;
+        const uint32_t tp = tmem_base + lane_base + kTmP;
         uint32_t blk_n = 0, item_n = 0;
         // The exponentials are MUFU-bound (16 ex2/clk/SM: a tile's 128 x 128 block is 1024 cycles when it has the unit to itself) and
         // the rest of a block -- score load, P stores, barrier round trips -- is not.  Left alone the two tiles run in lockstep and
         // share the MUFU in the same phase (2 x ~2500 cycles per block, phase timeline in profiles/r02_attention_timeline.md); a token
         // passed between the two softmax groups on a pair of named barriers makes them alternate, so one tile's exponentials overlap
         // the other tile's loads and stores.
-        const bool pingpong = !(p.debug & 64);
+        const bool pingpong = true;   // the shared P buffer relies on the alternation
         if (pingpong && t == 1) ptx::named_bar_arrive(2, 256);   // tile A goes first
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, item_n++) {
             const int qi = item % p.q_items, bh = item / p.q_items, h = bh % p.H, b = bh / p.H;
@@ -341,16 +353,19 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                 }
                 if (row == 0) TR((int)t);        // 3: PV(j-1) done (+ rescale)
                 l_run = fmaf(l_run, f, rs0 + rs1);
-                // 128 keys = 16 chunks of 8 halfs; chunk c8 lives in 64-key SW128 tile (c8 >> 3) at slot (c8 & 7) ^ (row & 7)
-                if (!(p.debug & 2))
-#pragma unroll
-                for (int c8 = 0; c8 < kBN / 8; c8++) {
-                    const uint32_t chunk = (uint32_t)(c8 & 7) ^ (row & 7);
-                    *(uint4 *)(pt + (c8 >> 3) * kT64 + chunk * 16) = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+                // the P buffer is shared: the other tile's P V of its latest block must have read it.  The token order is A(bn), B(bn),
+                // A(bn + 1), ...: tile B waits for P V_A(bn), tile A for P V_B(bn - 1) -- both long done in steady state.
+                if (t == 1) ptx::mbar_wait(&o_full[0], bn & 1);
+                else if (bn > 0) ptx::mbar_wait(&o_full[1], (bn - 1) & 1);
+                ptx::tc_fence_after();
+                // P as packed fp16 pairs straight into tensor memory (256 B/clk, against 128 B/clk + a proxy fence through shared memory):
+                // thread = row = lane, 64 columns = 128 keys; the P V MMA takes its A operand from there
+                if (!(p.debug & 2)) {
+                    tmem_st_32x32(tp, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+                    tmem_st_32x32(tp + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
+                    tmem_st_wait();
                 }
-                // P written: make the generic-proxy stores (and the TMEM rescale) visible to the tensor core
                 ptx::tc_fence_before();
-                ptx::fence_proxy_async();
                 ptx::mbar_arrive(&p_full[t]);
                 if (row == 0) TR((int)t);        // 4: P stored
             }

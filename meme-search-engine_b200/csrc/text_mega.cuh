@@ -331,8 +331,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_text_blocks(Params p) {
     const float *stats = (const float *)(smem + kOffStats);
     uint32_t bar_target = 0;
     constexpr int BN_QKV = kBnQkv, BN_PROJ = kBnProj, BN_FC1 = kBnFc1, BN_FC2 = kBnFc2;
-    // every phase must fit the grid in one pass (the host checks): one item per CTA
-    Item nxt = make_item(p.layers[0].qkv_w, 3 * D, D, BN_QKV, 1, cta);
+    // every phase must fit the grid in one pass (the host checks): one item per CTA.  The items are the same in every block but for
+    // the weight pointer, so their index arithmetic (integer divisions) is done once.
+    const Item item_qkv = make_item(nullptr, 3 * D, D, BN_QKV, 1, cta), item_proj = make_item(nullptr, D, D, BN_PROJ, 1, cta),
+               item_fc1 = make_item(nullptr, F, D, BN_FC1, 1, cta), item_fc2 = make_item(nullptr, D, F, BN_FC2, kFc2Splits, cta);
+    auto with_w = [](Item it, const __half *w) { it.W = w; return it; };
+    const uint32_t fc2_split = cta / ((D + BN_FC2 - 1) / BN_FC2);
+    Item nxt = with_w(item_qkv, p.layers[0].qkv_w);
     prefetch_b<BN_QKV>(smem, nxt);
     prefetch_vec(nxt, p.layers[0].qkv_cs, BN_QKV);
     prefetch_vec(nxt, p.layers[0].qkv_b, BN_QKV);
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_text_blocks(Params p) {
             const Item it = nxt;
             float acc[BN_QKV / 8][4];
             if (it.valid) gemm_main<BN_QKV, true>(smem, p.x, D, it, true, acc, p.eps, p.debug);
-            nxt = make_item(L.proj_w, D, D, BN_PROJ, 1, cta);
+            nxt = with_w(item_proj, L.proj_w);
             prefetch_b<BN_PROJ>(smem, nxt);
             prefetch_vec(nxt, L.proj_b, BN_PROJ);
             if (it.valid && kq == 0)
@@ -367,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_text_blocks(Params p) {
             const Item it = nxt;
             float acc[BN_PROJ / 8][4];
             if (it.valid) gemm_main<BN_PROJ, false>(smem, p.att, D, it, true, acc, p.eps, p.debug);
-            nxt = make_item(L.fc1_w, F, D, BN_FC1, 1, cta);
+            nxt = with_w(item_fc1, L.fc1_w);
             prefetch_b<BN_FC1>(smem, nxt);
             prefetch_vec(nxt, L.fc1_cs, BN_FC1);
             prefetch_vec(nxt, L.fc1_b, BN_FC1);
@@ -385,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_text_blocks(Params p) {
             const Item it = nxt;
             float acc[BN_FC1 / 8][4];
             if (it.valid) gemm_main<BN_FC1, true>(smem, p.x, D, it, true, acc, p.eps, p.debug);
-            nxt = make_item(L.fc2_w, D, F, BN_FC2, kFc2Splits, cta);
+            nxt = with_w(item_fc2, L.fc2_w);
             prefetch_b<BN_FC2>(smem, nxt);
             prefetch_vec(nxt, L.fc2_b, BN_FC2);
             if (it.valid && kq == 0)
@@ -404,13 +409,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_text_blocks(Params p) {
             float acc[BN_FC2 / 8][4];
             if (it.valid) gemm_main<BN_FC2, false>(smem, p.h, F, it, true, acc, p.eps, p.debug);
             if (l + 1 < p.depth) {
-                nxt = make_item(p.layers[l + 1].qkv_w, 3 * D, D, BN_QKV, 1, cta);
+                nxt = with_w(item_qkv, p.layers[l + 1].qkv_w);
                 prefetch_b<BN_QKV>(smem, nxt);
                 prefetch_vec(nxt, p.layers[l + 1].qkv_cs, BN_QKV);
                 prefetch_vec(nxt, p.layers[l + 1].qkv_b, BN_QKV);
             }
             if (it.valid) {
-                const uint32_t slices = (D + BN_FC2 - 1) / BN_FC2, sl = it.n0 / BN_FC2, sp = cta / slices;
+                const uint32_t sl = it.n0 / BN_FC2, sp = fc2_split;
                 if (kq == 0)
                     for_each_out<BN_FC2>(it, acc, [&](uint32_t row, uint32_t col, float v0, float v1) {
                         __stcg((float2 *)(p.ws + ((size_t)sp * kBM + row) * D + col), make_float2(v0, v1));
