@@ -3,19 +3,23 @@
 // Reference op: softmax(Q K^T / sqrt(dh)) V per (image, head) inside each of the 27 blocks
 // (aitemplate/model.py:30-36: nn.MultiheadAttention(use_mem_eff=True); clip_server.py:114).
 //
-// Persistent kernel, one CTA per SM, work item = 128 query rows of one (image, head):
-//   warp 0      TMA producer.  qkv is viewed as a 3-D tensor [token][3*H head slots][72]; a box of 64 dims lands as a
+// Persistent kernel, one CTA per SM, work item = 256 query rows (two 128-row tiles A / B) of one (image, head):
+//   warp 8      TMA producer.  qkv is viewed as a 3-D tensor [token][3*H head slots][72]; a box of 64 dims lands as a
 //               SWIZZLE_128B K-major tile and the remaining 8 dims as a 16-wide SWIZZLE_32B tile whose upper 8 columns
-//               are out of bounds in dim 0 and therefore zero-filled by TMA -- dh = 72 is padded to 80 for free.
-//   warp 1      MMA issuer.  S_j = Q K_j^T: 4 x (K=16, SW128) + 1 x (K=16, SW32) tcgen05.mma, M=128, N=128 keys, fp32
-//               in TMEM (double buffered).  O_j = P_j V_j: per 16 keys one N=64 (SW128, MN-major B) and one N=16 (SW32,
-//               MN-major B) tcgen05.mma into a per-block O buffer (double buffered) -- V is consumed exactly as it lies
-//               in memory ([key][dh]), no transpose.
-//   warps 2..5  softmax: thread = query row.  Reads S_j from TMEM (two passes: max, then exp2), writes P_j as fp16 into a
-//               SW128 K-major shared tile for the PV MMA, keeps the running max / sum, and folds each finished O_j into
-//               its 72 fp32 output registers with the usual rescale.  Normalises and stores fp16 at the end.
-// S_{j+1} is issued before P_j V_j, so the tensor core works on the next score block while the softmax warps are busy.
-// Bound: the 128x128 exp2 per block (MUFU, 16/clk/SM) -- about 1.0 k cycles per block against 0.64 k cycles of MMA.
+//               are out of bounds in dim 0 and therefore zero-filled by TMA -- dh = 72 is padded to 80 for free.  Four K/V stages.
+//   warps 9/10  MMA issuers, one per query tile.  S_j = Q K_j^T: 4 x (K=16, SW128) + 1 x (K=16, SW32) tcgen05.mma, M=128,
+//               N=128 keys, fp32 in TMEM.  O += P_j V_j: per 16 keys ONE N=80 MMA whose A operand P is read from TENSOR MEMORY
+//               (TS form) and whose B operand V is five SW32 MN-major tiles exactly as V lies in memory ([key][dh]).
+//   warps 0-3 / 4-7  softmax groups of tile A / B: thread = query row.  Reads S_j from TMEM once (128 scores in registers), exp2,
+//               writes P_j as packed fp16 pairs with tcgen05.st into ONE 64-column P tile the two query tiles share, keeps the
+//               running max / sum; O accumulates in TMEM with a lazy rescale.  Normalises and stores fp16 at the end.
+// The two softmax groups alternate on a token (named barriers): one tile's exponentials (MUFU, 16/clk/SM: ~1.1 k cycles per
+// 128 x 128 block) overlap the other tile's score load, P store and barrier round trips.  r03: P moved from shared memory (two SW128
+// tiles per query tile, 128 B/clk + a generic-to-async proxy fence per block) to tensor memory (tcgen05.st, 256 B/clk, no proxy
+// fence); a tile writes the shared P buffer only after the other tile's P V has read it, which the token order makes a wait that is
+// already satisfied.  0.306-0.33 -> 0.277 ms per layer at batch 64 (565 TFLOP/s); 45.4 -> 40.4 ms inside the power-capped tower step.
+// Measured without gain on top of it: 2^x for a quarter / half of the elements on the FMA pipe (packed-fp32 Cody-Waite polynomial;
+// profiles/r03f_attention_p_in_tmem.md).
 #pragma once
 #include "ptx.cuh"
 #include <cuda_fp16.h>
@@ -27,17 +31,15 @@ static constexpr int kBM = 128;          // query rows per tile; a work item is 
 static constexpr int kBN = 128;          // keys per block
 static constexpr int kDH = 72;
 static constexpr int kThreads = 384;     // warps 0-3: softmax group A, 4-7: softmax group B, 8: TMA, 9/10: MMA issuers (tile A/B), 11: idle
-static constexpr int kKVStages = 3;
+static constexpr int kKVStages = 4;       // the P tiles moved to tensor memory: their 64 KB hold a fourth K/V stage
 static constexpr uint32_t kT64 = kBM * 128;   // [128 rows][64 halfs] SW128 tile bytes
 static constexpr uint32_t kT16 = kBM * 32;    // [128 rows][16 halfs] SW32 tile bytes
 static constexpr uint32_t kQBytes = 2 * (kT64 + kT16);      // both query tiles
 static constexpr uint32_t kKVBytes = 2 * (kT64 + kT16);     // K tile pair + V tile pair
-static constexpr uint32_t kPBytes = 2 * kT64;               // 128 keys = two 64-key SW128 tiles (one buffer per query tile)
 // smem map (all tile bases 1024-aligned)
 static constexpr uint32_t kOffQ = 0;
 static constexpr uint32_t kOffKV = kOffQ + kQBytes;                     // 40960
-static constexpr uint32_t kOffP = kOffKV + kKVStages * kKVBytes;        // + 122880
-static constexpr uint32_t kOffBar = kOffP + 2 * kPBytes;                // + 65536 = 229376
+static constexpr uint32_t kOffBar = kOffKV + kKVStages * kKVBytes;      // + 163840 = 204800
 static constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;
 static constexpr uint32_t kTmemCols = 512;
 // S_A @0, S_B @128 (fp32 scores), O_A @256, O_B @336 (80 fp32 columns each), P @416: ONE fp16 probability tile [128 rows][128 keys] = 64
@@ -117,10 +119,10 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(smem + kOffBar);
     uint64_t *q_full = bars + 0, *q_empty = bars + 1;
-    uint64_t *kv_full = bars + 2, *kv_empty = bars + 2 + kKVStages;           // [3] each
-    uint64_t *s_full = bars + 8, *s_empty = bars + 10;                        // [2] = per query tile
-    uint64_t *p_full = bars + 12, *o_full = bars + 14, *o_empty = bars + 16;  // [2] = per query tile
-    uint32_t *tmem_slot = (uint32_t *)(bars + 18);
+    uint64_t *kv_full = bars + 2, *kv_empty = bars + 2 + kKVStages;           // [kKVStages] each
+    uint64_t *s_full = bars + 2 + 2 * kKVStages, *s_empty = s_full + 2;       // [2] = per query tile
+    uint64_t *p_full = s_empty + 2, *o_full = p_full + 2, *o_empty = o_full + 2;  // [2] = per query tile
+    uint32_t *tmem_slot = (uint32_t *)(o_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
