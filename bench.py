@@ -50,7 +50,8 @@ NCU_TRAFFIC = {
     "flat_gemm_bytes_per_row_byte": ((17.154500 + 0.010778) / 17.149723, "profiles/r02t_ncu_full.md"),
     # profiles/r02t_ncu_full.md (12.5 M rows, 4096 queries): greedy L = 64: 14.872 GB read + 0.594 GB written for 15.17 GB of gathered rows;
     # RabitQ beam L = 512: 17.377 + 4.516 GB per launch (visited-set tables), 1.53 GB algorithmic
-    "greedy_bytes_per_row_byte": ((14.872 + 0.594) / 15.17, "profiles/r02t_ncu_full.md"),
+    "greedy_bytes_per_row_byte": ((15.818 + 0.595) / 15.17, "profiles/r03e_ncu_full.md"),   # with the L2 row prefetch (r02t: 14.872 + 0.594)
+    "text_blocks_bytes_per_launch": ((824.36 + 4.99) * 1e6, "profiles/r03e_ncu_full.md"),     # k_text_blocks: the 0.826 GB of weights, once
     "beam_l512_bytes_per_launch": ((17.377 + 4.516) * 1e9, "profiles/r02t_ncu_full.md"),
 }
 
@@ -664,8 +665,10 @@ def main():
             res_host.copy_(out_ids, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
+        # the ground-truth flat search just before leaves the board at its power-cap clocks (r03g: 1237 MHz during a 125 ms timed
+        # region): warm up for ~0.5 s so that the timed steps see the clocks a search-only workload runs at
         with ClockSampler(local_rank) as cs:
-            ms_g, launches_g = timed(greedy_resident, warmup, steps)
+            ms_g, launches_g = timed(greedy_resident, max(warmup, 100), max(steps, 40))
         gclocks = cs.summary()
         dk.greedy_search_check(vl, nq)
         rec_g = recall(out_ids)
@@ -680,7 +683,7 @@ def main():
         trg, trg_src = NCU_TRAFFIC["greedy_bytes_per_row_byte"]
         greedy = {"value": nq / (ms_g * 1e-3), "unit": "queries/s", "recall_at_10": rec_g, "L": L, "ms_per_step": ms_g,
                   "e2e": {"value": nq / (ms_g_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * D * 2, "d2h_bytes_per_step": nq * k * 4, "ms_per_step": ms_g_e2e},
-                  "gpu_launches": launches_g, "distances_per_query_per_shard": n_dist / nq,
+                  "gpu_launches_per_step": launches_g / max(steps, 40), "distances_per_query_per_shard": n_dist / nq,
                   "roofline": {"kernel": "k_greedy_search_wq<18> (one warp per query, half a warp per gathered row, exact fp16 rows)", "bound": "hbm",
                                "achieved": g_bytes / (ms_gk * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": g_bytes / (ms_gk * 1e-3) / 1e9 / pk["hbm"],
                                "algorithmic_bytes": "distances x 2304 B (gathered rows; adjacency lists and the query are < 2 %)",
@@ -905,11 +908,12 @@ def main():
                       "clocks": cs.summary(), "steps": n_c1,
                       "e2e": {"value": 1e3 / ms_c1_e2e, "unit": "queries/s", "h2d_bytes_per_step": 64 * 4 + D * 4, "d2h_bytes_per_step": D * 2 + 10 * 8, "ms_per_step": ms_c1_e2e},
                       "gpu_launches": launches_c1 / n_c1, "resident_and_e2e_ids_identical": same,
-                      "roofline": {"kernel": "text tower forward at batch 1 (k_gemm_skinny weight streaming + attention + LN)", "bound": "hbm",
+                      "roofline": {"kernel": "text tower forward at batch 1 (tmega::k_text_blocks: the 27 blocks as one persistent cooperative kernel, + embed / final LN / projection kernels)", "bound": "hbm",
                                    "achieved": TEXT_WEIGHT_BYTES / (ms_tower * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                                    "frac": TEXT_WEIGHT_BYTES / (ms_tower * 1e-3) / 1e9 / pk["hbm"],
                                    "algorithmic_bytes": "0.826 GB of fp16 weights touched once per forward (SURVEY 8d C1)", "kernel_ms_per_step": ms_tower,
-                                   "kernel_share_of_step": ms_tower / ms_c1, "traffic": None}}
+                                   "kernel_share_of_step": ms_tower / ms_c1, "traffic": NCU_TRAFFIC["text_blocks_bytes_per_launch"][0],
+                                   "traffic_note": "k_text_blocks, ncu capture " + NCU_TRAFFIC["text_blocks_bytes_per_launch"][1] + ", not measured by this run"}}
         cix.close()
         tenc.close()
 
