@@ -93,6 +93,111 @@ __device__ __forceinline__ uint32_t nb_next_unvisited(NbView &b, int lane) {
     return b.ids[old];
 }
 
+__device__ __forceinline__ long long shfl_ll_any(long long v, int src) {
+    const unsigned full = 0xffffffffu;
+    const int lo = __shfl_sync(full, (int)(unsigned long long)v, src), hi = __shfl_sync(full, (int)((unsigned long long)v >> 32), src);
+    return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo);
+}
+
+// ---- NeighbourBuffer: up to 32 inserts of one pass as ONE merge (long lists: k_beam_search_wq with 256..608 entries listed; measured at
+// 12.5 M rows: L = 512 14.9 -> 11.9 ms, L = 256 7.33 -> 7.03 ms, but L = 128 3.80 -> 4.38 ms, hence the threshold)
+//
+// A sequence of NeighbourBuffer::insert calls (lib.rs:109-147) shifts the tail of the list once per call -- at L = 512 that was two
+// thirds of the beam kernel's instructions.  When no two scores involved are equal, the sequence has a closed form: the result is the
+// top-`cap` of (list + candidates) in descending score order, and next_unvisited is the first unvisited entry (every insert leaves it
+// there: min(loc, nu), :139-146).  Lane i holds candidate i of the pass (mask `m`: the candidates lib.rs:118 lets through against the
+// tail at pass start -- the tail only grows, so later calls would reject at least those).  Each candidate finds its rank in the list
+// (binary search) and among the candidates; a bit mask over the new list marks where candidates go, and the new list is written from
+// the top chunk down, every destination slot pulling either its candidate or the old entry (slot - number of candidates before it).
+// Sources of a destination chunk lie in that chunk or below and are not needed again, so the move is in place.
+// Equal scores (a candidate against the list or another candidate -- also how an id that is already listed shows up, :127) have
+// position rules that depend on the call order (:120-127): the function then changes nothing and returns false, and the caller
+// replays the pass with nb_insert.  scratch: 20 words of mask (lists of up to 608 entries) + 32 x (u32, i64) candidates, per warp.
+static constexpr uint32_t kNbBatchScratch = 80 + 32 * 4 + 32 * 8;   // bytes, 8-aligned layout: mask[20] | ids[32] | scores[32]
+
+__device__ __forceinline__ bool nb_insert_batch(NbView &b, uint32_t cid, long long cs, unsigned m, int lane, uint8_t *scratch) {
+    const unsigned full = 0xffffffffu;
+    uint32_t *mask = (uint32_t *)scratch;
+    uint32_t *c_ids = mask + 20;
+    long long *c_sc = (long long *)(c_ids + 32);
+    const bool mine = (m >> lane) & 1u;
+    // rank in the list: r = #entries with score > cs; a tie with the list aborts
+    int lo = 0, hi = b.len;
+    while (__any_sync(full, mine && lo < hi)) {
+        if (mine && lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (b.scores[mid] > cs) lo = mid + 1; else hi = mid;
+        }
+    }
+    const int r = lo;
+    bool tie = mine && r < b.len && b.scores[r] == cs;
+    // rank among the candidates; equal candidate scores abort
+    int k = 0;
+    for (unsigned mm = m; mm;) {
+        const int j = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const long long sj = shfl_ll_any(cs, j);
+        if (mine && j != lane) { k += sj > cs; tie |= sj == cs; }
+    }
+    if (__any_sync(full, tie)) return false;
+    const int pos = r + k;                                    // final index of this candidate
+    const int n_cand = __popc(m);
+    const int new_len = min(b.cap, b.len + n_cand);
+    const bool kept = mine && pos < new_len;
+    // mask over the new list + candidates by rank
+    if (lane < 20) mask[lane] = 0;
+    __syncwarp();
+    if (kept) {
+        atomicOr(&mask[pos >> 5], 1u << (pos & 31));
+        c_ids[k] = cid;
+        c_sc[k] = cs;
+    }
+    __syncwarp();
+    const unsigned kept_m = __ballot_sync(full, kept);
+    if (kept_m == 0) return true;                             // everything fell off the end
+    int min_pos = kept ? pos : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) min_pos = min(min_pos, __shfl_xor_sync(full, min_pos, o));
+    // words of the mask: lane w holds word w and the number of candidates before it
+    const int n_words = (new_len + 31) >> 5;
+    const uint32_t my_word = lane < n_words ? mask[lane] : 0u;
+    int before = __popc(my_word);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(full, before, o);
+        if (lane >= o) before += t;
+    }
+    before -= __popc(my_word);                                // exclusive prefix
+    // next_unvisited: the first unvisited entry of the new list
+    int new_nu = min_pos;
+    if (b.nu >= 0) {
+        const long long snu = b.scores[b.nu];
+        const int moved = b.nu + __popc(__ballot_sync(full, mine && cs > snu));
+        if (moved < new_len) new_nu = min(new_nu, moved);
+    }
+    // new list, top chunk first, down to the chunk of the first candidate (everything below stays where it is)
+    for (int c = n_words - 1; c >= (min_pos >> 5); c--) {
+        const uint32_t w = __shfl_sync(full, my_word, c);
+        const int bef = __shfl_sync(full, before, c);
+        const int q = (c << 5) + lane;
+        const int below = bef + __popc(w & ((1u << lane) - 1));
+        const bool is_c = (w >> lane) & 1u;
+        uint32_t ti = 0;
+        long long ts = 0;
+        uint8_t tv = 0;
+        if (q < new_len) {
+            if (is_c) { ti = c_ids[below]; ts = c_sc[below]; }
+            else { const int src = q - below; ti = b.ids[src]; ts = b.scores[src]; tv = b.vis[src]; }
+        }
+        __syncwarp();
+        if (q < new_len && q >= min_pos) { b.ids[q] = ti; b.scores[q] = ts; b.vis[q] = tv; }
+        __syncwarp();
+    }
+    b.len = new_len;
+    b.nu = new_nu;
+    return true;
+}
+
 // ---- HashSet<u32>::insert: true when newly inserted.  Open addressing, linear probing, capacity a power of two.
 __device__ __forceinline__ bool hs_insert(uint32_t *tab, uint32_t mask, uint32_t key, uint32_t *fill) {
     uint32_t h = (key * 2654435761u) & mask;
@@ -704,7 +809,8 @@ __global__ void __launch_bounds__(kGsThreads) k_beam_search(GraphArgs g, BeamArg
 __host__ __device__ static size_t bq_warp_bytes(uint32_t L, uint32_t stride, uint32_t d, uint32_t W) {
     size_t o = (size_t)(L + 1) * 8 + (size_t)W * 8 + (size_t)d * 4 + (size_t)kRqPlaneWords * 4 + (size_t)(L + 1) * 4 + (size_t)W * stride * 4 +
                (size_t)W * 4 + (L + 1);
-    return (o + 15) & ~(size_t)15;
+    o = (o + 15) & ~(size_t)15;
+    return o + ((kNbBatchScratch + 15) & ~(size_t)15);   // nb_insert_batch scratch at the end
 }
 
 __device__ __forceinline__ long long shfl_ll(long long v, int src) {
@@ -730,6 +836,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
     uint32_t *pre = nb_ids + (L + 1);
     uint32_t *pts = pre + (size_t)W * S;
     uint8_t *nb_vis = (uint8_t *)(pts + W);
+    uint8_t *scratch = base + bq_warp_bytes(L, S, g.d, W) - ((kNbBatchScratch + 15) & ~(size_t)15);
     const uint32_t gw = blockIdx.x * kWqWarps + warp, nw = gridDim.x * kWqWarps;
     uint32_t *hadj = htabs + (size_t)gw * (hcap + vcap), *hvis = hadj + hcap;
     const uint32_t hmask = hcap - 1, vmask = vcap - 1;
@@ -768,6 +875,25 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
             }
             __syncwarp();
             if (np == 0 || fill_adj * 4 > hcap * 3 || fill_vis * 4 > vcap * 3) break;
+            // Everything below used to be a chain of ~17 dependent round trips to L2 / HBM per iteration (exact rows 2, adjacency 1, one
+            // visited-set atomicCAS per popped node 4, one visited_adjacent atomicCAS per 32 neighbours 8, codes 1-2).  Independent accesses
+            // are now issued together: the adjacency lists and degrees start towards L2 before the exact scores are computed, the popped
+            // nodes' visited-set inserts go out in one wave, and the neighbours are first LOOKED UP (plain L2 loads, all in flight at
+            // once): ~5 of 6 were seen in an earlier iteration and sit in their home slot, so only the rest -- compacted in list order --
+            // go through the ordered atomicCAS passes.  Same fresh candidates in the same order as before (a key found at its home slot
+            // is a key the atomicCAS would have found; everything else takes the old path).
+            {
+                const uint32_t adj_lines = (S * 4 + 127) / 128;
+                for (uint32_t i = lane; i < np * adj_lines; i += 32)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)(g.adj + (size_t)pts[i / adj_lines] * S) + (i % adj_lines) * 128));
+                if ((uint32_t)lane < np) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.deg + pts[lane]));
+            }
+            bool fresh_mine = false;                                                 // lane b: popped node b is expanded for the first time
+            {
+                const uint32_t pid = (uint32_t)lane < np ? pts[lane] : kEmpty;
+                const unsigned same = __match_any_sync(full, pid);
+                if ((uint32_t)lane < np && (same & ((1u << lane) - 1)) == 0) fresh_mine = hs_insert_nc(hvis, vmask, pid);
+            }
             for (uint32_t i = 0; i < np; i += 2) {                                   // exact scores of the expanded nodes :169
                 const uint32_t j = i + 1 < np ? i + 1 : i;
                 long long s0, s1;
@@ -775,23 +901,20 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
                 if (lane == 0) { pt_scores[i] = s0; pt_scores[j] = s1; }
             }
             __syncwarp();
-            // the adjacency lists (and degrees) of all popped nodes are fetched together into the candidate array: one exposed round trip per
-            // iteration instead of one per node.  The array is compacted in place below -- the write index never passes the read index.
-            const uint32_t my_deg = (uint32_t)lane < np ? g.deg[pts[lane]] : 0u;
+            // the adjacency lists (and degrees) of all popped nodes go into the candidate array, which is compacted in place twice below --
+            // the write index never passes the read index
+            const uint32_t my_deg = (uint32_t)lane < np ? min(g.deg[pts[lane]], S) : 0u;
             for (uint32_t b = 0; b < np; b++) {
                 const uint32_t *nbrs = g.adj + (size_t)pts[b] * S;
                 for (uint32_t i = lane; i < S; i += 32) pre[b * S + i] = nbrs[i];
             }
             __syncwarp();
-            int n_pre = 0;
             for (uint32_t b = 0; b < np; b++) {
                 const uint32_t id = pts[b];
                 long long sc = pt_scores[b];
                 if (ba.n_desc) sc += descriptor_product(ba, scales, id);             // :170
                 cmps++;
-                bool fresh_v = false;
-                if (lane == 0) fresh_v = hs_insert_nc(hvis, vmask, id);
-                fresh_v = __shfl_sync(full, fresh_v, 0);
+                const bool fresh_v = __shfl_sync(full, fresh_mine, (int)b);
                 fill_vis += fresh_v;
                 const bool rec = fresh_v && (!ba.has_url || ba.has_url[id]);              // :172
                 if (rec) {
@@ -801,27 +924,48 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
                     }
                     n_out++;
                 }
-                // out-neighbours not seen as a neighbour before, first occurrence first
-                const uint32_t dg = min(__shfl_sync(full, my_deg, (int)b), S);
-                for (uint32_t b0 = 0; b0 < dg; b0 += 32) {
-                    const uint32_t i = b0 + lane;
-                    const bool have = i < dg;
-                    const uint32_t nid = have ? pre[b * S + i] : kEmpty;
-                    __syncwarp();                                                     // every lane has read its slot before the compaction writes
-                    const unsigned same = __match_any_sync(full, nid);
-                    bool ins = false;
-                    if (have && (same & ((1u << lane) - 1)) == 0) ins = hs_insert_nc(hadj, hmask, nid);
-                    const unsigned m = __ballot_sync(full, ins);
-                    if (ins) {
-                        pre[n_pre + __popc(m & ((1u << lane) - 1))] = nid;
-                        // the candidate's code and scale are needed a few hundred cycles from now: start them towards L2 while the
-                        // remaining nodes of the iteration go through their visited-set round trips
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ba.codes + (size_t)nid * ba.M));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ba.code_scale + nid));
-                    }
-                    n_pre += __popc(m);
-                    __syncwarp();
+            }
+            // look-ups, eight 32-neighbour units in flight per lane
+            const uint32_t upn = (S + 31) / 32, units = np * upn;
+            int n_unk = 0;
+            for (uint32_t u0 = 0; u0 < units; u0 += 8) {
+                uint32_t key[8], slot[8];
+#pragma unroll
+                for (uint32_t t = 0; t < 8; t++) {
+                    const uint32_t u = u0 + t, b = u / upn, i = (u % upn) * 32 + lane;
+                    const uint32_t dg = u < units ? __shfl_sync(full, my_deg, (int)b) : 0u;
+                    key[t] = i < dg ? pre[b * S + i] : kEmpty;
+                    slot[t] = key[t] != kEmpty ? __ldcg(hadj + ((key[t] * 2654435761u) & hmask)) : kEmpty;
                 }
+                __syncwarp();                                                         // every lane holds its keys before the compaction writes
+#pragma unroll
+                for (uint32_t t = 0; t < 8; t++) {
+                    const bool unk = key[t] != kEmpty && slot[t] != key[t];
+                    const unsigned m = __ballot_sync(full, unk);
+                    if (unk) pre[n_unk + __popc(m & ((1u << lane) - 1))] = key[t];
+                    n_unk += __popc(m);
+                }
+                __syncwarp();
+            }
+            // out-neighbours not seen as a neighbour before, first occurrence first
+            int n_pre = 0;
+            for (int c0 = 0; c0 < n_unk; c0 += 32) {
+                const int i = c0 + lane;
+                const bool have = i < n_unk;
+                const uint32_t nid = have ? pre[i] : kEmpty;
+                __syncwarp();                                                         // every lane has read its slot before the compaction writes
+                const unsigned same = __match_any_sync(full, nid);
+                bool ins = false;
+                if (have && (same & ((1u << lane) - 1)) == 0) ins = hs_insert_nc(hadj, hmask, nid);
+                const unsigned m = __ballot_sync(full, ins);
+                if (ins) {
+                    pre[n_pre + __popc(m & ((1u << lane) - 1))] = nid;
+                    // the candidate's code and scale are needed a few hundred cycles from now: start them towards L2
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ba.codes + (size_t)nid * ba.M));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ba.code_scale + nid));
+                }
+                n_pre += __popc(m);
+                __syncwarp();
             }
             fill_adj += n_pre;
             pq_cmps += n_pre;
@@ -840,6 +984,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, 8) k_beam_search_wq(GraphArgs g
                 const bool full0 = nb.len == nb.cap;
                 const long long last0 = full0 ? nb.scores[nb.len - 1] : 0;
                 unsigned m = __ballot_sync(full, have && !(full0 && last0 > cs));    // lib.rs:118 against the tail as it is now (it only grows)
+                if (nb.len >= 256 && nb.cap <= 608 && __popc(m) >= 3 && nb_insert_batch(nb, cid, cs, m, lane, scratch)) m = 0;   // one merge instead of popc(m) shifts
                 while (m) {
                     const int src = __ffs(m) - 1;
                     m &= m - 1;
@@ -1359,8 +1504,8 @@ MSE_API int mse_search_beam_dev(mse_index *ix, const uint16_t *d_q_f16, const fl
               (unsigned long long *)d_pq_cmps, ix->gw_status.as<uint32_t>(), topk, d_top_ids, (long long *)d_top_scores, d_top_len};
     const uint32_t sms = (uint32_t)sm_count(ix->device);
     const size_t wsmem = bq_warp_bytes(L, ix->graph_stride, ix->d, W) * kWqWarps;
-    if (d_qtm && use_wq(ix, nq) && wsmem <= 200 * 1024) {
-        // one warp per query
+    if (d_qtm && use_wq(ix, nq) && wsmem <= 200 * 1024 && W <= 32) {
+        // one warp per query (lane b keeps the state of popped node b)
         const uint32_t grid = std::min<uint32_t>((nq + kWqWarps - 1) / kWqWarps, sms * 8);
         MSE_CHECK(ix->gw_htabs.ensure((size_t)grid * kWqWarps * (hcap + vcap) * 4));
         if (ix->d == 1152) {

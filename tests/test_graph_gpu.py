@@ -582,3 +582,57 @@ def test_load_packed_index_files(mse, oracle, world, tmp_path):
         ids, sc, (c, pc) = oracle.beam_search(x, adj, off, codes, lo, w["med"], q[i], 40, 3, descriptors=desc, desc_scales=scales[i])
         assert np.array_equal(res[i][0], ids) and np.array_equal(res[i][1], sc) and int(cmps[i]) == c and int(pqc[i]) == pc
     vl.set_descriptors(None, None)
+
+
+def test_beam_search_long_lists(mse, oracle):
+    """L >= 128 in the warp-per-query schedule: the candidates of a pass are merged into the list in one step (nb_insert_batch)
+    instead of one NeighbourBuffer::insert each.  The data holds duplicated rows, whose estimates tie with each other and with listed
+    entries (the merge must then stand back and the pass is replayed insert by insert): ids, i64 scores, counters and the on-device
+    top-k must stay bit-identical to the oracle's sequential traversal."""
+    import torch
+    from oracle.rabitq_np import RabitQ as NpRabitQ
+    n, R = 3000, 24
+    x = clustered_f16(31, n, n_clusters=12)
+    x[1500:1800] = x[200:500]                       # 300 duplicated rows: equal exact scores AND equal RabitQ estimates
+    g = oracle.IndexGraph(n, R)
+    oracle.random_fill_graph(g, R, seed=2)
+    med = oracle.medioid(x)
+    oracle.build_graph(g, med, x, oracle.make_config(r=R, l=48, maxc=150), seed=3)
+    vl = mse.diskann.VectorList.from_f16s(x)
+    vl.set_graph(g.adj.copy(), g.deg.copy())
+    adj, off = g.to_csr()
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    q = np.concatenate([x[200:216], x[900:908], clustered_f16(32, 16, n_clusters=12)])
+    nq, k = q.shape[0], 10
+    ref = NpRabitQ.train(x[:1000].astype(np.float32), output_dims=512, seed=4)
+    rq = mse.diskann.RabitQ(ref.mean, ref.p)
+    codes, norms, dots = rq.quantize(x)
+    scale = (norms * dots).astype(np.float32)
+    rq.encode_index(vl, 0)
+    dq16 = torch.from_numpy(q.view(np.int16)).to(dev)
+    dq32 = torch.from_numpy(q.astype(np.float32)).to(dev)
+    qtm = torch.empty((nq, 513), dtype=torch.float32, device=dev)
+    rq.query_dev(dq32.data_ptr(), nq, qtm.data_ptr(), stream)
+    qtm_h = qtm.cpu().numpy()
+    top_ids = torch.zeros((nq, k), dtype=torch.int32, device=dev)
+    top_sc = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+    top_len = torch.zeros(nq, dtype=torch.int32, device=dev)
+    cm = torch.zeros(nq, dtype=torch.int64, device=dev)
+    pc = torch.zeros(nq, dtype=torch.int64, device=dev)
+    mse.diskann.set_graph_mode(2)
+    try:
+        for L, W in ((160, 4), (512, 4), (300, 2), (608, 8)):
+            mse.diskann.beam_search_dev(vl, dq16.data_ptr(), nq, L, W, med, k, top_ids.data_ptr(), top_sc.data_ptr(), top_len.data_ptr(),
+                                        cm.data_ptr(), pc.data_ptr(), stream, d_qtm=qtm.data_ptr(), rabitq=rq)
+            mse.diskann.greedy_search_check(vl, nq)
+            ti, ts, tl = top_ids.cpu().numpy().view(np.uint32), top_sc.cpu().numpy(), top_len.cpu().numpy()
+            for i in range(nq):
+                ids, sc, (c, p_) = oracle.beam_search(x, adj, off, codes, None, med, q[i], L, W, code_scale=scale, rabitq_qtm=qtm_h[i],
+                                                      rabitq_scale=np.float32(1.0 / np.sqrt(1152.0)))
+                o = np.argsort(-sc, kind="stable")[:k]
+                m = int(tl[i])
+                assert m == len(o) and np.array_equal(ti[i, :m], ids[o]) and np.array_equal(ts[i, :m], sc[o]), (L, W, i)
+                assert int(cm[i].item()) == c and int(pc[i].item()) == p_, (L, W, i)
+    finally:
+        mse.diskann.set_graph_mode(0)
