@@ -52,7 +52,7 @@ NCU_TRAFFIC = {
     # RabitQ beam L = 512: 17.377 + 4.516 GB per launch (visited-set tables), 1.53 GB algorithmic
     "greedy_bytes_per_row_byte": ((15.818 + 0.595) / 15.17, "profiles/r03e_ncu_full.md"),   # with the L2 row prefetch (r02t: 14.872 + 0.594)
     "text_blocks_bytes_per_launch": ((824.36 + 4.99) * 1e6, "profiles/r03e_ncu_full.md"),     # k_text_blocks: the 0.826 GB of weights, once
-    "beam_l512_bytes_per_launch": ((17.377 + 4.516) * 1e9, "profiles/r02t_ncu_full.md"),
+    "beam_l512_bytes_per_launch": ((20.838 + 3.397) * 1e9, "profiles/r03h_beam_l512_lines.txt"),   # r02t: 17.377 + 4.516
 }
 
 
@@ -773,7 +773,7 @@ def main():
                               "algorithmic_bytes": "expanded nodes x (2304 B row + 256 B adjacency) + scored candidates x (64 B code + 4 B scale), from the kernel's counters",
                               "kernel_ms_per_step": ms_bk, "kernel_share_of_step": ms_bk / hv["ms_per_step"],
                               "traffic": NCU_TRAFFIC["beam_l512_bytes_per_launch"][0] if (Lh, Wh, per_gpu) == (512, 4, 12_500_000) else None,
-                              "traffic_note": "ncu capture " + NCU_TRAFFIC["beam_l512_bytes_per_launch"][1] + " (L = 512, W = 4, 12.5 M rows): 14 x the algorithmic "
+                              "traffic_note": "ncu capture " + NCU_TRAFFIC["beam_l512_bytes_per_launch"][1] + " (L = 512, W = 4, 12.5 M rows): 16 x the algorithmic "
                                               "bytes -- the visited-set tables (cleared per query, one cold sector per probe)"},
                  "sweep": {s: {kk: vv for kk, vv in v.items() if kk not in ("clocks", "bytes", "unit")} for s, v in variants.items()},
                  "greedy_exact": greedy, "greedy_clocks": gclocks,
