@@ -129,6 +129,50 @@ __global__ void __launch_bounds__(256) k_layernorm(const __half *__restrict__ x,
     }
 }
 
+// Row statistics for a LayerNorm that is folded into the GEMM behind it (gemm_epilogues.cuh GemmOut::ln_stats): (mean, rstd) per row,
+// the same two-pass fp32 arithmetic as k_layernorm; reads x once and writes 8 bytes per row instead of a normalised copy.
+template <int NV>
+__global__ void __launch_bounds__(256) k_rowstats(const __half *__restrict__ x, float2 *__restrict__ stats, uint32_t rows, uint32_t D, float eps) {
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
+    if (row >= rows) return;
+    const uint4 *xr = (const uint4 *)(x + (size_t)row * D);
+    const uint32_t nv = D >> 3;
+    float v[NV][8];
+    float s = 0.f;
+    uint4 raw[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        uint32_t p = lane + 32 * i;
+        raw[i] = p < nv ? __ldg(xr + p) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const __half2 *h = (const __half2 *)&raw[i];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            float2 f = __half22float2(h[e]);
+            v[i][2 * e] = f.x; v[i][2 * e + 1] = f.y;
+            s += f.x + f.y;
+        }
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        uint32_t p = lane + 32 * i;
+        if (p < nv) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) { float d = v[i][e] - mean; q = fmaf(d, d, q); }
+        }
+    }
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) stats[row] = make_float2(mean, rsqrtf(q / (float)D + eps));
+}
+
 // MAP head pooling (aitemplate/model.py:98-111): one learned probe query per head against all S tokens.
 // kv: [B*S][2*D] (k | v).  qp: [D] fp32 = Wq*probe + bq, precomputed at load.  out: [B][D] fp16.  grid (H, B), 128 threads
 __global__ void __launch_bounds__(128) k_map_pool(const __half *__restrict__ kv, const float *__restrict__ qp, __half *__restrict__ out,
@@ -342,6 +386,10 @@ struct mse_encoder {
     cudaGraphExec_t text_graph[kGraphMaxBatch + 1] = {nullptr};
     uint64_t text_graph_launches[kGraphMaxBatch + 1] = {0};
     cudaStream_t cap_stream = nullptr;
+    // vision tower: LN1 / LN2 folded into the qkv / fc1 GEMMs (k_fold_ln weights, k_rowstats statistics)
+    struct FoldW { __half *qkv_w = nullptr, *fc1_w = nullptr; float *qkv_b = nullptr, *qkv_cs = nullptr, *fc1_b = nullptr, *fc1_cs = nullptr; };
+    std::vector<FoldW> vis_fold;
+    float2 *ln_stats = nullptr;             // [max_tokens]
     // one text query (64 tokens): the blocks as one persistent kernel (text_mega.cuh)
     tmega::LayerP *mega_layers = nullptr;   // device array [depth_t], LN folded into the qkv / fc1 weights
     uint32_t *mega_bar = nullptr;
@@ -456,7 +504,7 @@ void prof_collect(mse_encoder *e, uint64_t launches) {
 }
 
 int gemm(mse_encoder *e, const __half *A, const __half *W, uint32_t M, uint32_t N, uint32_t K, __half *C, const float *bias, int act,
-         const __half *res, uint32_t res_mod, cudaStream_t st) {
+         const __half *res, uint32_t res_mod, cudaStream_t st, const float2 *ln_stats = nullptr, const float *ln_cs = nullptr) {
     e->gemm_flops += 2.0 * M * N * (double)K;
     prof_mark(e, 0, st);
     struct Done { mse_encoder *e; cudaStream_t st; ~Done() { prof_mark(e, 0, st); } } done{e, st};
@@ -470,6 +518,8 @@ int gemm(mse_encoder *e, const __half *A, const __half *W, uint32_t M, uint32_t 
     o.splitk_ws = e->splitk_ws;
     o.splitk_cnt = e->splitk_cnt;
     o.splitk_ws_floats = mse_encoder::kSplitkFloats;
+    o.ln_stats = ln_stats;
+    o.ln_cs = ln_cs;
     return gemm_f16_tn_dev(e->device, A, W, M, N, K, K, K, o, st);
 }
 
@@ -477,6 +527,37 @@ int layernorm(const __half *x, __half *y, const float *g, const float *b, uint32
     if (D <= 5 * 256) launch_pdl(k_layernorm<5>, (rows * 32 + 255) / 256, 256, 0, st, x, y, g, b, rows, D, 1e-6f, D, 0u);
     else launch_pdl(k_layernorm<8>, (rows * 32 + 255) / 256, 256, 0, st, x, y, g, b, rows, D, 1e-6f, D, 0u);
     MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
+int rowstats(const __half *x, float2 *stats, uint32_t rows, uint32_t D, cudaStream_t st) {
+    if (D <= 5 * 256) launch_pdl(k_rowstats<5>, (rows * 32 + 255) / 256, 256, 0, st, x, stats, rows, D, 1e-6f);
+    else launch_pdl(k_rowstats<8>, (rows * 32 + 255) / 256, 256, 0, st, x, stats, rows, D, 1e-6f);
+    MSE_LAUNCH_OK();
+    return MSE_OK;
+}
+
+// vision tower: LN1 / LN2 folded into the weights of the GEMM behind them (the algebra is in text_mega.cuh)
+int prepare_vision_fold(mse_encoder *e) {
+    const uint32_t D = e->cfg[2], F = e->cfg[5];
+    const int depth = e->cfg[3];
+    if (getenv("MSE_NO_LN_FOLD") || D % 8 != 0 || D > 8 * 256) return MSE_OK;
+    std::vector<mse_encoder::FoldW> fw(depth);
+    for (int l = 0; l < depth; l++) {
+        const LayerW &L = e->vis.layers[l];
+        mse_encoder::FoldW &f = fw[l];
+        MSE_CHECK(dev_alloc(e, (void **)&f.qkv_w, (size_t)3 * D * D * 2));
+        MSE_CHECK(dev_alloc(e, (void **)&f.fc1_w, (size_t)F * D * 2));
+        MSE_CHECK(dev_alloc(e, (void **)&f.qkv_cs, (size_t)3 * D * 4));
+        MSE_CHECK(dev_alloc(e, (void **)&f.qkv_b, (size_t)3 * D * 4));
+        MSE_CHECK(dev_alloc(e, (void **)&f.fc1_cs, (size_t)F * 4));
+        MSE_CHECK(dev_alloc(e, (void **)&f.fc1_b, (size_t)F * 4));
+        tmega::k_fold_ln<<<(3 * D * 32 + 255) / 256, 256>>>(L.qkv_w, L.qkv_b, L.ln1_g, L.ln1_b, 3 * D, D, f.qkv_w, f.qkv_cs, f.qkv_b);
+        tmega::k_fold_ln<<<(F * 32 + 255) / 256, 256>>>(L.fc1_w, L.fc1_b, L.ln2_g, L.ln2_b, F, D, f.fc1_w, f.fc1_cs, f.fc1_b);
+        MSE_LAUNCH_OK();
+    }
+    MSE_CUDA(cudaDeviceSynchronize());
+    e->vis_fold = std::move(fw);
     return MSE_OK;
 }
 
@@ -572,10 +653,18 @@ int run_blocks(mse_encoder *e, const TowerW &tw, int depth, uint32_t B, uint32_t
         ap.n_items = (int)(B * H) * ap.q_items;
         ap.scale_log2e = scale_log2e;
     }
+    // vision tower: no LayerNorm pass -- row statistics (half the traffic) + the LN-folded GEMM on the raw residual stream
+    const bool fold = &tw == &e->vis && (int)e->vis_fold.size() >= depth && e->ln_stats && T > 128 && getenv("MSE_NO_LN_FOLD") == nullptr;
     for (int l = 0; l < depth; l++) {
         const LayerW &L = tw.layers[l];
+        if (fold) {
+            const mse_encoder::FoldW &f = e->vis_fold[l];
+            MSE_CHECK(rowstats(e->x, e->ln_stats, T, D, st));
+            MSE_CHECK(gemm(e, e->x, f.qkv_w, T, 3 * D, D, e->qkv, f.qkv_b, ACT_NONE, nullptr, 0, st, e->ln_stats, f.qkv_cs));
+        } else {
         MSE_CHECK(layernorm(e->x, e->xn, L.ln1_g, L.ln1_b, T, D, st));
         MSE_CHECK(gemm(e, e->xn, L.qkv_w, T, 3 * D, D, e->qkv, L.qkv_b, ACT_NONE, nullptr, 0, st));
+        }
         prof_mark(e, 1, st);
         if (use_tc)
             attn_tc::k_mha_tc<<<std::min(ap.n_items, sm_count(e->device)), attn_tc::kThreads, attn_tc::kSmemBytes, st>>>(tm64, tm16, e->att, ap);
@@ -585,8 +674,14 @@ int run_blocks(mse_encoder *e, const TowerW &tw, int depth, uint32_t B, uint32_t
         prof_mark(e, 1, st);
         MSE_LAUNCH_OK();
         MSE_CHECK(gemm(e, e->att, L.proj_w, T, D, D, e->x, L.proj_b, ACT_NONE, e->x, 0, st));
+        if (fold) {
+            const mse_encoder::FoldW &f = e->vis_fold[l];
+            MSE_CHECK(rowstats(e->x, e->ln_stats, T, D, st));
+            MSE_CHECK(gemm(e, e->x, f.fc1_w, T, F, D, e->hbuf, f.fc1_b, act, nullptr, 0, st, e->ln_stats, f.fc1_cs));
+        } else {
         MSE_CHECK(layernorm(e->x, e->xn, L.ln2_g, L.ln2_b, T, D, st));
         MSE_CHECK(gemm(e, e->xn, L.fc1_w, T, F, D, e->hbuf, L.fc1_b, act, nullptr, 0, st));
+        }
         MSE_CHECK(gemm(e, e->hbuf, L.fc2_w, T, D, F, e->x, L.fc2_b, ACT_NONE, e->x, 0, st));
     }
     return MSE_OK;
@@ -745,6 +840,8 @@ MSE_API int mse_encoder_create(const char *weights_path, int device, int max_bat
         if (has_v && (rc = dev_alloc(e, (void **)&e->img_dev, Bm * img * img * 3))) break;
         if (has_t && (rc = dev_alloc(e, (void **)&e->ids_dev, Bm * ctx * 4))) break;
         if ((rc = dev_alloc(e, (void **)&e->splitk_ws, mse_encoder::kSplitkFloats * 4))) break;
+        if ((rc = dev_alloc(e, (void **)&e->ln_stats, T * sizeof(float2)))) break;
+        if (has_v && (rc = prepare_vision_fold(e))) break;
         if ((rc = dev_alloc(e, (void **)&e->splitk_cnt, 256 * 4))) break;
         if (cudaMemset(e->splitk_cnt, 0, 256 * 4) != cudaSuccess) { set_error("encoder_create: cudaMemset failed"); rc = MSE_ERR_CUDA; break; }
     } while (0);

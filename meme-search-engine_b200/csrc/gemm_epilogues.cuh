@@ -23,6 +23,11 @@ struct GemmOut {
     float *splitk_ws;      // [splits][rows rounded to 64][ldws] fp32
     uint32_t *splitk_cnt;  // [n-slices x m-tiles]
     size_t splitk_ws_floats;
+    // LayerNorm folded into this GEMM (text_mega.cuh explains the algebra): the A operand is the raw residual stream, the weights carry
+    // gamma (k_fold_ln), and the epilogue applies  rstd[row] * (acc - mean[row] * ln_cs[col]) + bias[col]  (bias = b + W beta).
+    // ln_stats: [M] (mean, rstd) from k_rowstats; both NULL = plain GEMM.  tcgen05 TMA-store path only.
+    const float2 *ln_stats;
+    const float *ln_cs;
     int pdl_trigger_at;    // skinny kernels: where the CTA lets the next kernel's CTAs be scheduled (common.cuh): 0 start, 1 after the main loop, 2 never
 };
 
@@ -108,6 +113,25 @@ struct LinearEpilogueT {
     // bias / activation / (position-embedding style residual) applied in place on 32 fp32 accumulators
     __device__ __forceinline__ void compute(uint32_t row, uint32_t col0, uint32_t (&v)[32]) {
         const bool fullc = col0 + 32 <= N;
+        if (o.ln_stats) {
+            const float2 st = row < M ? __ldg(o.ln_stats + row) : make_float2(0.f, 0.f);
+            const float nmean = -st.x;
+            if (fullc) {
+                const float4 *c4 = (const float4 *)(o.ln_cs + col0);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 c = __ldg(c4 + j);
+                    v[4 * j] = __float_as_uint(st.y * fmaf(nmean, c.x, __uint_as_float(v[4 * j])));
+                    v[4 * j + 1] = __float_as_uint(st.y * fmaf(nmean, c.y, __uint_as_float(v[4 * j + 1])));
+                    v[4 * j + 2] = __float_as_uint(st.y * fmaf(nmean, c.z, __uint_as_float(v[4 * j + 2])));
+                    v[4 * j + 3] = __float_as_uint(st.y * fmaf(nmean, c.w, __uint_as_float(v[4 * j + 3])));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if (col0 + j < N) v[j] = __float_as_uint(st.y * fmaf(nmean, o.ln_cs[col0 + j], __uint_as_float(v[j])));
+            }
+        }
         if (o.bias) {
             if (fullc) {
                 const float4 *b4 = (const float4 *)(o.bias + col0);
