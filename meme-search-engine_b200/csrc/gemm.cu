@@ -94,7 +94,7 @@ int gemm_f16_tn_dev(int device, const __half *dA, const __half *dB, uint32_t M, 
     // a folded LayerNorm lives in LinearEpilogueT<true>::compute only: refuse every other route rather than drop it silently
     const bool tma_store_route = out.c16 && !out.c32 && out.ldc % 8 == 0 && ((uintptr_t)out.c16 & 15) == 0 && !out.debug_no_store && force_bn != 128 &&
                                  force_bn != 192 && getenv("MSE_GEMM_DIRECT_STORE") == nullptr;
-    MSE_REQUIRE(!out.ln_stats || (out.ln_cs && M > kSkinnyMaxM && tma_store_route), MSE_ERR_UNSUPPORTED,
+    MSE_REQUIRE(!out.ln_stats || (out.ln_cs && out.bias && M > kSkinnyMaxM && tma_store_route), MSE_ERR_UNSUPPORTED,
                 "gemm: a folded LayerNorm needs the tcgen05 TMA-store path (M > %u, fp16 output with 16-byte rows)", kSkinnyMaxM);
     static const bool use_pr = getenv("MSE_GEMM_PANEL") != nullptr;
     if (use_pr && M <= (uint32_t)skinny::pr::kBM && force_bn == 0 && ((uintptr_t)dA & 15) == 0 && ((uintptr_t)dB & 15) == 0 && getenv("MSE_GEMM_NO_SKINNY") == nullptr) {

@@ -114,25 +114,25 @@ struct LinearEpilogueT {
     __device__ __forceinline__ void compute(uint32_t row, uint32_t col0, uint32_t (&v)[32]) {
         const bool fullc = col0 + 32 <= N;
         if (o.ln_stats) {
+            // rstd * (acc - mean * cs) + bias  =  acc * rstd + (bias - mean * rstd * cs): two FMAs per element, bias included
             const float2 st = row < M ? __ldg(o.ln_stats + row) : make_float2(0.f, 0.f);
-            const float nmean = -st.x;
+            const float rstd = st.y, nmr = -st.x * st.y;
             if (fullc) {
-                const float4 *c4 = (const float4 *)(o.ln_cs + col0);
+                const float4 *c4 = (const float4 *)(o.ln_cs + col0), *b4 = (const float4 *)(o.bias + col0);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const float4 c = __ldg(c4 + j);
-                    v[4 * j] = __float_as_uint(st.y * fmaf(nmean, c.x, __uint_as_float(v[4 * j])));
-                    v[4 * j + 1] = __float_as_uint(st.y * fmaf(nmean, c.y, __uint_as_float(v[4 * j + 1])));
-                    v[4 * j + 2] = __float_as_uint(st.y * fmaf(nmean, c.z, __uint_as_float(v[4 * j + 2])));
-                    v[4 * j + 3] = __float_as_uint(st.y * fmaf(nmean, c.w, __uint_as_float(v[4 * j + 3])));
+                    const float4 c = __ldg(c4 + j), b = __ldg(b4 + j);
+                    v[4 * j] = __float_as_uint(fmaf(__uint_as_float(v[4 * j]), rstd, fmaf(nmr, c.x, b.x)));
+                    v[4 * j + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 1]), rstd, fmaf(nmr, c.y, b.y)));
+                    v[4 * j + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 2]), rstd, fmaf(nmr, c.z, b.z)));
+                    v[4 * j + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 3]), rstd, fmaf(nmr, c.w, b.w)));
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; j++)
-                    if (col0 + j < N) v[j] = __float_as_uint(st.y * fmaf(nmean, o.ln_cs[col0 + j], __uint_as_float(v[j])));
+                    if (col0 + j < N) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), rstd, fmaf(nmr, o.ln_cs[col0 + j], o.bias[col0 + j])));
             }
-        }
-        if (o.bias) {
+        } else if (o.bias) {
             if (fullc) {
                 const float4 *b4 = (const float4 *)(o.bias + col0);
 #pragma unroll
