@@ -18,8 +18,9 @@
 // tiles per query tile, 128 B/clk + a generic-to-async proxy fence per block) to tensor memory (tcgen05.st, 256 B/clk, no proxy
 // fence); a tile writes the shared P buffer only after the other tile's P V has read it, which the token order makes a wait that is
 // already satisfied.  0.306-0.33 -> 0.277 ms per layer at batch 64 (565 TFLOP/s); 45.4 -> 40.4 ms inside the power-capped tower step.
-// Measured without gain on top of it: 2^x for a quarter / half of the elements on the FMA pipe (packed-fp32 Cody-Waite polynomial;
-// profiles/r03f_attention_p_in_tmem.md).
+// Measured without gain on top of it (profiles/r03f_attention_p_in_tmem.md): 2^x for a quarter / half of the elements on the FMA pipe
+// (Cody-Waite polynomial; packed fp32 inside the token phase, and scalar OUTSIDE it -- every variant is slower the more elements it
+// moves), and passing the token a quarter / half / three quarters of the exponentials early (no change at all).
 #pragma once
 #include "ptx.cuh"
 #include <cuda_fp16.h>
@@ -297,7 +298,6 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&s_empty[t]);  // the score buffer can take block j+1 while we work from registers
                 if (row == 0) TR((int)t);        // 1: scores in registers
-                if (pingpong) ptx::named_bar_sync(2 + t, 256);     // wait for the MUFU token
                 const int kvalid = p.S - j * kBN;   // keys of this block that exist (>= 1); only the last block is partial
                 if (kvalid < kBN) {                 // warp-uniform
 #pragma unroll
@@ -316,13 +316,17 @@ k_mha_tc(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUten
                 const float f = grow ? ex2_approx(m_ref - m_blk) : 1.0f;  // rescale of O and l if the reference moves
                 if (grow) m_ref = m_blk;
                 const float neg_m = -m_ref;
+                // the row maximum above and the scaling of the scores need no MUFU: only the exponentials run under the token
+#pragma unroll
+                for (int i = 0; i < kBN; i++) v[i] = __float_as_uint(fmaf(__uint_as_float(v[i]), sc, neg_m));
+                if (pingpong) ptx::named_bar_sync(2 + t, 256);     // wait for the MUFU token
                 // all 128 exponentials first, packed to fp16 in registers: none of this needs the P buffer or O, so it
                 // overlaps the P V MMAs of the previous block
                 uint32_t pk[kBN / 2];
                 float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
                 for (int i = 0; i < kBN / 2; i++) {
-                    float p0 = fmaf(__uint_as_float(v[2 * i]), sc, neg_m), p1 = fmaf(__uint_as_float(v[2 * i + 1]), sc, neg_m);
+                    float p0 = __uint_as_float(v[2 * i]), p1 = __uint_as_float(v[2 * i + 1]);
                     if (!(p.debug & 1)) { p0 = ex2_approx(p0); p1 = ex2_approx(p1); }
                     rs0 += p0;
                     rs1 += p1;
