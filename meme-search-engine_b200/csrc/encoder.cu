@@ -574,6 +574,9 @@ int prepare_text_mega(mse_encoder *e) {
     if (items > (uint32_t)sm_count(e->device) || slices(D, tmega::kBnFc2) > 256 ||
         (size_t)tmega::kFc2Splits * 64 * D > mse_encoder::kSplitkFloats)
         return MSE_OK;
+    int coop = 0;
+    MSE_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device));
+    if (!coop) return MSE_OK;                  // no co-residency guarantee: keep the multi-kernel path
     MSE_CUDA(cudaFuncSetAttribute(tmega::k_text_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmega::kSmemBytes));
     int per_sm = 0;
     MSE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tmega::k_text_blocks, tmega::kThreads, tmega::kSmemBytes));
