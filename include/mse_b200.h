@@ -329,6 +329,14 @@ int mse_encode_images_u8_dev(mse_encoder *e, const uint8_t *d_rgb_hwc, int batch
  * files, the headers are read on the host and the pixel arrays (BGR, bottom-up) are unpacked on the device.  Any other size or pixel
  * format is MSE_ERR_UNSUPPORTED -- decode it on the host and call mse_encode_images_u8. */
 int mse_encode_images_bmp(mse_encoder *e, const uint8_t *const *bmps, const size_t *lens, int batch, uint16_t *out_f16);
+/* resize_for_embed_sync (src/common.rs:31-54) on the device: an RGB8 image [h][w][3] of any size -> out_w x out_h by a separable
+ * convolution in Pillow's fixed-point arithmetic (the fast_image_resize crate the reference calls descends from it); filter 0 = the
+ * reference's rule (Hamming when both dimensions shrink, else Lanczos3, :43-44), 1 = Hamming, 2 = Lanczos3.  Host pointers. */
+int mse_resize_rgb_u8(int device, const uint8_t *rgb, uint32_t w, uint32_t h, uint32_t out_w, uint32_t out_h, int filter, uint8_t *out);
+/* decoded images of any size (rgb[i]: host RGB8 [heights[i]][widths[i]][3]) resized on the device into the tower's input: what the
+ * ingest client does with resize_for_embed_sync + a BMP + the HTTP hop (src/main.rs:392,445,946) in one call */
+int mse_encode_images_resized(mse_encoder *e, const uint8_t *const *rgb, const uint32_t *widths, const uint32_t *heights, int batch,
+                              uint16_t *out_f16);
 int mse_encode_text_ids(mse_encoder *e, const int32_t *ids, int batch, uint16_t *out_f16);
 int mse_encode_text_ids_dev(mse_encoder *e, const int32_t *d_ids, int batch, uint16_t *d_out_f16, void *stream);
 /* per-layer parity hooks: token activations [batch*S][dim] fp16 after the embedding and the first n_blocks blocks */

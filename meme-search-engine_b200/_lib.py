@@ -117,6 +117,8 @@ _SIGS = {
     "mse_encode_images_u8": (_i32, [_vp, _vp, _i32, _vp]),
     "mse_encode_images_u8_dev": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "mse_encode_images_bmp": (_i32, [_vp, _vp, _vp, _i32, _vp]),
+    "mse_resize_rgb_u8": (_i32, [_i32, _vp, _u32, _u32, _u32, _u32, _i32, _vp]),
+    "mse_encode_images_resized": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "mse_encode_text_ids": (_i32, [_vp, _vp, _i32, _vp]),
     "mse_encode_text_ids_dev": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "mse_encode_images_hidden": (_i32, [_vp, _vp, _i32, _i32, _vp]),

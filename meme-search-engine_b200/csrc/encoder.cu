@@ -1017,6 +1017,37 @@ MSE_API int mse_encode_images_bmp(mse_encoder *e, const uint8_t *const *bmps, co
     return MSE_OK;
 }
 
+// Decoded images of any size (what the ingest client holds before resize_for_embed_sync, src/common.rs:31-54): resized on the device
+// straight into the tower's input buffer, no BMP round trip.
+MSE_API int mse_encode_images_resized(mse_encoder *e, const uint8_t *const *rgb, const uint32_t *widths, const uint32_t *heights, int batch,
+                                      uint16_t *out_f16) {
+    MSE_REQUIRE(e != nullptr, MSE_ERR_INVALID, "encode_images_resized: NULL handle");
+    MSE_REQUIRE(e->cfg[9], MSE_ERR_STATE, "encode_images_resized: this encoder was loaded without a vision tower");
+    MSE_REQUIRE(batch >= 0 && (batch == 0 || (rgb && widths && heights && out_f16)), MSE_ERR_INVALID, "encode_images_resized: bad argument");
+    MSE_REQUIRE(batch <= e->max_batch, MSE_ERR_INVALID, "encode_images_resized: max batch size is %d", e->max_batch);
+    if (batch == 0) return MSE_OK;
+    MSE_CHECK(use_device(e->device));
+    const uint32_t S = e->cfg[0];
+    cudaStream_t st = e->stream;
+    ResizeWork wk;
+    int rc = MSE_OK;
+    for (int i = 0; i < batch && rc == MSE_OK; i++)
+        rc = resize_rgb_to_device(wk, rgb[i], widths[i], heights[i], S, S, 0, e->img_dev + (size_t)i * S * S * 3, st);
+    if (rc == MSE_OK) {
+        prof_begin(e);
+        const uint64_t l0 = g_launches.load();
+        rc = vision_forward(e, (uint32_t)batch, -1, st);
+        e->stats[4] = g_launches.load() - l0;
+    }
+    if (rc == MSE_OK && cudaMemcpyAsync(out_f16, e->outb, (size_t)batch * e->cfg[2] * 2, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+        set_error("encode_images_resized: D2H failed");
+        rc = MSE_ERR_CUDA;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == MSE_OK) { set_error("encode_images_resized: stream failed"); rc = MSE_ERR_CUDA; }
+    wk.release();
+    return rc;
+}
+
 MSE_API int mse_encode_images_hidden(mse_encoder *e, const uint8_t *rgb_hwc, int batch, int n_blocks, uint16_t *out_tokens_f16) {
     MSE_REQUIRE(n_blocks >= 0, MSE_ERR_INVALID, "encode_images_hidden: n_blocks must be >= 0");
     return encode_images_impl(e, rgb_hwc, false, batch, out_tokens_f16, false, n_blocks, e ? e->stream : nullptr);

@@ -45,6 +45,15 @@ struct FlatPending {
     FlatPending(const float *q, uint32_t nq_, uint32_t k_, const FlatOut &o, cudaStream_t s, bool live_) : d_q(q), nq(nq_), k(k_), out(o), st(s), live(live_), queued(true) {}
 };
 
+// resize.cu: device buffers of one resize (source image, intermediate image, bounds + fixed-point coefficients of the two passes)
+struct ResizeWork {
+    DevBuf src, tmp, bh, kh, bv, kv;
+    void release() { src.release(); tmp.release(); bh.release(); kh.release(); bv.release(); kv.release(); }
+};
+// host RGB8 [h][w][3] -> device RGB8 [out_h][out_w][3]; filter 0 = resize_for_embed_sync's rule (common.rs:43-44), 1 Hamming, 2 Lanczos3
+int resize_rgb_to_device(ResizeWork &wk, const uint8_t *rgb, uint32_t w, uint32_t h, uint32_t out_w, uint32_t out_h, int filter, uint8_t *d_out,
+                         cudaStream_t st);
+
 }  // namespace mse
 
 struct mse_index {

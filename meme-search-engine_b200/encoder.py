@@ -51,6 +51,21 @@ class Encoder:
         check(lib().mse_encode_images_bmp(self._h, ptrs, lens, n, out.ctypes.data_as(C.c_void_p)), "mse_encode_images_bmp")
         return out
 
+    def encode_image_resized(self, images) -> np.ndarray:
+        """images: decoded RGB8 arrays [h, w, 3] of ANY size (what the ingest client holds before resize_for_embed_sync,
+        src/common.rs:31-54): resized on the device (Hamming when both dimensions shrink, else Lanczos3) into the tower's input."""
+        arrs = [np.ascontiguousarray(a, np.uint8) for a in images]
+        for a in arrs:
+            if a.ndim != 3 or a.shape[2] != 3:
+                raise MseError(f"encode_image_resized expects [h,w,3] uint8 arrays, got {a.shape}")
+        n = len(arrs)
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        ws = (C.c_uint32 * n)(*[a.shape[1] for a in arrs])
+        hs = (C.c_uint32 * n)(*[a.shape[0] for a in arrs])
+        out = np.empty((n, self.dim), np.float16)
+        check(lib().mse_encode_images_resized(self._h, ptrs, ws, hs, n, out.ctypes.data_as(C.c_void_p)), "mse_encode_images_resized")
+        return out
+
     def encode_text(self, ids: np.ndarray) -> np.ndarray:
         """ids: [B, ctx] token ids (int). -> [B, dim] fp16."""
         t = np.ascontiguousarray(ids, np.int32)
@@ -87,3 +102,16 @@ class Encoder:
         out = np.empty((t.shape[0], self.ctx, self.dim), np.float16)
         check(lib().mse_encode_text_hidden(self._h, t.ctypes.data_as(C.c_void_p), t.shape[0], n_blocks, out.ctypes.data_as(C.c_void_p)), "mse_encode_text_hidden")
         return out
+
+
+def resize_for_embed(image: np.ndarray, size: tuple[int, int], device: int = 0, filter: int = 0) -> np.ndarray:
+    """resize_for_embed_sync (src/common.rs:31-54) on the device: RGB8 [h, w, 3] -> [size[1], size[0], 3] (size = (width, height) as
+    InferenceServerConfig.image_size); filter 0 = the reference's rule, 1 = Hamming, 2 = Lanczos3."""
+    a = np.ascontiguousarray(image, np.uint8)
+    if a.ndim != 3 or a.shape[2] != 3:
+        raise MseError(f"resize_for_embed expects an [h,w,3] uint8 array, got {a.shape}")
+    out = np.empty((size[1], size[0], 3), np.uint8)
+    check(lib().mse_resize_rgb_u8(device, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], size[0], size[1], filter,
+                                  out.ctypes.data_as(C.c_void_p)), "mse_resize_rgb_u8")
+    return out
+
