@@ -44,8 +44,8 @@ TEXT_WEIGHT_BYTES = 0.826e9  # 412.9 M parameters touched x 2 B
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernels from the committed `ncu --set full` captures (per launch
 # or per algorithmic byte).  Measured under a profiler on the named capture, not by this run.
 NCU_TRAFFIC = {
-    # profiles/r02t_ncu_full.md: one block at batch 256 = fc2 2.573 + QKV 1.680 + out-proj 1.257 + fc1 2.004 GB (read + write); x 27 blocks
-    "tower_gemm_bytes_per_step_b256": (27 * (2.573 + 1.680 + 1.257 + 2.004) * 1e9, "profiles/r02t_ncu_full.md"),
+    # profiles/r03k_tower_block_final_ncu.md: one block at batch 256 = QKV 1.759 + out-proj 1.263 + fc1 2.072 + fc2 3.606 GB (read + write); x 27 blocks
+    "tower_gemm_bytes_per_step_b256": (27 * (1.759 + 1.263 + 2.072 + 3.606) * 1e9, "profiles/r03k_tower_block_final_ncu.md"),
     # profiles/r02t_ncu_full.md: 17.155 GB read + 10.8 MB written for the 17.150 GB of rows the launch scored
     "flat_gemm_bytes_per_row_byte": ((17.154500 + 0.010778) / 17.149723, "profiles/r02t_ncu_full.md"),
     # profiles/r02t_ncu_full.md (12.5 M rows, 4096 queries): greedy L = 64: 14.872 GB read + 0.594 GB written for 15.17 GB of gathered rows;
