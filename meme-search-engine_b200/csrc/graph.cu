@@ -1202,7 +1202,8 @@ static int check_dev_start(const mse_index *ix, const uint32_t *d_starts, uint32
 // bytes: every probe of a cold table is a sector from HBM, every query clears its table), but HALVING it measured slower, not faster
 // (12.5 M rows: L = 64 2.91 -> 3.67 ms, L = 512 21.1 -> 21.6 ms; MSE_BEAM_HASH_PER_L): longer probe chains are dependent round trips.
 static uint32_t beam_hash_capacity(uint32_t L, uint32_t stride) {
-    static const long env = getenv("MSE_BEAM_HASH_PER_L") ? atol(getenv("MSE_BEAM_HASH_PER_L")) : 0;   // tuning aid: slots per unit of L
+    const char *e = getenv("MSE_BEAM_HASH_PER_L");   // tuning aid: slots per unit of L
+    const long env = e ? atol(e) : 0;
     uint64_t v = (uint64_t)std::max<uint32_t>(L, 64) * (env > 0 ? (uint64_t)env : 4ull * stride);
     uint32_t p = 8192;
     while (p < v && p < (1u << 30)) p <<= 1;

@@ -81,12 +81,21 @@ for v in variants:
         nd = float(dist.double().sum().item())
         out[v] = {"ms": ms, "qps": nq / ms * 1e3, "recall_at_10": recall(ids), "distances_per_query": nd / nq, "row_gbs": nd * D * 2 / (ms * 1e-3) / 1e9}
     else:
-        L, W = int(p[1]), int(p[2])
+        L, W = int(p[1]), int(p[2])                      # b:L:W[:hp=<visited_adjacent slots per unit of L>]
+        import os
+        for kv in p[3:]:
+            key, val = kv.split("=")
+            os.environ[{"hp": "MSE_BEAM_HASH_PER_L"}[key]] = val
         ti = torch.empty((nq, k), dtype=torch.int32, device=dev); ts = torch.empty((nq, k), dtype=torch.int64, device=dev)
         tl = torch.empty(nq, dtype=torch.int32, device=dev); cm = torch.empty(nq, dtype=torch.int64, device=dev); pc = torch.empty(nq, dtype=torch.int64, device=dev)
         ms = timed(lambda: dk.beam_search_dev(vl, q16.data_ptr(), nq, L, W, med, k, ti.data_ptr(), ts.data_ptr(), tl.data_ptr(), cm.data_ptr(), pc.data_ptr(),
                                               stream, d_qtm=qtm.data_ptr(), rabitq=rq))
-        dk.greedy_search_check(vl, nq)
+        try:
+            dk.greedy_search_check(vl, nq)
+        except Exception as e:
+            out[v] = {"ms": ms, "error": str(e)}
+            print(json.dumps({v: out[v]}), flush=True)
+            continue
         ex, co = float(cm.double().sum().item()), float(pc.double().sum().item())
         out[v] = {"ms": ms, "qps": nq / ms * 1e3, "recall_at_10": recall(ti), "exact_rows_per_query": ex / nq, "codes_per_query": co / nq,
                   "algorithmic_gbs": (ex * (D * 2 + R * 4) + co * 68) / (ms * 1e-3) / 1e9}
