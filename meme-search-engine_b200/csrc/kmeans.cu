@@ -281,6 +281,7 @@ MSE_API int mse_shard_assign(mse_index *ix, const float *centroids, uint32_t k, 
                              uint64_t *bal_count, uint32_t *assign) {
     MSE_CHECK(km_check_args(ix, centroids, k, spill, "shard_assign"));
     MSE_REQUIRE(shard_counts && bal_count && assign, MSE_ERR_INVALID, "shard_assign: NULL buffer");
+    MSE_REQUIRE(*bal_count >= 1, MSE_ERR_INVALID, "shard_assign: bal_count starts at 1 (dump_processor.rs:426), got 0");
     MSE_CHECK(use_device(ix->device));
     const uint64_t batch = 1u << 18;
     DevBuf cent, dots;
