@@ -74,3 +74,19 @@ def test_graph_entries_validate_arguments_without_device(mse):
     assert l.mse_index_robust_stitch(None, None, None, 0) == -1
     assert l.mse_rabitq_preprocess_query(None, None, 1, None, None) == -1
     assert l.mse_rabitq_query_dev(None, None, 1, None, None) == -1
+
+
+def test_r03_entries_validate_arguments_without_device(mse):
+    """The entries added in the second half of round 2 (shard k-means / assignment, resize) reject NULL handles, NULL buffers and
+    out-of-range sizes before touching a device."""
+    l = mse.lib()
+    cnt = np.zeros(4, np.uint32)
+    assert l.mse_kmeans_assign(None, None, 2, 2, 1, cnt.ctypes.data, None) == -1
+    assert l.mse_kmeans_anneal(None, 2, 2, 1, 0, None, None, None) == -1
+    st = np.zeros(2, np.uint64)
+    assert l.mse_shard_assign(None, None, 2, 2, 0.2, st.ctypes.data, st.ctypes.data, None) == -1
+    px = np.zeros((2, 2, 3), np.uint8)
+    out = np.zeros((2, 2, 3), np.uint8)
+    assert l.mse_resize_rgb_u8(0, px.ctypes.data, 2, 2, 2, 2, 7, out.ctypes.data) == -1      # filter out of range
+    assert l.mse_resize_rgb_u8(0, px.ctypes.data, 2, 2, 2, 2, 0, None) == -1                  # NULL output
+    assert l.mse_encode_images_resized(None, None, None, None, 1, None) == -1
