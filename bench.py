@@ -919,104 +919,108 @@ def main():
 
     # ============================================================ end to end (C5 at reduced scale): encode -> index -> build -> serve
     if "e2e" in wl:
-        B, nq_t, nq_i, Ls, k = 256, 500, 500, 64, 10
-        n_img = (args.e2e_images_total // world if args.e2e_images_total else args.e2e_images) // B * B
-        wpath = os.path.join(tempfile.gettempdir(), f"mse_bench_e2e_rank{rank}.msew")
-        sd = random_openclip_state_dict(dev)
-        sd.update(random_openclip_text_state_dict(dev))
-        mse_b200.weights.save_weights(wpath, sd, mse_b200.weights.config_for(sd))
-        del sd
-        enc = mse_b200.Encoder(wpath, device=local_rank, max_batch=B)
-        os.remove(wpath)
-        vl = dk.VectorList(D, device=local_rank, id_base=rank * n_img)      # this rank's id range of the index under construction
-        vl.reserve(n_img)
-        feat = torch.empty((B, D), dtype=torch.float16, device=dev)
+        try:   # the default N = 8 run does this workload at a size it was never run at: a failure here must not cost the whole line
+            B, nq_t, nq_i, Ls, k = 256, 500, 500, 64, 10
+            n_img = (args.e2e_images_total // world if args.e2e_images_total else args.e2e_images) // B * B
+            wpath = os.path.join(tempfile.gettempdir(), f"mse_bench_e2e_rank{rank}.msew")
+            sd = random_openclip_state_dict(dev)
+            sd.update(random_openclip_text_state_dict(dev))
+            mse_b200.weights.save_weights(wpath, sd, mse_b200.weights.config_for(sd))
+            del sd
+            enc = mse_b200.Encoder(wpath, device=local_rank, max_batch=B)
+            os.remove(wpath)
+            vl = dk.VectorList(D, device=local_rank, id_base=rank * n_img)      # this rank's id range of the index under construction
+            vl.reserve(n_img)
+            feat = torch.empty((B, D), dtype=torch.float16, device=dev)
 
-        def image_source(seed):
-            gg = torch.Generator(device=dev).manual_seed(seed)
-            base = torch.randint(0, 256, (B, 24, 24, 3), generator=gg, device=dev, dtype=torch.uint8)
+            def image_source(seed):
+                gg = torch.Generator(device=dev).manual_seed(seed)
+                base = torch.randint(0, 256, (B, 24, 24, 3), generator=gg, device=dev, dtype=torch.uint8)
 
-            def make_batch():
-                # blocky pattern + per-pixel noise so that images (and their embeddings) differ from each other
-                up = base[torch.randperm(B, generator=gg, device=dev)].repeat_interleave(16, 1).repeat_interleave(16, 2).to(torch.int16)
-                noise = torch.randint(-40, 41, (B, 384, 384, 3), generator=gg, device=dev, dtype=torch.int16)
-                return (up + noise).clamp_(0, 255).to(torch.uint8).contiguous()
-            return make_batch
-        make_batch = image_source(6 + rank)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        imgs = make_batch()
-        enc.encode_image_dev(imgs.data_ptr(), B, feat.data_ptr(), stream)      # warm-up
-        barrier()
-        t_wall0 = time.perf_counter()
-        enc_ms = 0.0
-        for b0 in range(0, n_img, B):
+                def make_batch():
+                    # blocky pattern + per-pixel noise so that images (and their embeddings) differ from each other
+                    up = base[torch.randperm(B, generator=gg, device=dev)].repeat_interleave(16, 1).repeat_interleave(16, 2).to(torch.int16)
+                    noise = torch.randint(-40, 41, (B, 384, 384, 3), generator=gg, device=dev, dtype=torch.int16)
+                    return (up + noise).clamp_(0, 255).to(torch.uint8).contiguous()
+                return make_batch
+            make_batch = image_source(6 + rank)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             imgs = make_batch()
-            ev[0].record()
-            enc.encode_image_dev(imgs.data_ptr(), B, feat.data_ptr(), stream)
-            vl.add_f16_dev(feat.data_ptr(), B, stream)
-            ev[1].record()
-            ev[1].synchronize()
-            enc_ms += ev[0].elapsed_time(ev[1])
-        t0 = time.perf_counter()
-        dk.random_fill_graph(vl, 64, seed=1 + rank)
-        med = dk.medioid(vl)
-        bst = dk.build_graph(vl, med, dk.IndexBuildConfig(r=64, l=192, maxc=750), seed=7 + rank)
-        build_s = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([enc_ms, build_s], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            enc_ms, build_s = float(t[0].item()), float(t[1].item())
-        # serve: the same 500 text + 500 image queries on every rank (replicated), every shard searched, one all-gather + merge
-        gid = torch.Generator(device="cpu").manual_seed(8)
-        ids = torch.ones((nq_t, 64), dtype=torch.int32)
-        for i in range(nq_t):
-            Lt = int(torch.randint(3, 17, (1,), generator=gid))
-            ids[i, :Lt] = torch.randint(2, 32000, (Lt,), generator=gid, dtype=torch.int32)
-        ids_dev = ids.to(dev)
-        nq = nq_t + nq_i
-        q_feat = torch.empty((nq, D), dtype=torch.float16, device=dev)
-        make_query_batch = image_source(66)
-        q_imgs = [make_query_batch() for _ in range((nq_i + B - 1) // B)]
-        o_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
-        o_sc = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        res_host = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+            enc.encode_image_dev(imgs.data_ptr(), B, feat.data_ptr(), stream)      # warm-up
+            barrier()
+            t_wall0 = time.perf_counter()
+            enc_ms = 0.0
+            for b0 in range(0, n_img, B):
+                imgs = make_batch()
+                ev[0].record()
+                enc.encode_image_dev(imgs.data_ptr(), B, feat.data_ptr(), stream)
+                vl.add_f16_dev(feat.data_ptr(), B, stream)
+                ev[1].record()
+                ev[1].synchronize()
+                enc_ms += ev[0].elapsed_time(ev[1])
+            t0 = time.perf_counter()
+            dk.random_fill_graph(vl, 64, seed=1 + rank)
+            med = dk.medioid(vl)
+            bst = dk.build_graph(vl, med, dk.IndexBuildConfig(r=64, l=192, maxc=750), seed=7 + rank)
+            build_s = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([enc_ms, build_s], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                enc_ms, build_s = float(t[0].item()), float(t[1].item())
+            # serve: the same 500 text + 500 image queries on every rank (replicated), every shard searched, one all-gather + merge
+            gid = torch.Generator(device="cpu").manual_seed(8)
+            ids = torch.ones((nq_t, 64), dtype=torch.int32)
+            for i in range(nq_t):
+                Lt = int(torch.randint(3, 17, (1,), generator=gid))
+                ids[i, :Lt] = torch.randint(2, 32000, (Lt,), generator=gid, dtype=torch.int32)
+            ids_dev = ids.to(dev)
+            nq = nq_t + nq_i
+            q_feat = torch.empty((nq, D), dtype=torch.float16, device=dev)
+            make_query_batch = image_source(66)
+            q_imgs = [make_query_batch() for _ in range((nq_i + B - 1) // B)]
+            o_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+            o_sc = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            res_host = torch.empty((nq, k), dtype=torch.int32).pin_memory()
 
-        def embed_queries():
-            for b0 in range(0, nq_t, B):
-                m = min(B, nq_t - b0)
-                enc.encode_text_dev(ids_dev[b0:b0 + m].data_ptr(), m, q_feat[b0:b0 + m].data_ptr(), stream)
-            for bi, b0 in enumerate(range(0, nq_i, B)):
-                m = min(B, nq_i - b0)
-                enc.encode_image_dev(q_imgs[bi].data_ptr(), m, q_feat[nq_t + b0:nq_t + b0 + m].data_ptr(), stream)
+            def embed_queries():
+                for b0 in range(0, nq_t, B):
+                    m = min(B, nq_t - b0)
+                    enc.encode_text_dev(ids_dev[b0:b0 + m].data_ptr(), m, q_feat[b0:b0 + m].data_ptr(), stream)
+                for bi, b0 in enumerate(range(0, nq_i, B)):
+                    m = min(B, nq_i - b0)
+                    enc.encode_image_dev(q_imgs[bi].data_ptr(), m, q_feat[nq_t + b0:nq_t + b0 + m].data_ptr(), stream)
 
-        def serve():
-            embed_queries()
-            grp.graph_search_dev(vl, q_feat.data_ptr(), nq, Ls, med, k, o_ids.data_ptr(), o_sc.data_ptr(), 0, stream)
-            res_host.copy_(o_ids, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            def serve():
+                embed_queries()
+                grp.graph_search_dev(vl, q_feat.data_ptr(), nq, Ls, med, k, o_ids.data_ptr(), o_sc.data_ptr(), 0, stream)
+                res_host.copy_(o_ids, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
 
-        serve()
-        ms_serve, _ = timed(serve, 1, 3)
-        dk.greedy_search_check(vl, nq)
-        # recall@10 of the served answers against the exact top-10 over all shards
-        q32 = q_feat.float().contiguous()
-        gt_i = torch.empty((nq, k), dtype=torch.int32, device=dev)
-        gt_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        grp.flat_search_dev(vl, q32.data_ptr(), nq, k, gt_i.data_ptr(), gt_s.data_ptr(), stream)
-        grp.check()
-        rec = float((o_ids.long().unsqueeze(2) == gt_i.long().unsqueeze(1)).any(dim=2).float().mean().item())
-        wall = time.perf_counter() - t_wall0
-        full["e2e_pipeline"] = {"metric": "end to end: encode + index + build + serve (BASELINE configs[4])", "n_gpus": world,
-                                "config": {"workload": "e2e_encode_build_serve", "images_total": n_img * world, "images_per_gpu": n_img, "graph": "R 64, L 192, C 750, one sub-graph per GPU",
-                                           "queries": "500 text (token ids) + 500 image, replicated, L = 64, top-10 merged over the shards",
-                                           "note": "configs[4] names 1M images on 8 GPUs (>= 61 s of encoder work at the tensor roofline); default at N = 8: 1M / 8 per rank"},
-                                "encode": {"images_per_s": world * n_img / (enc_ms * 1e-3), "seconds": enc_ms * 1e-3},
-                                "build": {"seconds": build_s, "points_per_s": world * n_img / build_s, "stats": bst},
-                                "serve": {"queries_per_s": nq / (ms_serve * 1e-3), "ms_per_batch_of_1000": ms_serve, "recall_at_10": rec,
-                                          "includes": "text tower (500) + image tower (500) on every rank + sharded graph search + gather/merge + D2H of top-10 ids"},
-                                "wall_seconds_total": wall}
-        vl.close()
-        enc.close()
+            serve()
+            ms_serve, _ = timed(serve, 1, 3)
+            dk.greedy_search_check(vl, nq)
+            # recall@10 of the served answers against the exact top-10 over all shards
+            q32 = q_feat.float().contiguous()
+            gt_i = torch.empty((nq, k), dtype=torch.int32, device=dev)
+            gt_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            grp.flat_search_dev(vl, q32.data_ptr(), nq, k, gt_i.data_ptr(), gt_s.data_ptr(), stream)
+            grp.check()
+            rec = float((o_ids.long().unsqueeze(2) == gt_i.long().unsqueeze(1)).any(dim=2).float().mean().item())
+            wall = time.perf_counter() - t_wall0
+            full["e2e_pipeline"] = {"metric": "end to end: encode + index + build + serve (BASELINE configs[4])", "n_gpus": world,
+                                    "config": {"workload": "e2e_encode_build_serve", "images_total": n_img * world, "images_per_gpu": n_img, "graph": "R 64, L 192, C 750, one sub-graph per GPU",
+                                               "queries": "500 text (token ids) + 500 image, replicated, L = 64, top-10 merged over the shards",
+                                               "note": "configs[4] names 1M images on 8 GPUs (>= 61 s of encoder work at the tensor roofline); default at N = 8: 1M / 8 per rank"},
+                                    "encode": {"images_per_s": world * n_img / (enc_ms * 1e-3), "seconds": enc_ms * 1e-3},
+                                    "build": {"seconds": build_s, "points_per_s": world * n_img / build_s, "stats": bst},
+                                    "serve": {"queries_per_s": nq / (ms_serve * 1e-3), "ms_per_batch_of_1000": ms_serve, "recall_at_10": rec,
+                                              "includes": "text tower (500) + image tower (500) on every rank + sharded graph search + gather/merge + D2H of top-10 ids"},
+                                    "wall_seconds_total": wall}
+            vl.close()
+            enc.close()
+        except Exception as ex:
+            full["e2e_pipeline_error"] = f"{type(ex).__name__}: {ex}"
+            print("e2e workload failed:", full["e2e_pipeline_error"], file=sys.stderr)
 
     # ============================================================ CPU baselines (rank 0, N = 1) and the output line
     comm = {"backend": "nccl" if world > 1 else None, **grp.info()}
@@ -1085,6 +1089,8 @@ def main():
         result["e2e_pipeline"] = {"images_total": e["config"]["images_total"], "encode_images_per_s": round(e["encode"]["images_per_s"], 1),
                                   "encode_s": round(e["encode"]["seconds"], 1), "build_s": round(e["build"]["seconds"], 2),
                                   "serve_queries_per_s": round(e["serve"]["queries_per_s"], 1), "serve_recall_at_10": round(e["serve"]["recall_at_10"], 4)}
+    elif "e2e_pipeline_error" in full:
+        result["e2e_pipeline"] = {"error": full["e2e_pipeline_error"][:200]}
     sys.stdout.flush()
     print(json.dumps(result), flush=True)
 
