@@ -42,13 +42,33 @@ def main():
     data = torch.tensor(clustered_f16(71, ROWS, n_clusters=16).astype(np.float32))
     torch.manual_seed(SEED)
     buf = io.StringIO()
-    with contextlib.redirect_stdout(buf):
-        out = ns["simulated_annealing"](data, K, max_iter=ITERS, batch_size=BATCH)
+    # the script's cluster_sizes never leave `fitness`; torch.bincount (kmeans.py:88) is observed while the unchanged function runs
+    seen = []
+    real_bincount = torch.bincount
+
+    def spy(*a, **kw):
+        r = real_bincount(*a, **kw)
+        seen.append(r.tolist())
+        return r
+    torch.bincount = spy
+    try:
+        with contextlib.redirect_stdout(buf):
+            out = ns["simulated_annealing"](data, K, max_iter=ITERS, batch_size=BATCH)
+    finally:
+        torch.bincount = real_bincount
+    n_batches = -(-ROWS // BATCH)
+    per_call = n_batches * ns["SPILL_K"]                      # bincount calls per fitness evaluation: batches x ranks (:84-89)
+    assert len(seen) == per_call * (ITERS + 1)
+    cluster_sizes = []
+    for c in range(ITERS + 1):
+        calls = seen[c * per_call:(c + 1) * per_call]
+        cluster_sizes.append([[sum(calls[b * ns["SPILL_K"] + j][i] for b in range(n_batches)) for i in range(K)] for j in range(ns["SPILL_K"])])
     lines = [ln.split() for ln in buf.getvalue().strip().splitlines()]
     assert len(lines) == ITERS and all(len(ln) == 3 for ln in lines), buf.getvalue()
     golden = {"script": "kmeans.py:73-131 executed unchanged (ast-extracted simulated_annealing)", "seed": SEED, "rows": ROWS, "k": K, "iters": ITERS,
               "batch_size": BATCH, "data": "helpers.clustered_f16(71, 3000, n_clusters=16)",
               "printed": [[float(a), float(b), float(c)] for a, b, c in lines],
+              "cluster_sizes": cluster_sizes,   # [evaluation][rank][cluster], evaluation 0 = the initial centroids, i >= 1 = iteration i's candidate
               "result_head": [float(v) for v in out[0, :8]], "result_norms": [float(v) for v in out.norm(dim=1)]}
     with open(os.path.join(HERE, "kmeans_reference.json"), "w") as f:
         json.dump(golden, f, indent=1)
